@@ -1,0 +1,196 @@
+/*
+ * libqaintensor_cuda -- C ABI of the B200-native contraction / truncation engine
+ * that replaces the arithmetic of Qaintensor.jl's hot path.
+ *
+ * The reference is pure Julia and has no FFI of its own; the seams this ABI cuts
+ * at are the Julia call sites listed beside each entry point (paths relative to
+ * the reference checkout).  INTEGRATION.md shows the `ccall` stubs.
+ *
+ * Conventions
+ *   - column-major dense arrays; ComplexF64 = two interleaved doubles
+ *     (binary-identical to Julia's Complex{Float64} / cuDoubleComplex);
+ *   - tensor / leg / contraction indices crossing the ABI are 1-based where the
+ *     reference's are (labels follow `contract_rep`, src/contract.jl:39-60:
+ *     +k for contraction k, -(i + ncontractions) for open leg i);
+ *   - the caller owns every host buffer; the library owns device memory and the
+ *     opaque handles; nothing is freed across the boundary;
+ *   - every function returns 0 on success, a negative QTN_E* code otherwise;
+ *     qtn_last_error() returns the message of the last failure on this thread
+ *     (the reference's own error strings where one exists, e.g.
+ *     "Error must be positive", src/svd.jl:9);
+ *   - there is NO CPU fallback: compute entry points fail with QTN_ENODEVICE
+ *     when no sm_100 device is usable.  Host-only entry points (ordering,
+ *     planning, cost queries) work without a GPU;
+ *   - not re-entrant: call from one host thread at a time.
+ */
+#ifndef QAINTENSOR_CUDA_H
+#define QAINTENSOR_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QTN_OK 0
+#define QTN_EINVAL (-1)    /* malformed arguments / network            */
+#define QTN_ENODEVICE (-2) /* no usable CUDA device (no CPU fallback)  */
+#define QTN_ECUDA (-3)     /* CUDA runtime / kernel failure            */
+#define QTN_ENOMEM (-4)    /* device arena exhausted                   */
+#define QTN_ENCCL (-5)     /* NCCL unavailable or failed               */
+#define QTN_EDOMAIN (-6)   /* reference error() condition (see message) */
+
+typedef struct qtn_plan qtn_plan;       /* contraction plan (opaque)          */
+typedef struct qtn_mps qtn_mps;         /* device-resident MPS (opaque)       */
+
+/* ---- lifetime / diagnostics ------------------------------------------------ */
+int qtn_version(void);                           /* 10000*major + 100*minor + patch */
+const char* qtn_last_error(void);
+/* Selects the device (cudaSetDevice) and creates the library stream.          */
+int qtn_init(int device);
+int qtn_shutdown(void);
+int qtn_device_count(int* count);
+/* The stream every kernel of this library is launched on (cudaStream_t).      */
+void* qtn_stream(void);
+/* Number of this library's kernels launched since the last reset.             */
+int64_t qtn_launch_count(int reset);
+
+/* ---- contraction order (host, integer-only, bit-exact) ----------------------
+ * Replaces `contraction_order(net)` / `optimize_contraction_order!(net)`
+ * (src/network2graph.jl:429-446, 473-479).  pairs[k] = (t1, l1, t2, l2) of
+ * contraction k (1-based).  perm_out[ncontr] receives the permutation such that
+ * net.contractions = net.contractions[perm].  tw_out (optional) = width of the
+ * tree decomposition of the line graph.                                         */
+int qtn_order_treewidth(int32_t ntensors, int32_t ncontr, const int32_t* pairs,
+                        int32_t* perm_out, int32_t* tw_out);
+/* Treewidth heuristic on a plain graph (src/network2graph.jl:300-337), for the
+ * reference's known-answer tests: edges[2*ne] 1-based.                          */
+int qtn_graph_treewidth(int32_t nv, int32_t ne, const int32_t* edges, int32_t* tw_out,
+                        int32_t* ordering_out /* nv, min-fill order, may be NULL */);
+/* Replaces `contract_order` (src/contract.jl:184-235): exhaustive cost-capped
+ * search.  labels as in qtn_plan_create; legdims[nlabels] = extent of label
+ * abs(l) = 1..nlabels.  seq_out holds up to ncontr labels, *nseq_out its length. */
+int qtn_order_exhaustive(int32_t nt, const int32_t* ranks, const int32_t* const* labels,
+                         int32_t nlabels, const int64_t* legdims, int32_t* seq_out,
+                         int32_t* nseq_out, int64_t* cost_out);
+
+/* ---- contraction plans -------------------------------------------------------
+ * Replaces `TensorOperations.ncon(tensors, indexlist; order)` as called from
+ * src/contract.jl:257, 263.  A plan fixes shapes, labels and order; it can be
+ * executed many times with new tensor data of the same shapes.
+ *   order == NULL  -> ascending positive labels (ncon default).
+ *   slice_labels   -> EXTENSION (no reference counterpart): labels fixed per slice.
+ *   dtype          -> QTN_C128 (ComplexF64) or QTN_C64 (ComplexF32 mode).        */
+#define QTN_C128 0
+#define QTN_C64 1
+int qtn_plan_create(int32_t nt, const int32_t* ranks, const int64_t* const* dims,
+                    const int32_t* const* labels, const int32_t* order, int32_t norder,
+                    const int32_t* slice_labels, int32_t nslice_labels, int32_t dtype,
+                    qtn_plan** plan_out);
+int qtn_plan_destroy(qtn_plan* plan);
+/* Deterministic greedy slice-label choice (rule in DESIGN.md / oracle/plan.py):
+ * slice until the largest tensor has <= 2^max_log2_elems elements and there are
+ * at least min_slices slices.  Host-only.  labels_out capacity = ncontr.         */
+int qtn_choose_slices(int32_t nt, const int32_t* ranks, const int64_t* const* dims,
+                      const int32_t* const* labels, const int32_t* order, int32_t norder,
+                      int32_t max_log2_elems, int64_t min_slices, int32_t* labels_out,
+                      int32_t* nlabels_out);
+/* Plan facts (host-only): info[0]=#pairwise steps, [1]=#slices, [2]=output rank,
+ * [3]=#output elements, [4]=max tensor elements (per slice), [5]=#slice-invariant
+ * steps, [6]=arena bytes, [7]=#kernel launches per slice.
+ * cost[0]=sum 8MNK per slice, cost[1]=sum 16(MK+KN+MN) per slice.               */
+int qtn_plan_info(const qtn_plan* plan, int64_t info[8], double cost[2]);
+int qtn_plan_out_dims(const qtn_plan* plan, int64_t* dims_out /* rank entries */);
+/* Per-step shapes: mnk[3*nsteps], flags[nsteps] (bit0 = slice-invariant).        */
+int qtn_plan_steps(const qtn_plan* plan, int64_t* mnk, int32_t* flags);
+
+/* Copy the nt input tensors host -> device (one staged transfer).               */
+int qtn_plan_upload(qtn_plan* plan, const void* const* host_data);
+/* Run slices [slice_begin, slice_end) on the library stream and ADD their sum to
+ * the device buffer dev_out (#output elements, caller-zeroed, device pointer).
+ * Asynchronous: returns after enqueueing.                                       */
+int qtn_plan_execute(qtn_plan* plan, int64_t slice_begin, int64_t slice_end, void* dev_out);
+/* Host-buffer convenience: upload, run slices, download (sum over the slices).  */
+int qtn_plan_execute_host(qtn_plan* plan, const void* const* host_data, int64_t slice_begin,
+                          int64_t slice_end, void* host_out);
+/* Per-step device timing of one slice (CUDA events, ms[nsteps]); diagnostics.   */
+int qtn_plan_time_steps(qtn_plan* plan, int64_t slice_id, float* ms);
+
+/* One-shot `ncon`: plan + upload + execute + download (src/contract.jl:257, 263). */
+int qtn_contract(int32_t nt, const void* const* host_data, const int32_t* ranks,
+                 const int64_t* const* dims, const int32_t* const* labels,
+                 const int32_t* order, int32_t norder, int32_t dtype, void* host_out,
+                 int32_t* out_rank, int64_t* out_dims /* capacity 64 */);
+
+/* Slice-parallel contraction across ranks: rank r of nranks runs its contiguous
+ * block of slices and the partial results are summed with ONE ncclAllReduce.
+ * EXTENSION.  Requires qtn_nccl_init.  host_out receives the full sum on all ranks. */
+int qtn_nccl_unique_id(void* id_out /* 128 bytes */);
+int qtn_nccl_init(int32_t rank, int32_t nranks, const void* id /* 128 bytes */);
+int qtn_nccl_allreduce_sum_f64(void* dev_buf, int64_t count);
+int qtn_contract_sliced(qtn_plan* plan, const void* const* host_data, int32_t rank,
+                        int32_t nranks, void* host_out);
+
+/* ---- permutedims ---------------------------------------------------------------
+ * Replaces Julia `permutedims(A, perm)` at src/contract.jl:244, src/svd.jl:20-21,
+ * src/switch.jl:29-35.  out axis i = in axis perm[i] (1-based).                  */
+int qtn_permutedims(const void* host_in, int32_t rank, const int64_t* dims,
+                    const int32_t* perm, int32_t dtype, void* host_out);
+int qtn_permutedims_device(const void* dev_in, int32_t rank, const int64_t* dims,
+                           const int32_t* perm, int32_t dtype, void* dev_out);
+
+/* ---- dense ZGEMM (device pointers, column-major) --------------------------------
+ * C[m x n] = op(A) * op(B); op = 'N', 'T' or 'C' (adjoint).  Replaces the
+ * `*` chains at src/svd.jl:35 and `diagm(S)*adjoint(V)` products.                */
+int qtn_zgemm_device(char opa, char opb, int64_t m, int64_t n, int64_t k, const void* dev_a,
+                     int64_t lda, const void* dev_b, int64_t ldb, void* dev_c, int64_t ldc);
+
+/* ---- truncated SVD ---------------------------------------------------------------
+ * Replaces `LinearAlgebra.svd` + the tail-norm rule of src/svd.jl:29-33
+ * (k = n - r* + 1, r* = first r with sqrt(S[n]^2+...+S[n-r+1]^2) > er, strict),
+ * then EXTENSION k <- min(k, maxdim) (maxdim <= 0: no cap).  A is m x n column-major
+ * (host).  U: m x min(m,n), S: min(m,n), Vh: min(m,n) x n are fully written; the
+ * first *k_out columns / values / rows are the kept ones.  er < 0: all values
+ * kept (plain `svd`).  If no tail exceeds er, *k_out = 0 (the reference throws).  */
+int qtn_svd_trunc(const void* host_a, int64_t m, int64_t n, double er, int64_t maxdim,
+                  void* host_u, double* host_s, void* host_vh, int64_t* k_out);
+/* Batch of independent problems (ragged shapes allowed).                          */
+int qtn_svd_trunc_batched(int32_t batch, const void* const* host_a, const int64_t* m,
+                          const int64_t* n, double er, int64_t maxdim, void* const* host_u,
+                          double* const* host_s, void* const* host_vh, int64_t* k_out);
+/* Device-resident variant: sweeps / final off-diagonal measure reported.          */
+int qtn_svd_trunc_device(void* dev_a /* overwritten */, int64_t m, int64_t n, double er,
+                         int64_t maxdim, void* dev_u, double* dev_s, void* dev_vh,
+                         int64_t* k_out, int32_t* sweeps_out);
+
+/* ---- contract_svd ------------------------------------------------------------------
+ * Replaces `contract_svd(T1, T2, (i1, i2); er)` (src/svd.jl:7-38) as a whole.
+ * out has dims (T1 without leg i1..., T2 without leg i2...).  Errors:
+ * "Error must be positive", "Dimensions of contraction legs do not match".        */
+int qtn_contract_svd(const void* host_t1, int32_t rank1, const int64_t* dims1, int32_t i1,
+                     const void* host_t2, int32_t rank2, const int64_t* dims2, int32_t i2,
+                     double er, void* host_out);
+
+/* ---- device-resident MPS (EXTENSION built from src/switch.jl:18-56) ----------------
+ * Site tensors have layout (lbond, 2, rbond) (src/mps.jl:99-110).                  */
+int qtn_mps_create(int32_t nsites, const void* const* host_sites, const int64_t* lbond,
+                   const int64_t* rbond, int64_t maxdim_capacity, qtn_mps** mps_out);
+int qtn_mps_destroy(qtn_mps* mps);
+int qtn_mps_bonds(const qtn_mps* mps, int64_t* lbond, int64_t* rbond);
+int qtn_mps_download(const qtn_mps* mps, void* const* host_sites);
+/* theta = T_i * T_{i+1}; gate (4x4 column-major, index = p_i + 2 p_{i+1}) on the
+ * physical legs; SVD; truncate (er, maxdim); T_i <- U, T_{i+1} <- S*V'.
+ * site is 1-based.  disc_out = 2-norm of the discarded singular values.           */
+int qtn_mps_apply_gate2(qtn_mps* mps, int32_t site, const void* host_gate, double er,
+                        int64_t maxdim, double* disc_out);
+/* All gates of one brickwork half-layer (disjoint bonds) through the batched SVD.  */
+int qtn_mps_apply_layer(qtn_mps* mps, int32_t ngates, const int32_t* sites,
+                        const void* host_gates /* ngates 4x4 */, double er, int64_t maxdim,
+                        double* disc_out /* ngates */);
+/* <a|b> by transfer-matrix contraction; result (re, im).                           */
+int qtn_mps_overlap(const qtn_mps* a, const qtn_mps* b, double out[2]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QAINTENSOR_CUDA_H */

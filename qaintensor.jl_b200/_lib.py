@@ -1,0 +1,133 @@
+"""ctypes binding of ``libqaintensor_cuda.so`` (C ABI in ``include/qaintensor_cuda.h``).
+
+There is no CPU fallback: importing works without a GPU (host-only entry points such
+as ordering and planning are usable), but every compute entry point raises
+``QtnError`` when the library or an sm_100 device is missing.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libqaintensor_cuda.so")
+
+QTN_C128 = 0
+QTN_ENODEVICE = -2
+QTN_EDOMAIN = -6
+
+
+class QtnError(RuntimeError):
+    """Raised for every non-zero return of the C ABI; ``.code`` holds the QTN_E* value."""
+
+    def __init__(self, code, msg):
+        super().__init__(msg)
+        self.code = code
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise QtnError(QTN_ENODEVICE, "libqaintensor_cuda.so not built at %s -- run __graft_entry__.build(); "
+                       "there is no CPU fallback" % LIB_PATH)
+    return C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+
+
+lib = _load()
+
+i32, i64, f64, vp = C.c_int32, C.c_int64, C.c_double, C.c_void_p
+P = C.POINTER
+lib.qtn_last_error.restype = C.c_char_p
+lib.qtn_stream.restype = vp
+lib.qtn_launch_count.restype = i64
+lib.qtn_launch_count.argtypes = [C.c_int]
+
+_SIGS = {
+    "qtn_init": [C.c_int],
+    "qtn_device_count": [P(C.c_int)],
+    "qtn_order_treewidth": [i32, i32, P(i32), P(i32), P(i32)],
+    "qtn_graph_treewidth": [i32, i32, P(i32), P(i32), P(i32)],
+    "qtn_order_exhaustive": [i32, P(i32), P(P(i32)), i32, P(i64), P(i32), P(i32), P(i64)],
+    "qtn_plan_create": [i32, P(i32), P(P(i64)), P(P(i32)), P(i32), i32, P(i32), i32, i32, P(vp)],
+    "qtn_plan_destroy": [vp],
+    "qtn_choose_slices": [i32, P(i32), P(P(i64)), P(P(i32)), P(i32), i32, i32, i64, P(i32), P(i32)],
+    "qtn_plan_info": [vp, P(i64), P(f64)],
+    "qtn_plan_out_dims": [vp, P(i64)],
+    "qtn_plan_steps": [vp, P(i64), P(i32)],
+    "qtn_plan_upload": [vp, P(vp)],
+    "qtn_plan_execute": [vp, i64, i64, vp],
+    "qtn_plan_execute_host": [vp, P(vp), i64, i64, vp],
+    "qtn_plan_time_steps": [vp, i64, P(C.c_float)],
+    "qtn_contract": [i32, P(vp), P(i32), P(P(i64)), P(P(i32)), P(i32), i32, i32, vp, P(i32), P(i64)],
+    "qtn_nccl_unique_id": [vp],
+    "qtn_nccl_init": [i32, i32, vp],
+    "qtn_nccl_allreduce_sum_f64": [vp, i64],
+    "qtn_contract_sliced": [vp, P(vp), i32, i32, vp],
+    "qtn_permutedims": [vp, i32, P(i64), P(i32), i32, vp],
+    "qtn_permutedims_device": [vp, i32, P(i64), P(i32), i32, vp],
+    "qtn_zgemm_device": [C.c_char, C.c_char, i64, i64, i64, vp, i64, vp, i64, vp, i64],
+    "qtn_svd_trunc": [vp, i64, i64, f64, i64, vp, P(f64), vp, P(i64)],
+    "qtn_svd_trunc_batched": [i32, P(vp), P(i64), P(i64), f64, i64, P(vp), P(vp), P(vp), P(i64)],
+    "qtn_svd_trunc_device": [vp, i64, i64, f64, i64, vp, vp, vp, P(i64), P(i32)],
+    "qtn_contract_svd": [vp, i32, P(i64), i32, vp, i32, P(i64), i32, f64, vp],
+    "qtn_mps_create": [i32, P(vp), P(i64), P(i64), i64, P(vp)],
+    "qtn_mps_destroy": [vp],
+    "qtn_mps_bonds": [vp, P(i64), P(i64)],
+    "qtn_mps_download": [vp, P(vp)],
+    "qtn_mps_apply_gate2": [vp, i32, vp, f64, i64, P(f64)],
+    "qtn_mps_apply_layer": [vp, i32, P(i32), vp, f64, i64, P(f64)],
+    "qtn_mps_overlap": [vp, vp, P(f64)],
+}
+for _name, _args in _SIGS.items():
+    _f = getattr(lib, _name)
+    _f.argtypes = _args
+    _f.restype = C.c_int
+
+
+def check(rc):
+    if rc != 0:
+        raise QtnError(rc, lib.qtn_last_error().decode("utf-8", "replace"))
+
+
+def device_count():
+    n = C.c_int(0)
+    lib.qtn_device_count(C.byref(n))
+    return n.value
+
+
+def require_device():
+    """Fail loudly when the CUDA path cannot run (no fallback exists)."""
+    check(lib.qtn_init(int(os.environ.get("LOCAL_RANK", "0")) if device_count() > 1 else 0))
+
+
+def launch_count(reset=False):
+    return int(lib.qtn_launch_count(1 if reset else 0))
+
+
+def as_c128(a):
+    """Column-major ComplexF64 copy/view of ``a`` (the ABI's memory layout)."""
+    return np.asfortranarray(np.asarray(a, dtype=np.complex128))
+
+
+def arr_i32(v):
+    return (i32 * max(len(v), 1))(*[int(x) for x in v])
+
+
+def arr_i64(v):
+    return (i64 * max(len(v), 1))(*[int(x) for x in v])
+
+
+class NetworkArgs:
+    """Marshals (tensors' ranks, dims, labels) into the ABI's pointer arrays."""
+
+    def __init__(self, shapes, labels):
+        nt = len(shapes)
+        self.nt = nt
+        self.ranks = arr_i32([len(s) for s in shapes])
+        self._dims = [arr_i64(s) for s in shapes]
+        self._labs = [arr_i32(l) for l in labels]
+        self.dims = (P(i64) * max(nt, 1))(*[C.cast(d, P(i64)) for d in self._dims])
+        self.labels = (P(i32) * max(nt, 1))(*[C.cast(l, P(i32)) for l in self._labs])
+
+
+def data_ptrs(arrays):
+    return (vp * max(len(arrays), 1))(*[a.ctypes.data for a in arrays])

@@ -1,0 +1,380 @@
+// Plan executor: device arena, staged upload, per-slice CUDA graph, launches.
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+
+#define QTN_KERNELS_IMPL
+#include "kernels.cuh"
+#include "qtn_internal.h"
+
+namespace qtn {
+
+// ---------------------------------------------------------------------------
+// error text + global device state
+// ---------------------------------------------------------------------------
+static thread_local char g_err[1024] = "";
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+const char* last_error_text() { return g_err; }
+
+static bool g_inited = false;
+static int g_device = -1;
+static cudaStream_t g_stream = nullptr;
+static int64_t g_launches = 0;
+
+#define CUDA_TRY(expr)                                                                          \
+    do {                                                                                        \
+        cudaError_t _e = (expr);                                                                \
+        if (_e != cudaSuccess)                                                                  \
+            return fail(QTN_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+cudaStream_t stream() { return g_stream; }
+int64_t launch_count(int reset) {
+    int64_t v = g_launches;
+    if (reset) g_launches = 0;
+    return v;
+}
+void count_launch(int64_t n) { g_launches += n; }
+
+int device_init(int device) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(QTN_ENODEVICE, "no CUDA device available (%s); libqaintensor_cuda has no CPU fallback",
+                    e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= n) return fail(QTN_EINVAL, "qtn_init: device %d out of range (0..%d)", device, n - 1);
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(QTN_ENODEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+    CUDA_TRY(cudaSetDevice(device));
+    if (g_inited && g_device == device) return QTN_OK;
+    if (g_stream) { cudaStreamDestroy(g_stream); g_stream = nullptr; }
+    CUDA_TRY(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
+    g_device = device;
+    g_inited = true;
+    return QTN_OK;
+}
+
+int device_shutdown() {
+    if (g_stream) { cudaStreamSynchronize(g_stream); cudaStreamDestroy(g_stream); g_stream = nullptr; }
+    g_inited = false;
+    g_device = -1;
+    return QTN_OK;
+}
+
+int device_ready() {
+    if (g_inited) { cudaSetDevice(g_device); return QTN_OK; }
+    return device_init(0);
+}
+
+// ---------------------------------------------------------------------------
+// GEMM launch (shared by plans and the dense qtn_zgemm_device entry point)
+// ---------------------------------------------------------------------------
+template <int BM, int BN, int WM, int WN, int BK, int STAGES>
+static int launch_gemm_t(GemmArgs& g, int split_k, cudaStream_t st) {
+    constexpr int NT = (BM / WM) * (BN / WN) * 32;
+    constexpr size_t smem = (size_t)STAGES * BK * (BM + 2 + BN + 2) * 16 + (BM + BN) * 8;
+    static bool attr_done = false;
+    auto kern = zgemm_gather_kernel<BM, BN, WM, WN, BK, STAGES>;
+    if (!attr_done) {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done = true;
+    }
+    int64_t tm = (g.M + BM - 1) / BM, tn = (g.N + BN - 1) / BN;
+    if (tm * tn > 2147483647LL) return fail(QTN_EINVAL, "GEMM grid too large");
+    g.tiles_m = (int)tm;
+    int64_t kps = (g.K + split_k - 1) / split_k;
+    kps = (kps + BK - 1) / BK * BK;
+    g.k_per_split = kps;
+    int sy = (int)((g.K + kps - 1) / kps);
+    dim3 grid((unsigned)(tm * tn), (unsigned)sy, 1);
+    kern<<<grid, NT, smem, st>>>(g);
+    CUDA_TRY(cudaGetLastError());
+    count_launch(1);
+    return QTN_OK;
+}
+
+int launch_gemm(GemmArgs& g, int variant, int split_k, cudaStream_t st) {
+    if (g.M <= 0 || g.N <= 0) return QTN_OK;
+    if (variant == 2) {
+        int blocks = (int)std::min<int64_t>(2 * 148, (g.K + 255) / 256);
+        if (blocks < 1) blocks = 1;
+        zdot_gather_kernel<<<blocks, 256, 0, st>>>(g);
+        CUDA_TRY(cudaGetLastError());
+        count_launch(1);
+        return QTN_OK;
+    }
+    if (variant == 1) return launch_gemm_t<128, 8, 32, 8, 16, 3>(g, split_k, st);
+    return launch_gemm_t<64, 64, 32, 32, 16, 3>(g, split_k, st);
+}
+
+// ---------------------------------------------------------------------------
+// per-plan device state
+// ---------------------------------------------------------------------------
+struct DevPlan {
+    double2* inputs = nullptr;
+    double2* arena = nullptr;
+    i64* tables = nullptr;
+    i64* sid = nullptr;
+    i64* soff = nullptr;
+    i64* slice_dims = nullptr;
+    int* first = nullptr;
+    int* pos = nullptr;
+    i64* stride = nullptr;
+    void* h_stage = nullptr;
+    size_t h_stage_bytes = 0;
+    cudaGraphExec_t graph = nullptr;
+    void* graph_out = nullptr;
+    bool uploaded = false;
+    bool invariants_done = false;
+    int graph_launches = 0;
+};
+
+static TabArg tab_arg(const DevPlan* d, const OffTable& t) {
+    TabArg a;
+    a.lo = d->tables + t.lo;
+    a.hi = d->tables + t.hi;
+    a.L = t.L;
+    a.shift = -1;
+    if ((t.L & (t.L - 1)) == 0) { int s = 0; while (((i64)1 << s) < t.L) ++s; a.shift = s; }
+    return a;
+}
+
+int plan_device_init(Plan* p) {
+    int rc = device_ready();
+    if (rc) return rc;
+    if (p->dev) return QTN_OK;
+    rc = materialize_tables(p);
+    if (rc) return rc;
+    DevPlan* d = new DevPlan();
+    p->dev = d;
+    auto guard_fail = [&](int code) { plan_device_free(p); return code; };
+    cudaError_t e;
+#define ALLOC(ptr, bytes)                                                                     \
+    if ((e = cudaMalloc((void**)&(ptr), std::max<size_t>((size_t)(bytes), 256))) != cudaSuccess) \
+        return guard_fail(fail(e == cudaErrorMemoryAllocation ? QTN_ENOMEM : QTN_ECUDA,          \
+                               "cudaMalloc(%zu bytes) failed: %s", (size_t)(bytes), cudaGetErrorString(e)));
+    ALLOC(d->inputs, (size_t)p->input_elems * 16);
+    ALLOC(d->arena, (size_t)p->arena_elems * 16);
+    ALLOC(d->tables, p->tables.size() * 8);
+    ALLOC(d->sid, 8);
+    ALLOC(d->soff, (size_t)p->nt * 8);
+    ALLOC(d->slice_dims, p->slice_dims.size() * 8 + 8);
+    std::vector<int> first(p->nt + 1, 0), pos;
+    std::vector<i64> stride;
+    for (int t = 0; t < p->nt; ++t) {
+        for (auto& ps : p->nodes[t].slice_strides) { pos.push_back(ps.first); stride.push_back(ps.second); }
+        first[t + 1] = (int)pos.size();
+    }
+    ALLOC(d->first, first.size() * 4);
+    ALLOC(d->pos, pos.size() * 4 + 4);
+    ALLOC(d->stride, stride.size() * 8 + 8);
+#undef ALLOC
+    CUDA_TRY(cudaMemcpy(d->tables, p->tables.data(), p->tables.size() * 8, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(d->first, first.data(), first.size() * 4, cudaMemcpyHostToDevice));
+    if (!pos.empty()) {
+        CUDA_TRY(cudaMemcpy(d->pos, pos.data(), pos.size() * 4, cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(d->stride, stride.data(), stride.size() * 8, cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(d->slice_dims, p->slice_dims.data(), p->slice_dims.size() * 8, cudaMemcpyHostToDevice));
+    }
+    CUDA_TRY(cudaMemset(d->soff, 0, (size_t)p->nt * 8));
+    d->h_stage_bytes = (size_t)p->input_elems * 16;
+    CUDA_TRY(cudaMallocHost(&d->h_stage, std::max<size_t>(d->h_stage_bytes, 256)));
+    return QTN_OK;
+}
+
+void plan_device_free(Plan* p) {
+    DevPlan* d = (DevPlan*)p->dev;
+    if (!d) return;
+    if (g_stream) cudaStreamSynchronize(g_stream);
+    if (d->graph) cudaGraphExecDestroy(d->graph);
+    cudaFree(d->inputs); cudaFree(d->arena); cudaFree(d->tables); cudaFree(d->sid); cudaFree(d->soff);
+    cudaFree(d->slice_dims); cudaFree(d->first); cudaFree(d->pos); cudaFree(d->stride);
+    if (d->h_stage) cudaFreeHost(d->h_stage);
+    delete d;
+    p->dev = nullptr;
+}
+
+int plan_upload(Plan* p, const void* const* host_data) {
+    int rc = plan_device_init(p);
+    if (rc) return rc;
+    DevPlan* d = (DevPlan*)p->dev;
+    CUDA_TRY(cudaStreamSynchronize(g_stream));  // staging buffer may still be in flight
+    for (int t = 0; t < p->nt; ++t) {
+        const Node& n = p->nodes[t];
+        int64_t full = n.numel;
+        for (auto& ps : n.slice_strides) full *= p->slice_dims[ps.first];
+        if (!host_data[t] && full > 0) return fail(QTN_EINVAL, "tensor %d: null data pointer", t + 1);
+        memcpy((char*)d->h_stage + (size_t)n.offset * 16, host_data[t], (size_t)full * 16);
+    }
+    CUDA_TRY(cudaMemcpyAsync(d->inputs, d->h_stage, d->h_stage_bytes, cudaMemcpyHostToDevice, g_stream));
+    d->uploaded = true;
+    d->invariants_done = false;
+    return QTN_OK;
+}
+
+static const double2* node_ptr(const Plan* p, const DevPlan* d, int n, const i64** soff, void* dev_out) {
+    const Node& nd = p->nodes[n];
+    *soff = nullptr;
+    if (nd.is_input) {
+        if (!nd.slice_strides.empty()) *soff = d->soff + nd.input_index;
+        return d->inputs + nd.offset;
+    }
+    if (n == p->final_node) return (const double2*)dev_out;
+    return d->arena + nd.offset;
+}
+
+static int run_step(Plan* p, DevPlan* d, const Step& s, void* dev_out, cudaStream_t st) {
+    const i64 *sa = nullptr, *sb = nullptr, *sc = nullptr;
+    if (s.kind == STEP_GEMM) {
+        GemmArgs g;
+        memset(&g, 0, sizeof(g));
+        g.A = node_ptr(p, d, s.a, &sa, dev_out);
+        g.B = node_ptr(p, d, s.b, &sb, dev_out);
+        g.C = const_cast<double2*>(node_ptr(p, d, s.out, &sc, dev_out));
+        g.a_soff = sa;
+        g.b_soff = sb;
+        g.a_row = tab_arg(d, s.a_row);
+        g.a_k = tab_arg(d, s.a_k);
+        g.b_k = tab_arg(d, s.b_k);
+        g.b_col = tab_arg(d, s.b_col);
+        g.c_dense = s.c_dense ? 1 : 0;
+        if (!s.c_dense) { g.c_row = tab_arg(d, s.c_row); g.c_col = tab_arg(d, s.c_col); }
+        g.M = s.M; g.N = s.N; g.K = s.K;
+        int variant = s.variant, split = s.split_k;
+        bool atomic = (variant == 2) || split > 1;
+        if (s.final_step) g.mode = atomic ? 2 : 1;
+        else {
+            g.mode = atomic ? 2 : 0;
+            if (atomic) CUDA_TRY(cudaMemsetAsync(g.C, 0, (size_t)s.M * s.N * 16, st));
+        }
+        return launch_gemm(g, variant, split, st);
+    }
+    UnaryArgs u;
+    memset(&u, 0, sizeof(u));
+    u.A = node_ptr(p, d, s.a, &sa, dev_out);
+    u.C = const_cast<double2*>(node_ptr(p, d, s.out, &sc, dev_out));
+    u.a_soff = sa;
+    u.a_row = tab_arg(d, s.a_row);
+    u.M = s.M;
+    u.K = s.K;
+    int blocks = (int)std::min<int64_t>((s.M + 255) / 256, 148 * 8);
+    if (blocks < 1) blocks = 1;
+    if (s.kind == STEP_PERMUTE) {
+        u.c_row = tab_arg(d, s.c_row);
+        u.mode = 1;
+        permute_gather_kernel<<<blocks, 256, 0, st>>>(u);
+    } else {
+        u.a_k = tab_arg(d, s.a_k);
+        trace_gather_kernel<<<blocks, 256, 0, st>>>(u);
+    }
+    CUDA_TRY(cudaGetLastError());
+    count_launch(1);
+    return QTN_OK;
+}
+
+__global__ void set_i64_kernel(i64* p, i64 v) { *p = v; }
+
+static int enqueue_slice(Plan* p, DevPlan* d, void* dev_out, cudaStream_t st) {
+    if (p->nslices > 1) {
+        slice_offsets_kernel<<<1, 256, 0, st>>>(d->sid, (int)p->slice_dims.size(), d->slice_dims, p->nt, d->first,
+                                                d->pos, d->stride, d->soff);
+        CUDA_TRY(cudaGetLastError());
+        count_launch(1);
+    }
+    for (const Step& s : p->steps) {
+        if (s.invariant) continue;
+        int rc = run_step(p, d, s, dev_out, st);
+        if (rc) return rc;
+    }
+    return QTN_OK;
+}
+
+int plan_execute(Plan* p, int64_t s0, int64_t s1, void* dev_out) {
+    DevPlan* d = (DevPlan*)p->dev;
+    if (!d || !d->uploaded) return fail(QTN_EINVAL, "qtn_plan_execute: call qtn_plan_upload first");
+    if (s0 < 0 || s1 > p->nslices || s0 > s1) return fail(QTN_EINVAL, "slice range [%lld, %lld) outside [0, %lld)", (long long)s0, (long long)s1, (long long)p->nslices);
+    if (!dev_out) return fail(QTN_EINVAL, "qtn_plan_execute: null output");
+    cudaSetDevice(g_device);
+    if (s0 == s1) return QTN_OK;
+    if (!d->invariants_done) {
+        for (const Step& s : p->steps)
+            if (s.invariant) { int rc = run_step(p, d, s, dev_out, g_stream); if (rc) return rc; }
+        d->invariants_done = true;
+    }
+    if (p->nslices > 1) {
+        set_i64_kernel<<<1, 1, 0, g_stream>>>(d->sid, s0);
+        CUDA_TRY(cudaGetLastError());
+        count_launch(1);
+    }
+    if (!d->graph || d->graph_out != dev_out) {
+        if (d->graph) { cudaGraphExecDestroy(d->graph); d->graph = nullptr; }
+        // make sure every kernel's max-smem attribute is set outside capture: warm-run slice s0 directly
+        int64_t before = launch_count(0);
+        int rc = enqueue_slice(p, d, dev_out, g_stream);
+        if (rc) return rc;
+        d->graph_launches = (int)(launch_count(0) - before);
+        ++s0;
+        if (s0 == s1) return QTN_OK;
+        cudaGraph_t graph;
+        CUDA_TRY(cudaStreamBeginCapture(g_stream, cudaStreamCaptureModeThreadLocal));
+        int64_t keep = launch_count(0);
+        rc = enqueue_slice(p, d, dev_out, g_stream);
+        cudaError_t e = cudaStreamEndCapture(g_stream, &graph);
+        launch_count(1);
+        count_launch(keep);
+        if (rc) return rc;
+        if (e != cudaSuccess) return fail(QTN_ECUDA, "graph capture failed: %s", cudaGetErrorString(e));
+        e = cudaGraphInstantiate(&d->graph, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) return fail(QTN_ECUDA, "graph instantiate failed: %s", cudaGetErrorString(e));
+        d->graph_out = dev_out;
+    }
+    for (int64_t s = s0; s < s1; ++s) CUDA_TRY(cudaGraphLaunch(d->graph, g_stream));
+    count_launch((s1 - s0) * d->graph_launches);
+    return QTN_OK;
+}
+
+int plan_time_steps(Plan* p, int64_t sid, float* ms) {
+    DevPlan* d = (DevPlan*)p->dev;
+    if (!d || !d->uploaded) return fail(QTN_EINVAL, "qtn_plan_time_steps: call qtn_plan_upload first");
+    cudaSetDevice(g_device);
+    double2* scratch = nullptr;
+    CUDA_TRY(cudaMalloc((void**)&scratch, std::max<size_t>((size_t)p->out_numel * 16, 256)));
+    CUDA_TRY(cudaMemsetAsync(scratch, 0, (size_t)p->out_numel * 16, g_stream));
+    if (p->nslices > 1) {
+        set_i64_kernel<<<1, 1, 0, g_stream>>>(d->sid, sid);
+        slice_offsets_kernel<<<1, 256, 0, g_stream>>>(d->sid, (int)p->slice_dims.size(), d->slice_dims, p->nt, d->first,
+                                                      d->pos, d->stride, d->soff);
+    }
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    int rc = QTN_OK;
+    for (size_t i = 0; i < p->steps.size() && !rc; ++i) {
+        cudaEventRecord(e0, g_stream);
+        rc = run_step(p, d, p->steps[i], scratch, g_stream);
+        cudaEventRecord(e1, g_stream);
+        cudaEventSynchronize(e1);
+        cudaEventElapsedTime(&ms[i], e0, e1);
+    }
+    d->invariants_done = true;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaStreamSynchronize(g_stream);
+    cudaFree(scratch);
+    return rc;
+}
+
+}  // namespace qtn

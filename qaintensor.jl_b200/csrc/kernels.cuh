@@ -1,0 +1,307 @@
+// Device kernels of the contraction path (sm_100a).
+//
+//  zgemm_gather_kernel   K2: ComplexF64 GEMM on the FP64 tensor pipe
+//                        (mma.sync.m8n8k4.f64 -> SASS DMMA.8x8x4; tcgen05 has no
+//                        f64 kind).  Operands are gathered straight from the
+//                        tensors' native layouts through additive offset tables
+//                        (row offset + k offset), staged to shared memory with
+//                        16-byte cp.async in a multi-stage ring, so the TTGT
+//                        permutes of the reference (TensorOperations.ncon,
+//                        src/contract.jl:257, 263) never touch HBM.
+//  zdot_gather_kernel    tiny-M*N / huge-K steps (the closing dot products).
+//  permute_gather_kernel / trace_gather_kernel   unary steps.
+//  slice_offsets_kernel  per-slice base offsets of the sliced input tensors.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace qtn {
+
+typedef long long i64;
+
+struct TabArg {
+    const i64* lo;
+    const i64* hi;
+    i64 L;
+    int shift;  // log2(L) if L is a power of two, else -1
+};
+
+// lo == nullptr: linear mode, offset = i * L (dense matrices need no table).
+__device__ __forceinline__ i64 tab_off(const TabArg& t, i64 i) {
+    if (t.lo == nullptr) return i * t.L;
+    if (t.shift >= 0) return __ldg(t.lo + (i & (t.L - 1))) + __ldg(t.hi + (i >> t.shift));
+    i64 q = i / t.L;
+    return __ldg(t.lo + (i - q * t.L)) + __ldg(t.hi + q);
+}
+
+struct GemmArgs {
+    const double2* A;
+    const double2* B;
+    double2* C;
+    const i64* a_soff;  // per-slice base offset (elements) or nullptr
+    const i64* b_soff;
+    TabArg a_row, a_k, b_k, b_col, c_row, c_col;
+    i64 M, N, K;
+    i64 k_per_split;
+    int tiles_m;
+    int c_dense;
+    int mode;  // 0 store, 1 add (single writer), 2 atomic add
+    int conj_a, conj_b;  // conjugate the operand on the way into the tensor pipe
+};
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool valid) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    int sz = valid ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gsrc), "r"(sz));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ void store_c(double2* p, double re, double im, int mode) {
+    if (mode == 0) {
+        *p = make_double2(re, im);
+    } else if (mode == 1) {
+        double2 o = *p;
+        *p = make_double2(o.x + re, o.y + im);
+    } else {
+        atomicAdd(&p->x, re);
+        atomicAdd(&p->y, im);
+    }
+}
+
+struct UnaryArgs {
+    const double2* A;
+    double2* C;
+    const i64* a_soff;
+    TabArg a_row, a_k, c_row;
+    i64 M, K;
+    int mode;
+};
+
+#ifdef QTN_KERNELS_IMPL
+// CTA tile BM x BN complex, warp tile WM x WN, K chunk BK, STAGES-deep cp.async ring.
+template <int BM, int BN, int WM, int WN, int BK, int STAGES>
+__global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32)
+zgemm_gather_kernel(const __grid_constant__ GemmArgs g) {
+    constexpr int WARPS_M = BM / WM;
+    constexpr int NT = (BM / WM) * (BN / WN) * 32;
+    constexpr int PA = BM + 2, PB = BN + 2;  // smem pitch (complex elements), +32 B kills LDS.128 conflicts
+    constexpr int MI = WM / 8, NI = WN / 8;
+    constexpr int TPK = NT / BK;  // threads cooperating on one k-row of a stage
+    static_assert(NT % BK == 0 && BM % TPK == 0, "tile/thread mismatch");
+    constexpr int A_PER = BM / TPK;
+    constexpr int B_PER = (BN + TPK - 1) / TPK;
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double2* sA = reinterpret_cast<double2*>(smem_raw);  // [STAGES][BK][PA]
+    double2* sB = sA + STAGES * BK * PA;                 // [STAGES][BK][PB]
+    i64* sRow = reinterpret_cast<i64*>(sB + STAGES * BK * PB);  // [BM]
+    i64* sCol = sRow + BM;                                       // [BN]
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp % WARPS_M, wn = warp / WARPS_M;
+    const i64 tile = blockIdx.x;
+    const i64 m0 = (tile % g.tiles_m) * BM, n0 = (tile / g.tiles_m) * BN;
+    const i64 kb = (i64)blockIdx.y * g.k_per_split;
+    const i64 ke = min(g.K, kb + g.k_per_split);
+
+    const double2* A = g.A + (g.a_soff ? *g.a_soff : 0);
+    const double2* B = g.B + (g.b_soff ? *g.b_soff : 0);
+
+    for (int i = tid; i < BM; i += NT) sRow[i] = (m0 + i < g.M) ? tab_off(g.a_row, m0 + i) : -1;
+    for (int i = tid; i < BN; i += NT) sCol[i] = (n0 + i < g.N) ? tab_off(g.b_col, n0 + i) : -1;
+    __syncthreads();
+
+    const int lk = tid / TPK, lr = tid % TPK;
+    auto load_stage = [&](int stage, i64 k0) {
+        const i64 k = k0 + lk;
+        const bool kv = k < ke;
+        const i64 ka = kv ? tab_off(g.a_k, k) : 0;
+        const i64 kbo = kv ? tab_off(g.b_k, k) : 0;
+        double2* da = sA + (stage * BK + lk) * PA;
+        double2* db = sB + (stage * BK + lk) * PB;
+#pragma unroll
+        for (int i = 0; i < A_PER; ++i) {
+            const int m = lr + i * TPK;
+            const i64 ro = sRow[m];
+            const bool v = kv && ro >= 0;
+            cp_async16(da + m, v ? (A + ro + ka) : A, v);
+        }
+#pragma unroll
+        for (int i = 0; i < B_PER; ++i) {
+            const int n = lr + i * TPK;
+            if (n < BN) {
+                const i64 co = sCol[n];
+                const bool v = kv && co >= 0;
+                cp_async16(db + n, v ? (B + co + kbo) : B, v);
+            }
+        }
+    };
+
+    double cr[MI][NI][2], ci[MI][NI][2];
+#pragma unroll
+    for (int i = 0; i < MI; ++i)
+#pragma unroll
+        for (int j = 0; j < NI; ++j) cr[i][j][0] = cr[i][j][1] = ci[i][j][0] = ci[i][j][1] = 0.0;
+
+    const int nk = (int)((ke - kb + BK - 1) / BK);
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; ++s) {
+        if (s < nk) load_stage(s, kb + (i64)s * BK);
+        cp_async_commit();
+    }
+    for (int it = 0; it < nk; ++it) {
+        cp_async_wait<STAGES - 2>();
+        __syncthreads();
+        {
+            const int nx = it + STAGES - 1;
+            if (nx < nk) load_stage(nx % STAGES, kb + (i64)nx * BK);
+            cp_async_commit();
+        }
+        const double2* a_s = sA + (it % STAGES) * BK * PA + wm * WM + (lane >> 2);
+        const double2* b_s = sB + (it % STAGES) * BK * PB + wn * WN + (lane >> 2);
+#pragma unroll
+        for (int k4 = 0; k4 < BK / 4; ++k4) {
+            const int kr = k4 * 4 + (lane & 3);
+            double2 af[MI], bf[NI];
+#pragma unroll
+            for (int i = 0; i < MI; ++i) {
+                af[i] = a_s[kr * PA + i * 8];
+                if (g.conj_a) af[i].y = -af[i].y;
+            }
+#pragma unroll
+            for (int j = 0; j < NI; ++j) {
+                bf[j] = b_s[kr * PB + j * 8];
+                if (g.conj_b) bf[j].y = -bf[j].y;
+            }
+#pragma unroll
+            for (int i = 0; i < MI; ++i)
+#pragma unroll
+                for (int j = 0; j < NI; ++j) {
+                    dmma884(cr[i][j][0], cr[i][j][1], af[i].x, bf[j].x);
+                    dmma884(cr[i][j][0], cr[i][j][1], -af[i].y, bf[j].y);
+                    dmma884(ci[i][j][0], ci[i][j][1], af[i].x, bf[j].y);
+                    dmma884(ci[i][j][0], ci[i][j][1], af[i].y, bf[j].x);
+                }
+        }
+    }
+    cp_async_wait<0>();
+
+    // epilogue: scatter the accumulators through the C offset tables
+    i64 crow[MI];
+#pragma unroll
+    for (int i = 0; i < MI; ++i) {
+        const i64 r = m0 + wm * WM + i * 8 + (lane >> 2);
+        crow[i] = (r < g.M) ? (g.c_dense ? r : tab_off(g.c_row, r)) : -1;
+    }
+#pragma unroll
+    for (int j = 0; j < NI; ++j)
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const i64 c = n0 + wn * WN + j * 8 + 2 * (lane & 3) + q;
+            if (c >= g.N) continue;
+            const i64 co = g.c_dense ? c * g.M : tab_off(g.c_col, c);
+#pragma unroll
+            for (int i = 0; i < MI; ++i)
+                if (crow[i] >= 0) store_c(g.C + crow[i] + co, cr[i][j][q], ci[i][j][q], g.mode);
+        }
+}
+
+// C[m, n] += sum_k A[m, k] B[k, n] for M*N <= 16 and huge K (the closing dot products):
+// every thread strides over k, block-reduces, one atomic per (m, n) per CTA.  C must
+// be pre-zeroed (or hold the running sum when accumulating).
+__global__ void __launch_bounds__(256) zdot_gather_kernel(const __grid_constant__ GemmArgs g) {
+    const double2* A = g.A + (g.a_soff ? *g.a_soff : 0);
+    const double2* B = g.B + (g.b_soff ? *g.b_soff : 0);
+    const int M = (int)g.M, N = (int)g.N;
+    __shared__ double red[8][2];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int e = 0; e < M * N; ++e) {
+        const int m = e % M, n = e / M;
+        const i64 ro = tab_off(g.a_row, m), co = tab_off(g.b_col, n);
+        double r0 = 0, i0 = 0, r1 = 0, i1 = 0;
+        const i64 stride = (i64)gridDim.x * blockDim.x;
+        i64 k = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+        for (; k + stride < g.K; k += 2 * stride) {
+            const double2 a0 = __ldg(A + ro + tab_off(g.a_k, k)), b0 = __ldg(B + co + tab_off(g.b_k, k));
+            const double2 a1 = __ldg(A + ro + tab_off(g.a_k, k + stride)), b1 = __ldg(B + co + tab_off(g.b_k, k + stride));
+            r0 += a0.x * b0.x - a0.y * b0.y;
+            i0 += a0.x * b0.y + a0.y * b0.x;
+            r1 += a1.x * b1.x - a1.y * b1.y;
+            i1 += a1.x * b1.y + a1.y * b1.x;
+        }
+        if (k < g.K) {
+            const double2 a0 = __ldg(A + ro + tab_off(g.a_k, k)), b0 = __ldg(B + co + tab_off(g.b_k, k));
+            r0 += a0.x * b0.x - a0.y * b0.y;
+            i0 += a0.x * b0.y + a0.y * b0.x;
+        }
+        double r = r0 + r1, i = i0 + i1;
+        for (int o = 16; o > 0; o >>= 1) {
+            r += __shfl_xor_sync(0xffffffffu, r, o);
+            i += __shfl_xor_sync(0xffffffffu, i, o);
+        }
+        __syncthreads();
+        if (lane == 0) { red[warp][0] = r; red[warp][1] = i; }
+        __syncthreads();
+        if (threadIdx.x < 2) {
+            double s = 0;
+            for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[w][threadIdx.x];
+            const i64 off = g.c_dense ? (m + (i64)n * g.M) : (tab_off(g.c_row, m) + tab_off(g.c_col, n));
+            atomicAdd(reinterpret_cast<double*>(g.C + off) + threadIdx.x, s);
+        }
+    }
+}
+
+
+// out[c_row(i)] (+)= in[a_row(i)]; i enumerates the OUTPUT layout (coalesced writes).
+__global__ void __launch_bounds__(256) permute_gather_kernel(const __grid_constant__ UnaryArgs g) {
+    const double2* A = g.A + (g.a_soff ? *g.a_soff : 0);
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < g.M; i += (i64)gridDim.x * blockDim.x) {
+        const double2 v = __ldg(A + tab_off(g.a_row, i));
+        store_c(g.C + tab_off(g.c_row, i), v.x, v.y, g.mode);
+    }
+}
+
+// out[i] = sum_t in[a_row(i) + a_k(t)]  (partial trace, src/network2graph.jl:436-445 networks)
+__global__ void __launch_bounds__(256) trace_gather_kernel(const __grid_constant__ UnaryArgs g) {
+    const double2* A = g.A + (g.a_soff ? *g.a_soff : 0);
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < g.M; i += (i64)gridDim.x * blockDim.x) {
+        const i64 ro = tab_off(g.a_row, i);
+        double re = 0, im = 0;
+        for (i64 t = 0; t < g.K; ++t) {
+            const double2 v = __ldg(A + ro + tab_off(g.a_k, t));
+            re += v.x;
+            im += v.y;
+        }
+        g.C[i] = make_double2(re, im);
+    }
+}
+
+// soff[t] = sum over the sliced labels on input t of digit(label) * stride; then sid += 1.
+__global__ void slice_offsets_kernel(i64* sid_ptr, int nlab, const i64* slice_dims, int nt,
+                                     const int* first, const int* pos, const i64* stride, i64* soff) {
+    const i64 sid = *sid_ptr;
+    __syncthreads();
+    for (int t = threadIdx.x; t < nt; t += blockDim.x) {
+        i64 off = 0;
+        for (int e = first[t]; e < first[t + 1]; ++e) {
+            i64 r = sid;
+            for (int q = 0; q < pos[e]; ++q) r /= slice_dims[q];
+            off += (r % slice_dims[pos[e]]) * stride[e];
+        }
+        soff[t] = off;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) *sid_ptr = sid + 1;
+}
+
+#endif  // QTN_KERNELS_IMPL
+
+}  // namespace qtn

@@ -1,0 +1,60 @@
+"""The C-ABI library loads, exports every symbol include/qaintensor_cuda.h declares, and
+has no CPU fallback (compute entry points fail loudly without a device)."""
+import ctypes
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "qaintensor_cuda.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(qtn_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_exported(q):
+    from qaintensor_b200 import _lib
+    syms = declared_symbols()
+    assert len(syms) >= 35
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    missing = [s for s in syms if not hasattr(lib, s)]
+    assert not missing, missing
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (qtn_[a-z0-9_]+)", out))
+    assert exported == set(syms), exported ^ set(syms)
+
+
+def test_header_compiles_as_c(tmp_path):
+    c = tmp_path / "t.c"
+    c.write_text('#include "qaintensor_cuda.h"\nint main(void){return qtn_version()>0?0:1;}\n')
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), "-c", str(c), "-o",
+                    str(tmp_path / "t.o")], check=True)
+
+
+def test_no_cpu_fallback(q):
+    from qaintensor_b200 import _lib
+    if _lib.device_count() > 0:
+        pytest.skip("a GPU is present; the no-device error path cannot be observed")
+    a = np.ones((2, 2), dtype=complex)
+    net = q.GeneralTensorNetwork([q.Tensor(a), q.Tensor(a)], [q.Summation([(1, 2), (2, 1)])], [(1, 1), (2, 2)])
+    with pytest.raises(q.QtnError) as ei:
+        q.contract(net)
+    assert ei.value.code == _lib.QTN_ENODEVICE and "no CPU fallback" in str(ei.value)
+    with pytest.raises(q.QtnError):
+        q.svd_trunc(a)
+
+
+def test_product_never_imports_oracle():
+    """The product path must not import, include or execute anything under oracle/."""
+    pkg = os.path.join(ROOT, "qaintensor.jl_b200")
+    pat = re.compile(r"^\s*(from\s+oracle|import\s+oracle|#include\s+[\"<].*oracle)|oracle[/.]\w+\.(py|so|c)\b", re.M)
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cpp", ".h", ".cuh")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert not pat.search(txt), "%s reaches into oracle/" % f

@@ -1,0 +1,166 @@
+"""GPU parity of the contraction path (through the C ABI) against the CPU oracle.
+Tolerance: 1e-10 relative for ComplexF64 amplitudes (BASELINE.json north_star)."""
+import numpy as np
+import pytest
+
+from conftest import random_TN, rel_err, to_oracle
+from oracle import contract as oc
+from oracle import gates as og
+from oracle import network2graph as o2g
+from oracle import plan as oplan
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+
+def test_matmul_and_two_tensor_networks(gpu):  # test/test_svd.jl:13-25 shapes
+    q = gpu
+    rng = np.random.default_rng(1)
+    r = lambda *s: rng.standard_normal(s) + 1j * rng.standard_normal(s)  # noqa: E731
+    a, b = r(4, 4), r(4, 4)
+    net = q.GeneralTensorNetwork([q.Tensor(a), q.Tensor(b)], [q.Summation([(1, 2), (2, 1)])], [(1, 1), (2, 2)])
+    assert rel_err(q.contract(net), a @ b) < TOL
+    t1, t2 = r(2, 3, 4, 6), r(1, 5, 2, 4)
+    for con, opn in (([(1, 1), (2, 3)], [(1, 2), (1, 3), (1, 4), (2, 1), (2, 2), (2, 4)]),
+                     ([(1, 3), (2, 4)], [(1, 1), (1, 2), (1, 4), (2, 1), (2, 2), (2, 3)])):
+        net = q.GeneralTensorNetwork([q.Tensor(t1), q.Tensor(t2)], [q.Summation(con)], opn)
+        want = oc.contract(to_oracle(net))
+        got = q.contract(net)
+        assert got.shape == want.shape and rel_err(got, want) < TOL
+
+
+def test_single_tensor_permutedims(gpu):  # src/contract.jl:243-245
+    q = gpu
+    rng = np.random.default_rng(2)
+    d = rng.standard_normal((2, 6)) + 1j * rng.standard_normal((2, 6))
+    net = q.GeneralTensorNetwork([q.Tensor(d)], [], [(1, 1), (1, 2)])
+    assert np.array_equal(q.contract(net), d)
+    net = q.GeneralTensorNetwork([q.Tensor(d)], [], [(1, 2), (1, 1)])
+    assert np.array_equal(q.contract(net), d.T)
+
+
+@pytest.mark.parametrize("shape,perm", [((2, 3, 4, 5), (3, 1, 4, 2)), ((7, 6), (2, 1)), ((2,) * 12, (12, 3, 1, 7, 5, 2, 9, 11, 4, 6, 8, 10)),
+                                         ((64, 2, 2, 64), (1, 3, 2, 4)), ((5, 1, 3), (3, 2, 1)), ((128, 96), (2, 1)), ((4, 4, 4), (1, 2, 3))])
+def test_permutedims_bit_exact(gpu, shape, perm):
+    q = gpu
+    rng = np.random.default_rng(3)
+    a = rng.standard_normal(shape) + 1j * rng.standard_normal(shape)
+    got = q.permutedims(a, perm)
+    assert np.array_equal(got, np.transpose(a, [p - 1 for p in perm]))
+
+
+def test_qft12_state_vector(gpu):  # BASELINE config 1
+    q = gpu
+    net, vecs = q.circuits.cfg1_qft_network(12)
+    got = q.contract(net)
+    want = oc.contract(to_oracle(net))
+    assert got.shape == (2,) * 12 and rel_err(got, want) < TOL
+    psi0 = vecs[0]
+    for v in vecs[1:]:
+        psi0 = np.kron(v, psi0)
+    assert rel_err(got.reshape(-1, order="F"), og.apply(psi0, og.qft_circuit(12))) < TOL
+
+
+def test_tensor_circuit_qft3_default_and_exhaustive(gpu):  # test/test_tensor_circuit.jl:32-60
+    q = gpu
+    rng = np.random.default_rng(4)
+    r = lambda *s: rng.standard_normal(s) + 1j * rng.standard_normal(s)  # noqa: E731
+    net = q.GeneralTensorNetwork([q.Tensor(r(2, 6)), q.Tensor(r(2, 6, 7)), q.Tensor(r(2, 7))],
+                                 [q.Summation([(1, 2), (2, 2)]), q.Summation([(2, 3), (3, 2)])],
+                                 [(1, 1), (2, 1), (3, 1)])
+    psi0 = q.contract(net).reshape(-1, order="F")
+    assert rel_err(psi0, oc.contract(to_oracle(net)).reshape(-1, order="F")) < TOL
+    q.tensor_circuit(net, q.qft_circuit(3))
+    ref = og.apply(psi0, og.qft_circuit(3))
+    assert rel_err(q.contract(net).reshape(-1, order="F"), ref) < TOL
+    assert rel_err(q.contract(net, True).reshape(-1, order="F"), ref) < TOL
+
+
+def test_random_networks_default_vs_optimized_order(gpu):  # test/test_treewidth.jl:318-347
+    q = gpu
+    rng = np.random.default_rng(5)
+    for (Nn, Ne) in [(10, 10), (10, 20), (20, 40), (12, 30)]:
+        net = random_TN(q, Nn, Ne, rng)
+        want = complex(oc.contract(to_oracle(net)))
+        got0 = complex(q.contract(net))
+        n2 = net.copy()
+        q.optimize_contraction_order(n2)
+        got1 = complex(q.contract(n2))
+        assert abs(got0 - want) < TOL * abs(want) and abs(got1 - want) < TOL * abs(want)
+
+
+def test_self_contraction_and_disconnected(gpu):
+    q = gpu
+    rng = np.random.default_rng(6)
+    r = lambda *s: rng.standard_normal(s) + 1j * rng.standard_normal(s)  # noqa: E731
+    a, b, c = r(3, 4, 3), r(4, 5), r(2, 2)
+    net = q.GeneralTensorNetwork([q.Tensor(a), q.Tensor(b), q.Tensor(c)],
+                                 [q.Summation([(1, 1), (1, 3)]), q.Summation([(1, 2), (2, 1)])],
+                                 [(2, 2), (3, 2), (3, 1)])
+    want = np.einsum("iji,jk,ab->kba", a, b, c)
+    assert rel_err(q.contract(net), want) < TOL
+    assert rel_err(oc.contract(to_oracle(net)), want) < 1e-12
+
+
+def test_cfg2_small_and_full_amplitude(gpu):  # BASELINE config 2 at full size
+    q = gpu
+    for args in ((10, 8, 7), (24, 20, None)):
+        net, _, _ = q.circuits.cfg2_network(*args)
+        q.optimize_contraction_order(net)
+        want = complex(oc.contract(to_oracle(net)))
+        got = complex(q.contract(net))
+        assert abs(got - want) < TOL * abs(want)
+
+
+def test_plan_reuse_and_slicing_invariance(gpu):  # EXTENSION: sum over slices == unsliced
+    q = gpu
+    net, _, _ = q.circuits.cfg2_network(16, 12, seed=11)
+    q.optimize_contraction_order(net)
+    il = q.contract_rep(net)
+    arrays = [t.data for t in net.tensors]
+    shapes = [a.shape for a in arrays]
+    want = complex(oc.contract(to_oracle(net)))
+    plan = q.ContractionPlan(shapes, il)
+    assert abs(complex(plan.execute(arrays)) - want) < TOL * abs(want)
+    assert abs(complex(plan.execute(arrays)) - want) < TOL * abs(want)  # graph replay
+    S = q.choose_slices(shapes, il, None, 8, 16)
+    nodes, steps = oplan.contraction_tree(il)
+    assert S == oplan.choose_slice_labels(nodes, steps, oplan.label_dims(arrays, il), 8, 16)
+    sp = q.ContractionPlan(shapes, il, None, S)
+    assert sp.nslices >= 16
+    assert abs(complex(sp.execute(arrays)) - want) < TOL * abs(want)
+    half = sp.nslices // 2
+    parts = complex(sp.execute(arrays, 0, half)) + complex(sp.execute(None, half, sp.nslices))
+    assert abs(parts - want) < TOL * abs(want)
+    # per-slice parity against the oracle's tree execution
+    dims = oplan.label_dims(arrays, il)
+    for sid in (0, 5, sp.nslices - 1):
+        ws = complex(oplan.execute_tree(arrays, il, nodes, steps, oplan.slice_assignment(S, dims, sid)))
+        gs = complex(sp.execute(None, sid, sid + 1))
+        assert abs(gs - ws) < TOL * max(abs(ws), abs(want))
+
+
+def test_cfg3_reduced_depth_sliced(gpu):  # BASELINE config 3 topology at an oracle-sized depth
+    q = gpu
+    net, _, _ = q.circuits.cfg3_network(4, 4, 8, seed=21)
+    q.optimize_contraction_order(net)
+    il = q.contract_rep(net)
+    arrays = [t.data for t in net.tensors]
+    want = complex(oc.contract(to_oracle(net)))
+    S = q.choose_slices([a.shape for a in arrays], il, None, 10, 8)
+    sp = q.ContractionPlan([a.shape for a in arrays], il, None, S)
+    got = complex(sp.execute(arrays))
+    assert abs(got - want) < TOL * abs(want)
+
+
+def test_open_legs_many_amplitudes(gpu):  # open output legs
+    q = gpu
+    rng = np.random.default_rng(9)
+    gates = q.circuits.brickwork_gates(10, 6, rng)
+    net = q.circuits.amplitude_network(10, gates, None)
+    got = q.contract(net)
+    psi = np.zeros(2 ** 10, dtype=complex)
+    psi[0] = 1
+    # non-decomposed tensor_circuit! contracts the row bits: it applies U^T (quirk Q2)
+    ref = og.apply(psi, [og.CircuitGate(g.iwire, g.matrix.T) for g in gates])
+    assert rel_err(got.reshape(-1, order="F"), ref) < TOL

@@ -1,0 +1,132 @@
+"""Host-side (no GPU) parity of the library's C++ planner with the oracle: contraction
+order, exhaustive order, slice set and plan cost must be bit-exact."""
+import numpy as np
+import pytest
+
+from conftest import random_TN, to_oracle
+from oracle import contract as oc
+from oracle import network2graph as o2g
+from oracle import plan as oplan
+from oracle.lightgraphs import complete_graph
+
+
+def test_order_parity_random_networks(q):
+    rng = np.random.default_rng(5)
+    for (Nn, Ne) in [(10, 10), (10, 20), (10, 50), (20, 60), (30, 60), (40, 100)] * 4:
+        net = random_TN(q, Nn, Ne, rng)
+        try:
+            want = [t[2] for t in o2g.contraction_order(to_oracle(net))]
+        except StopIteration:
+            continue
+        perm, _ = q.network2graph.contraction_order_perm(net)
+        assert perm == want
+
+
+def test_order_parity_with_self_contractions(q):
+    rng = np.random.default_rng(6)
+    net = random_TN(q, 8, 14, rng)
+    # add a self-contraction on tensor 3: two new legs joined to each other
+    t = net.tensors[2]
+    net.tensors[2] = q.Tensor(rng.standard_normal(t.size() + (2, 2)) + 0j)
+    r = t.ndims()
+    net.contractions.insert(4, q.Summation([(3, r + 1), (3, r + 2)]))
+    perm, _ = q.network2graph.contraction_order_perm(net)
+    assert perm == [t[2] for t in o2g.contraction_order(to_oracle(net))]
+    assert perm[0] == 5
+
+
+def test_hand_traced_vector(q):
+    A = np.ones((2, 2), dtype=complex)
+    net = q.GeneralTensorNetwork([q.Tensor(A) for _ in range(4)],
+                                 [q.Summation([(1, 2), (2, 1)]), q.Summation([(2, 2), (3, 1)]),
+                                  q.Summation([(3, 2), (4, 1)]), q.Summation([(4, 2), (1, 1)])], [])
+    perm, tw = q.network2graph.contraction_order_perm(net)
+    assert perm == [3, 4, 2, 1] and tw == 2
+    assert q.contraction_order(net) == [(3, 4, 3), (1, 4, 4), (2, 3, 2), (1, 2, 1)]
+    n2 = net.copy()
+    q.optimize_contraction_order(n2)
+    assert set(n2.contractions) == set(net.contractions) and n2.tensors == net.tensors and n2.openidx == net.openidx
+
+
+def test_treewidth_known_answers_cxx(q):  # test/test_treewidth.jl:204-221 through the C ABI
+    for n in (10, 25, 50):
+        tw, order = q.tree_decomposition_width(n, complete_graph(n).edges())
+        assert tw == n - 1 and sorted(order) == list(range(1, n + 1))
+    for k in range(2, 6):
+        G = o2g.local_circuit_graph(10, k)
+        tw, order = q.tree_decomposition_width(10, G.edges())
+        assert tw == k - 1 and order == o2g.min_fill_ordering(G)
+
+
+def test_minfill_order_parity_random_graphs(q):
+    rng = np.random.default_rng(7)
+    for _ in range(10):
+        Nn = int(rng.integers(8, 40))
+        Ne = int(rng.integers(Nn, Nn * (Nn - 1) // 2 + 1))
+        G = o2g.random_graph(Nn, Ne, rng)
+        tw, order = q.tree_decomposition_width(Nn, G.edges())
+        assert order == o2g.min_fill_ordering(G) and tw == o2g.tree_decomposition(G)[0]
+
+
+@pytest.mark.parametrize("name", ["cfg2", "cfg3"])
+def test_baseline_configs_order_slices_cost(q, name):
+    net = (q.circuits.cfg2_network() if name == "cfg2" else q.circuits.cfg3_network())[0]
+    onet = to_oracle(net)
+    want = o2g.optimize_contraction_order(onet)
+    perm, tw = q.network2graph.contraction_order_perm(net)
+    assert perm == want and tw == (26 if name == "cfg2" else 54)
+    q.optimize_contraction_order(net)
+    il = q.contract_rep(net)
+    assert il == oc.contract_rep(onet)
+    shapes = [t.size() for t in net.tensors]
+    plan = q.ContractionPlan(shapes, il)
+    nodes, steps = oplan.contraction_tree(il)
+    dims = oplan.label_dims([t.data for t in net.tensors], il)
+    f, b, mx, mnk = oplan.tree_cost(nodes, steps, dims)
+    assert (plan.nsteps, plan.flops_per_slice, plan.bytes_per_slice, plan.max_elems) == (len(steps), f, b, mx)
+    got = sorted((max(m, n), min(m, n), k) for m, n, k, _ in plan.steps())
+    assert got == sorted((max(m, n), min(m, n), k) for m, n, k in mnk)
+    for lim, mins in ((28, 1), (30, 1)) if name == "cfg3" else ((16, 1), (12, 64)):
+        S = q.choose_slices(shapes, il, None, lim, mins)
+        assert S == oplan.choose_slice_labels(nodes, steps, dims, lim, mins)
+        sp = q.ContractionPlan(shapes, il, None, S)
+        f2, b2, mx2, _ = oplan.tree_cost(nodes, steps, dims, S)
+        assert (sp.flops_per_slice, sp.bytes_per_slice, sp.max_elems) == (f2, b2, mx2)
+        assert sp.nslices == 2 ** len(S) and mx2 <= 2 ** lim
+
+
+def test_exhaustive_order_parity(q):  # src/contract.jl:184-235 incl. quirk Q1 inputs
+    from oracle import gates as og, mpo as ompo, network as on
+    rng = np.random.default_rng(8)
+    r = lambda *s: rng.standard_normal(s) + 1j * rng.standard_normal(s)  # noqa: E731
+    ts = [r(2, 6), r(2, 6, 7), r(2, 7)]
+    net = q.GeneralTensorNetwork([q.Tensor(t) for t in ts],
+                                 [q.Summation([(1, 2), (2, 2)]), q.Summation([(2, 3), (3, 2)])],
+                                 [(1, 1), (2, 1), (3, 1)])
+    q.tensor_circuit(net, q.qft_circuit(3))
+    leg_costs, il = q.contract_rep(net, True)
+    seq, cost = q.contract_order(net, leg_costs, il)
+    onet = to_oracle(net)
+    lc, oil = oc.contract_rep(onet, True)
+    oseq, ocost = oc.contract_order(onet, lc, oil)
+    assert (seq, cost) == (oseq, ocost)
+    for trial in range(4):
+        net = random_TN(q, 6, 9, rng)
+        if any(t.size() == (1,) for t in net.tensors):
+            continue
+        leg_costs, il = q.contract_rep(net, True)
+        onet = to_oracle(net)
+        try:
+            want = oc.contract_order(onet, *oc.contract_rep(onet, True))
+        except Exception:
+            continue
+        assert q.contract_order(net, leg_costs, il) == want
+
+
+def test_plan_rejects_malformed_networks(q):
+    with pytest.raises(q.QtnError, match="appears 1 times"):
+        q.ContractionPlan([(2, 2), (2,)], [[1, 2], [1]])
+    with pytest.raises(q.QtnError, match="different extent"):
+        q.ContractionPlan([(2, 3), (2,)], [[-1, 1], [1]])
+    with pytest.raises(q.QtnError, match="not a contracted label"):
+        q.ContractionPlan([(2, 2), (2,)], [[-1, 1], [1]], None, [7])

@@ -54,6 +54,9 @@ int qtn_device_count(int* count);
 void* qtn_stream(void);
 /* Number of this library's kernels launched since the last reset.             */
 int64_t qtn_launch_count(int reset);
+/* Diagnostics: FP64 tensor-pipe ceiling (TFLOP/s) from a register-only DMMA issue loop;
+ * the denominator of the GEMM roofline (MEASURED_PEAKS.json carries no FP64 figure).   */
+int qtn_bench_dmma_peak(double* tflops_out);
 
 /* ---- contraction order (host, integer-only, bit-exact) ----------------------
  * Replaces `contraction_order(net)` / `optimize_contraction_order!(net)`
@@ -130,6 +133,10 @@ int qtn_nccl_init(int32_t rank, int32_t nranks, const void* id /* 128 bytes */);
 int qtn_nccl_allreduce_sum_f64(void* dev_buf, int64_t count);
 int qtn_contract_sliced(qtn_plan* plan, const void* const* host_data, int32_t rank,
                         int32_t nranks, void* host_out);
+/* Same over the slice window [first_slice, first_slice + nslices) only (partial sums,
+ * e.g. one batch of a long-running amplitude).                                    */
+int qtn_contract_sliced_range(qtn_plan* plan, const void* const* host_data, int64_t first_slice,
+                              int64_t nslices, int32_t rank, int32_t nranks, void* host_out);
 
 /* ---- permutedims ---------------------------------------------------------------
  * Replaces Julia `permutedims(A, perm)` at src/contract.jl:244, src/svd.jl:20-21,

@@ -44,6 +44,7 @@ lib.qtn_launch_count.argtypes = [C.c_int]
 _SIGS = {
     "qtn_init": [C.c_int],
     "qtn_device_count": [P(C.c_int)],
+    "qtn_bench_dmma_peak": [P(f64)],
     "qtn_order_treewidth": [i32, i32, P(i32), P(i32), P(i32)],
     "qtn_graph_treewidth": [i32, i32, P(i32), P(i32), P(i32)],
     "qtn_order_exhaustive": [i32, P(i32), P(P(i32)), i32, P(i64), P(i32), P(i32), P(i64)],
@@ -62,6 +63,7 @@ _SIGS = {
     "qtn_nccl_init": [i32, i32, vp],
     "qtn_nccl_allreduce_sum_f64": [vp, i64],
     "qtn_contract_sliced": [vp, P(vp), i32, i32, vp],
+    "qtn_contract_sliced_range": [vp, P(vp), i64, i64, i32, i32, vp],
     "qtn_permutedims": [vp, i32, P(i64), P(i32), i32, vp],
     "qtn_permutedims_device": [vp, i32, P(i64), P(i32), i32, vp],
     "qtn_zgemm_device": [C.c_char, C.c_char, i64, i64, i64, vp, i64, vp, i64, vp, i64],
@@ -97,6 +99,17 @@ def device_count():
 def require_device():
     """Fail loudly when the CUDA path cannot run (no fallback exists)."""
     check(lib.qtn_init(int(os.environ.get("LOCAL_RANK", "0")) if device_count() > 1 else 0))
+
+
+def dmma_peak_tflops():
+    """Measured FP64 tensor-pipe ceiling (register-only DMMA loop), TFLOP/s."""
+    v = f64(0.0)
+    check(lib.qtn_bench_dmma_peak(C.byref(v)))
+    return float(v.value)
+
+
+def stream_ptr():
+    return int(lib.qtn_stream() or 0)
 
 
 def launch_count(reset=False):

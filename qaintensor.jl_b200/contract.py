@@ -105,12 +105,17 @@ class ContractionPlan:
                                         out.ctypes.data_as(C.c_void_p)))
         return out
 
-    def contract_sliced(self, arrays, rank, nranks):
-        """Slice-parallel contraction: this rank's block of slices + one NCCL allreduce."""
+    def contract_sliced(self, arrays, rank=0, nranks=1, first_slice=0, nslices=None):
+        """Slice-parallel contraction of the window [first_slice, first_slice + nslices)
+        (default: all slices): this rank's contiguous block + one NCCL allreduce."""
         _lib.require_device()
         out = np.zeros(self.out_dims, dtype=np.complex128, order="F")
-        arrs = self._marshal(arrays)
-        check(lib.qtn_contract_sliced(self._h, data_ptrs(arrs), rank, nranks, out.ctypes.data_as(C.c_void_p)))
+        ptrs = None
+        if arrays is not None:
+            arrs = self._marshal(arrays)
+            ptrs = data_ptrs(arrs)
+        check(lib.qtn_contract_sliced_range(self._h, ptrs, first_slice, self.nslices if nslices is None else nslices,
+                                            rank, nranks, out.ctypes.data_as(C.c_void_p)))
         return out
 
     def time_steps(self, slice_id=0):

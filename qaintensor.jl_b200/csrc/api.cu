@@ -17,6 +17,7 @@ int64_t launch_count(int reset);
 void count_launch(int64_t n);
 int launch_gemm(GemmArgs& g, int variant, int split_k, cudaStream_t st);
 int permutedims_device(const void* in, int rank, const int64_t* dims, const int32_t* perm, void* out);
+int bench_dmma_peak(double* tflops_out);
 }  // namespace qtn
 
 using namespace qtn;
@@ -47,6 +48,10 @@ int qtn_device_count(int* count) {
 }
 void* qtn_stream(void) { return (void*)stream(); }
 int64_t qtn_launch_count(int reset) { return launch_count(reset); }
+int qtn_bench_dmma_peak(double* tflops_out) {
+    if (!tflops_out) return fail(QTN_EINVAL, "null argument");
+    return bench_dmma_peak(tflops_out);
+}
 
 int qtn_order_treewidth(int32_t ntensors, int32_t ncontr, const int32_t* pairs, int32_t* perm_out, int32_t* tw_out) {
     if (!pairs || !perm_out) return fail(QTN_EINVAL, "qtn_order_treewidth: null argument");
@@ -222,12 +227,18 @@ static int exec_host(Plan* p, const void* const* host_data, int64_t s0, int64_t 
     return rc;
 }
 
-int qtn_contract_sliced(qtn_plan* plan, const void* const* host_data, int32_t rank, int32_t nranks, void* host_out) {
+int qtn_contract_sliced_range(qtn_plan* plan, const void* const* host_data, int64_t first_slice, int64_t nslices,
+                              int32_t rank, int32_t nranks, void* host_out) {
     if (!plan || !host_out) return fail(QTN_EINVAL, "qtn_contract_sliced: null argument");
     if (nranks < 1 || rank < 0 || rank >= nranks) return fail(QTN_EINVAL, "qtn_contract_sliced: bad rank %d of %d", rank, nranks);
-    int64_t n = plan->p->nslices;
-    int64_t s0 = n * rank / nranks, s1 = n * (rank + 1) / nranks;  // contiguous blocks
+    if (first_slice < 0 || nslices < 0 || first_slice + nslices > plan->p->nslices)
+        return fail(QTN_EINVAL, "qtn_contract_sliced: slice range outside the plan's %lld slices", (long long)plan->p->nslices);
+    int64_t s0 = first_slice + nslices * rank / nranks, s1 = first_slice + nslices * (rank + 1) / nranks;  // contiguous blocks
     return exec_host(plan->p, host_data, s0, s1, host_out, nranks > 1);
+}
+int qtn_contract_sliced(qtn_plan* plan, const void* const* host_data, int32_t rank, int32_t nranks, void* host_out) {
+    if (!plan) return fail(QTN_EINVAL, "qtn_contract_sliced: null argument");
+    return qtn_contract_sliced_range(plan, host_data, 0, plan->p->nslices, rank, nranks, host_out);
 }
 
 // ---- permutedims ---------------------------------------------------------------------

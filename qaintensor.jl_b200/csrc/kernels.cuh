@@ -43,7 +43,7 @@ struct GemmArgs {
     TabArg a_row, a_k, b_k, b_col, c_row, c_col;
     i64 M, N, K;
     i64 k_per_split;
-    int tiles_m;
+    int tiles_m, tiles_n, group_n;
     int c_dense;
     int mode;  // 0 store, 1 add (single writer), 2 atomic add
     int conj_a, conj_b;  // conjugate the operand on the way into the tensor pipe
@@ -59,7 +59,7 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                  : "+d"(c0), "+d"(c1)
                  : "d"(a), "d"(b));
 }
@@ -107,8 +107,13 @@ zgemm_gather_kernel(const __grid_constant__ GemmArgs g) {
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = warp % WARPS_M, wn = warp / WARPS_M;
+    // grouped rasterization: a wave of CTAs covers ~square patches of C, so both operands
+    // are re-used out of L2 instead of A being re-streamed once per column tile
     const i64 tile = blockIdx.x;
-    const i64 m0 = (tile % g.tiles_m) * BM, n0 = (tile / g.tiles_m) * BN;
+    const i64 per_group = (i64)g.group_n * g.tiles_m;
+    const i64 grp = tile / per_group, in_grp = tile - grp * per_group;
+    const i64 gsz = min((i64)g.group_n, (i64)g.tiles_n - grp * g.group_n);
+    const i64 m0 = (in_grp / gsz) * BM, n0 = (grp * g.group_n + in_grp % gsz) * BN;
     const i64 kb = (i64)blockIdx.y * g.k_per_split;
     const i64 ke = min(g.K, kb + g.k_per_split);
 
@@ -167,29 +172,43 @@ zgemm_gather_kernel(const __grid_constant__ GemmArgs g) {
         }
         const double2* a_s = sA + (it % STAGES) * BK * PA + wm * WM + (lane >> 2);
         const double2* b_s = sB + (it % STAGES) * BK * PB + wn * WN + (lane >> 2);
-#pragma unroll
-        for (int k4 = 0; k4 < BK / 4; ++k4) {
+        // register double-buffered fragments: the LDS.128 of k4+1 fly under the DMMAs of k4
+        double2 af[2][MI], bf[2][NI];
+        auto load_frags = [&](int buf, int k4) {
             const int kr = k4 * 4 + (lane & 3);
-            double2 af[MI], bf[NI];
 #pragma unroll
             for (int i = 0; i < MI; ++i) {
-                af[i] = a_s[kr * PA + i * 8];
-                if (g.conj_a) af[i].y = -af[i].y;
+                af[buf][i] = a_s[kr * PA + i * 8];
+                if (g.conj_a) af[buf][i].y = -af[buf][i].y;
             }
 #pragma unroll
             for (int j = 0; j < NI; ++j) {
-                bf[j] = b_s[kr * PB + j * 8];
-                if (g.conj_b) bf[j].y = -bf[j].y;
+                bf[buf][j] = b_s[kr * PB + j * 8];
+                if (g.conj_b) bf[buf][j].y = -bf[buf][j].y;
             }
+        };
+        load_frags(0, 0);
+#pragma unroll
+        for (int k4 = 0; k4 < BK / 4; ++k4) {
+            const int cur = k4 & 1;
+            if (k4 + 1 < BK / 4) load_frags(cur ^ 1, k4 + 1);
+            // four passes of MI*NI independent DMMAs (no back-to-back dependent accumulators)
 #pragma unroll
             for (int i = 0; i < MI; ++i)
 #pragma unroll
-                for (int j = 0; j < NI; ++j) {
-                    dmma884(cr[i][j][0], cr[i][j][1], af[i].x, bf[j].x);
-                    dmma884(cr[i][j][0], cr[i][j][1], -af[i].y, bf[j].y);
-                    dmma884(ci[i][j][0], ci[i][j][1], af[i].x, bf[j].y);
-                    dmma884(ci[i][j][0], ci[i][j][1], af[i].y, bf[j].x);
-                }
+                for (int j = 0; j < NI; ++j) dmma884(cr[i][j][0], cr[i][j][1], af[cur][i].x, bf[cur][j].x);
+#pragma unroll
+            for (int i = 0; i < MI; ++i)
+#pragma unroll
+                for (int j = 0; j < NI; ++j) dmma884(ci[i][j][0], ci[i][j][1], af[cur][i].x, bf[cur][j].y);
+#pragma unroll
+            for (int i = 0; i < MI; ++i)
+#pragma unroll
+                for (int j = 0; j < NI; ++j) dmma884(cr[i][j][0], cr[i][j][1], -af[cur][i].y, bf[cur][j].y);
+#pragma unroll
+            for (int i = 0; i < MI; ++i)
+#pragma unroll
+                for (int j = 0; j < NI; ++j) dmma884(ci[i][j][0], ci[i][j][1], af[cur][i].y, bf[cur][j].x);
         }
     }
     cp_async_wait<0>();

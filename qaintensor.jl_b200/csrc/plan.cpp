@@ -557,7 +557,9 @@ int build_plan(int nt, const int32_t* ranks, const int64_t* const* dims, const i
             s.variant = (s.N <= 16) ? 1 : 0;
             int64_t tiles = ((s.M + bm - 1) / bm) * ((s.N + bn - 1) / bn);
             s.split_k = 1;
-            if (tiles < kNumSM && s.K >= 256) {
+            if (s.M * s.N <= 16 && s.K >= 2048) {
+                s.variant = 2;  // closing dot products: streaming gather-dot, HBM-bound
+            } else if (tiles < kNumSM && s.K >= 256) {
                 int64_t want = (2 * kNumSM + tiles - 1) / tiles;
                 int64_t maxs = s.K / 64;
                 s.split_k = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(want, maxs), 1024));
@@ -566,7 +568,7 @@ int build_plan(int nt, const int32_t* ranks, const int64_t* const* dims, const i
             pl.bytes += 16.0 * ((double)s.M * s.K + (double)s.K * s.N + (double)s.M * s.N);
             pl.max_elems = std::max(pl.max_elems, s.M * s.N);
         }
-        if (!s.invariant) pl.launches_per_slice += 1 + ((s.kind == STEP_GEMM && s.split_k > 1 && !s.final_step) ? 1 : 0);
+        if (!s.invariant) pl.launches_per_slice += 1;
     }
     for (int i = 0; i < nt; ++i) pl.max_elems = std::max(pl.max_elems, pl.nodes[i].numel);
     *out = plan.release();

@@ -1,0 +1,317 @@
+// contract_svd (src/svd.jl:7-38) and the device-resident MPS update loop built from
+// src/switch.jl:18-56 (two-site theta -> SVD -> split U / S*V'); EXTENSIONS are marked.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+#include "kernels.cuh"
+#include "qtn_internal.h"
+
+namespace qtn {
+cudaStream_t stream();
+void count_launch(int64_t n);
+int permutedims_device(const void* in, int rank, const int64_t* dims, const int32_t* perm, void* out);
+struct SvdJob {
+    double2* A;
+    int64_t m0, n0;
+    double2* U;
+    double* S;
+    double2* Vh;
+};
+int svd_batched_device(int batch, const SvdJob* jobs, double er, int64_t maxdim, int64_t* k_out, double* disc_out,
+                       int* sweeps_out);
+
+#define CUDA_TRY(expr)                                                                          \
+    do {                                                                                        \
+        cudaError_t _e = (expr);                                                                \
+        if (_e != cudaSuccess)                                                                  \
+            return fail(QTN_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+// out[r, c] = in[r, c] * (by_col ? s[c] : s[r]) for an (rows x cols) block; separate leading dimensions
+__global__ void scale_copy_kernel(const double2* __restrict__ in, int64_t ldi, double2* __restrict__ out, int64_t ldo,
+                                  int64_t rows, int64_t cols, const double* __restrict__ s, int by_col) {
+    const int64_t tot = rows * cols;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < tot; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = e % rows, c = e / rows;
+        const double f = s ? (by_col ? s[c] : s[r]) : 1.0;
+        const double2 v = in[c * ldi + r];
+        out[c * ldo + r] = make_double2(v.x * f, v.y * f);
+    }
+}
+
+// theta[(l,p1),(p2,r)] <- sum G[(p1',p2'),(p1,p2)] theta ; gate index = p1 + 2*p2, column-major 4x4
+__global__ void apply_gate2_kernel(double2* __restrict__ theta, int64_t L, int64_t R, const double2* __restrict__ gate) {
+    __shared__ double2 g[16];
+    if (threadIdx.x < 16) g[threadIdx.x] = gate[threadIdx.x];
+    __syncthreads();
+    const int64_t ld = 2 * L;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < L * R; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t l = e % L, r = e / L;
+        double2 v[4], o[4];
+#pragma unroll
+        for (int p2 = 0; p2 < 2; ++p2)
+#pragma unroll
+            for (int p1 = 0; p1 < 2; ++p1) v[p1 + 2 * p2] = theta[(p2 + 2 * r) * ld + l + L * p1];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            double re = 0, im = 0;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const double2 m = g[a + 4 * b];
+                re += m.x * v[b].x - m.y * v[b].y;
+                im += m.x * v[b].y + m.y * v[b].x;
+            }
+            o[a] = make_double2(re, im);
+        }
+#pragma unroll
+        for (int p2 = 0; p2 < 2; ++p2)
+#pragma unroll
+            for (int p1 = 0; p1 < 2; ++p1) theta[(p2 + 2 * r) * ld + l + L * p1] = o[p1 + 2 * p2];
+    }
+}
+
+static int scale_copy(const double2* in, int64_t ldi, double2* out, int64_t ldo, int64_t rows, int64_t cols, const double* s, int by_col) {
+    if (rows * cols == 0) return QTN_OK;
+    int blocks = (int)std::min<int64_t>((rows * cols + 255) / 256, 148 * 8);
+    scale_copy_kernel<<<blocks, 256, 0, stream()>>>(in, ldi, out, ldo, rows, cols, s, by_col);
+    count_launch(1);
+    return cudaGetLastError() == cudaSuccess ? QTN_OK : fail(QTN_ECUDA, "scale_copy launch failed");
+}
+
+struct DevBuf {
+    void* p = nullptr;
+    int alloc(size_t bytes) { return cudaMalloc(&p, std::max<size_t>(bytes, 256)) == cudaSuccess ? QTN_OK : fail(QTN_ENOMEM, "cudaMalloc(%zu) failed", bytes); }
+    ~DevBuf() { if (p) cudaFree(p); }
+};
+
+}  // namespace qtn
+
+using namespace qtn;
+
+struct qtn_mps {
+    int n = 0;
+    int64_t cap = 0;                  // bond capacity
+    std::vector<double2*> site;       // each 2 * cap * cap elements
+    std::vector<int64_t> lb, rb;
+    double2* theta = nullptr;         // batch scratch: per bond theta (2cap x 2cap), U, Vh, S
+    double2* ubuf = nullptr;
+    double2* vbuf = nullptr;
+    double* sbuf = nullptr;
+    double2* gates = nullptr;
+    int scratch_bonds = 0;
+};
+
+extern "C" {
+
+int qtn_contract_svd(const void* host_t1, int32_t rank1, const int64_t* dims1, int32_t i1, const void* host_t2,
+                     int32_t rank2, const int64_t* dims2, int32_t i2, double er, void* host_out) {
+    if (!(er >= 0)) return fail(QTN_EDOMAIN, "Error must be positive");
+    if (!host_t1 || !host_t2 || !host_out || !dims1 || !dims2) return fail(QTN_EINVAL, "qtn_contract_svd: null argument");
+    if (i1 < 1 || i2 < 1) return fail(QTN_EINVAL, "qtn_contract_svd: leg index must be >= 1");
+    const int64_t D1 = i1 <= rank1 ? dims1[i1 - 1] : 1, D2 = i2 <= rank2 ? dims2[i2 - 1] : 1;  // Julia size(A, d > ndims) == 1
+    if (D1 != D2) return fail(QTN_EDOMAIN, "Dimensions of contraction legs do not match");
+    if (i1 > rank1 || i2 > rank2) return fail(QTN_EINVAL, "qtn_contract_svd: leg index beyond the tensor rank");
+    int rc = device_ready();
+    if (rc) return rc;
+    cudaStream_t st = stream();
+    int64_t n1 = 1, n2 = 1;
+    for (int i = 0; i < rank1; ++i) n1 *= dims1[i];
+    for (int i = 0; i < rank2; ++i) n2 *= dims2[i];
+    const int64_t D = D1, m1 = n1 / D, m2 = n2 / D;
+    if (n1 == 0 || n2 == 0) return fail(QTN_EINVAL, "qtn_contract_svd: empty tensor");
+    const int64_t r1 = std::min(m1, D), r2 = std::min(D, m2);
+    DevBuf t1, t2, p1, p2, u1, u2, v1, v2, s1, s2, x1, x2, y, z, out;
+    if ((rc = t1.alloc(n1 * 16)) || (rc = t2.alloc(n2 * 16)) || (rc = p1.alloc(n1 * 16)) || (rc = p2.alloc(n2 * 16)) ||
+        (rc = u1.alloc(m1 * r1 * 16)) || (rc = v1.alloc(r1 * D * 16)) || (rc = s1.alloc(r1 * 8)) ||
+        (rc = u2.alloc(D * r2 * 16)) || (rc = v2.alloc(r2 * m2 * 16)) || (rc = s2.alloc(r2 * 8)))
+        return rc;
+    CUDA_TRY(cudaMemcpyAsync(t1.p, host_t1, n1 * 16, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(t2.p, host_t2, n2 * 16, cudaMemcpyHostToDevice, st));
+    // src/svd.jl:20-21: T1 -> (others..., i1), T2 -> (i2, others...)
+    std::vector<int32_t> perm1, perm2;
+    for (int a = 1; a <= rank1; ++a) if (a != i1) perm1.push_back(a);
+    perm1.push_back(i1);
+    perm2.push_back(i2);
+    for (int a = 1; a <= rank2; ++a) if (a != i2) perm2.push_back(a);
+    if ((rc = permutedims_device(t1.p, rank1, dims1, perm1.data(), p1.p))) return rc;
+    if ((rc = permutedims_device(t2.p, rank2, dims2, perm2.data(), p2.p))) return rc;
+    SvdJob jobs[2] = {{(double2*)p1.p, m1, D, (double2*)u1.p, (double*)s1.p, (double2*)v1.p},
+                      {(double2*)p2.p, D, m2, (double2*)u2.p, (double*)s2.p, (double2*)v2.p}};
+    int64_t k[2] = {0, 0};
+    if ((rc = svd_batched_device(2, jobs, er, 0, k, nullptr, nullptr))) return rc;
+    if (k[0] == 0 || k[1] == 0)
+        return fail(QTN_EDOMAIN, "contract_svd: the cutoff removes every singular value (the reference's findfirst returns nothing)");
+    const int64_t k1 = k[0], k2 = k[1];
+    // T = U1[:, :k1] diag(S1) V1h[:k1, :] U2[:, :k2] diag(S2) V2h[:k2, :]   (src/svd.jl:35)
+    if ((rc = x1.alloc(m1 * k1 * 16)) || (rc = x2.alloc(k2 * m2 * 16)) || (rc = y.alloc(k1 * k2 * 16)) || (rc = out.alloc(m1 * m2 * 16))) return rc;
+    if ((rc = scale_copy((double2*)u1.p, m1, (double2*)x1.p, m1, m1, k1, (double*)s1.p, 1))) return rc;
+    if ((rc = scale_copy((double2*)v2.p, r2, (double2*)x2.p, k2, k2, m2, (double*)s2.p, 0))) return rc;
+    if ((rc = qtn_zgemm_device('N', 'N', k1, k2, D, v1.p, r1, u2.p, D, y.p, k1))) return rc;
+    if (m1 * k1 * k2 + m1 * k2 * m2 <= k1 * k2 * m2 + m1 * k1 * m2) {
+        if ((rc = z.alloc(m1 * k2 * 16))) return rc;
+        if ((rc = qtn_zgemm_device('N', 'N', m1, k2, k1, x1.p, m1, y.p, k1, z.p, m1))) return rc;
+        if ((rc = qtn_zgemm_device('N', 'N', m1, m2, k2, z.p, m1, x2.p, k2, out.p, m1))) return rc;
+    } else {
+        if ((rc = z.alloc(k1 * m2 * 16))) return rc;
+        if ((rc = qtn_zgemm_device('N', 'N', k1, m2, k2, y.p, k1, x2.p, k2, z.p, k1))) return rc;
+        if ((rc = qtn_zgemm_device('N', 'N', m1, m2, k1, x1.p, m1, z.p, k1, out.p, m1))) return rc;
+    }
+    CUDA_TRY(cudaMemcpyAsync(host_out, out.p, m1 * m2 * 16, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return QTN_OK;
+}
+
+// ---------------- device-resident MPS (EXTENSION) -------------------------------------------------
+int qtn_mps_create(int32_t nsites, const void* const* host_sites, const int64_t* lbond, const int64_t* rbond,
+                   int64_t maxdim_capacity, qtn_mps** mps_out) {
+    if (nsites < 2 || !host_sites || !lbond || !rbond || !mps_out || maxdim_capacity < 1) return fail(QTN_EINVAL, "qtn_mps_create: bad argument");
+    int rc = device_ready();
+    if (rc) return rc;
+    for (int i = 0; i < nsites; ++i) {
+        if (lbond[i] < 1 || rbond[i] < 1 || lbond[i] > maxdim_capacity || rbond[i] > maxdim_capacity)
+            return fail(QTN_EINVAL, "qtn_mps_create: bond of site %d outside [1, capacity]", i + 1);
+        if (i > 0 && lbond[i] != rbond[i - 1]) return fail(QTN_EINVAL, "qtn_mps_create: bonds of sites %d and %d do not match", i, i + 1);
+    }
+    qtn_mps* m = new qtn_mps();
+    m->n = nsites;
+    m->cap = maxdim_capacity;
+    m->site.assign(nsites, nullptr);
+    m->lb.assign(lbond, lbond + nsites);
+    m->rb.assign(rbond, rbond + nsites);
+    const size_t sb = (size_t)2 * m->cap * m->cap * 16;
+    for (int i = 0; i < nsites; ++i) {
+        if (cudaMalloc((void**)&m->site[i], sb) != cudaSuccess) { qtn_mps_destroy(m); return fail(QTN_ENOMEM, "qtn_mps_create: out of device memory"); }
+        cudaMemcpyAsync(m->site[i], host_sites[i], (size_t)lbond[i] * 2 * rbond[i] * 16, cudaMemcpyHostToDevice, stream());
+    }
+    cudaStreamSynchronize(stream());
+    *mps_out = m;
+    return QTN_OK;
+}
+
+int qtn_mps_destroy(qtn_mps* m) {
+    if (!m) return QTN_OK;
+    if (stream()) cudaStreamSynchronize(stream());
+    for (auto p : m->site) if (p) cudaFree(p);
+    if (m->theta) cudaFree(m->theta);
+    if (m->ubuf) cudaFree(m->ubuf);
+    if (m->vbuf) cudaFree(m->vbuf);
+    if (m->sbuf) cudaFree(m->sbuf);
+    if (m->gates) cudaFree(m->gates);
+    delete m;
+    return QTN_OK;
+}
+
+int qtn_mps_bonds(const qtn_mps* m, int64_t* lbond, int64_t* rbond) {
+    if (!m) return fail(QTN_EINVAL, "null mps");
+    for (int i = 0; i < m->n; ++i) { if (lbond) lbond[i] = m->lb[i]; if (rbond) rbond[i] = m->rb[i]; }
+    return QTN_OK;
+}
+
+int qtn_mps_download(const qtn_mps* m, void* const* host_sites) {
+    if (!m || !host_sites) return fail(QTN_EINVAL, "null argument");
+    for (int i = 0; i < m->n; ++i)
+        CUDA_TRY(cudaMemcpyAsync(host_sites[i], m->site[i], (size_t)m->lb[i] * 2 * m->rb[i] * 16, cudaMemcpyDeviceToHost, stream()));
+    CUDA_TRY(cudaStreamSynchronize(stream()));
+    return QTN_OK;
+}
+
+static int mps_scratch(qtn_mps* m, int bonds) {
+    if (bonds <= m->scratch_bonds) return QTN_OK;
+    cudaStreamSynchronize(stream());
+    if (m->theta) cudaFree(m->theta);
+    if (m->ubuf) cudaFree(m->ubuf);
+    if (m->vbuf) cudaFree(m->vbuf);
+    if (m->sbuf) cudaFree(m->sbuf);
+    if (m->gates) cudaFree(m->gates);
+    m->theta = m->ubuf = m->vbuf = nullptr; m->sbuf = nullptr; m->gates = nullptr;
+    const size_t mat = (size_t)4 * m->cap * m->cap * 16;
+    if (cudaMalloc((void**)&m->theta, mat * bonds) != cudaSuccess || cudaMalloc((void**)&m->ubuf, mat * bonds) != cudaSuccess ||
+        cudaMalloc((void**)&m->vbuf, mat * bonds) != cudaSuccess || cudaMalloc((void**)&m->sbuf, (size_t)2 * m->cap * 8 * bonds) != cudaSuccess ||
+        cudaMalloc((void**)&m->gates, (size_t)256 * bonds) != cudaSuccess) {
+        m->scratch_bonds = 0;
+        return fail(QTN_ENOMEM, "qtn_mps: scratch for %d bonds does not fit", bonds);
+    }
+    m->scratch_bonds = bonds;
+    return QTN_OK;
+}
+
+int qtn_mps_apply_layer(qtn_mps* m, int32_t ngates, const int32_t* sites, const void* host_gates, double er, int64_t maxdim,
+                        double* disc_out) {
+    if (!m || !sites || !host_gates || ngates < 0) return fail(QTN_EINVAL, "qtn_mps_apply_layer: null argument");
+    if (ngates == 0) return QTN_OK;
+    if (maxdim <= 0 || maxdim > m->cap) maxdim = m->cap;
+    std::vector<char> used(m->n, 0);
+    for (int g = 0; g < ngates; ++g) {
+        const int s = sites[g];
+        if (s < 1 || s >= m->n) return fail(QTN_EINVAL, "qtn_mps_apply_layer: gate %d acts on sites (%d, %d) outside 1..%d", g + 1, s, s + 1, m->n);
+        if (used[s - 1] || used[s]) return fail(QTN_EINVAL, "qtn_mps_apply_layer: gates of one layer must act on disjoint bonds");
+        used[s - 1] = used[s] = 1;
+    }
+    int rc = mps_scratch(m, ngates);
+    if (rc) return rc;
+    cudaStream_t st = stream();
+    const size_t mat = (size_t)4 * m->cap * m->cap;
+    CUDA_TRY(cudaMemcpyAsync(m->gates, host_gates, (size_t)256 * ngates, cudaMemcpyHostToDevice, st));
+    std::vector<SvdJob> jobs(ngates);
+    for (int g = 0; g < ngates; ++g) {
+        const int i = sites[g] - 1;
+        const int64_t L = m->lb[i], B = m->rb[i], R = m->rb[i + 1];
+        double2* th = m->theta + mat * g;
+        // theta = T_i (2L x B) * T_{i+1} (B x 2R)      (src/switch.jl:26 with er = 0, no SVD round trip)
+        if ((rc = qtn_zgemm_device('N', 'N', 2 * L, 2 * R, B, m->site[i], 2 * L, m->site[i + 1], B, th, 2 * L))) return rc;
+        int blocks = (int)std::min<int64_t>((L * R + 255) / 256, 148 * 4);
+        apply_gate2_kernel<<<blocks, 256, 0, st>>>(th, L, R, m->gates + 16 * g);
+        count_launch(1);
+        jobs[g] = SvdJob{th, 2 * L, 2 * R, m->ubuf + mat * g, m->sbuf + 2 * m->cap * g, m->vbuf + mat * g};
+    }
+    std::vector<int64_t> k(ngates);
+    if ((rc = svd_batched_device(ngates, jobs.data(), er, maxdim, k.data(), disc_out, nullptr))) return rc;
+    for (int g = 0; g < ngates; ++g) {
+        const int i = sites[g] - 1;
+        const int64_t L = m->lb[i], R = m->rb[i + 1], rfull = std::min(2 * L, 2 * R);
+        int64_t kk = std::max<int64_t>(k[g], 1);  // keep at least one state
+        // T_i <- U[:, :k] (L,2,k);  T_{i+1} <- diag(S) V'[:k, :] (k,2,R)      (src/switch.jl:50-52)
+        if ((rc = scale_copy(m->ubuf + mat * g, 2 * L, m->site[i], 2 * L, 2 * L, kk, nullptr, 1))) return rc;
+        if ((rc = scale_copy(m->vbuf + mat * g, rfull, m->site[i + 1], kk, kk, 2 * R, m->sbuf + 2 * m->cap * g, 0))) return rc;
+        m->rb[i] = kk;
+        m->lb[i + 1] = kk;
+    }
+    return QTN_OK;
+}
+
+int qtn_mps_apply_gate2(qtn_mps* m, int32_t site, const void* host_gate, double er, int64_t maxdim, double* disc_out) {
+    return qtn_mps_apply_layer(m, 1, &site, host_gate, er, maxdim, disc_out);
+}
+
+int qtn_mps_overlap(const qtn_mps* a, const qtn_mps* b, double out[2]) {
+    if (!a || !b || !out) return fail(QTN_EINVAL, "null argument");
+    if (a->n != b->n) return fail(QTN_EINVAL, "qtn_mps_overlap: different lengths");
+    if (a->lb[0] != 1 || b->lb[0] != 1 || a->rb[a->n - 1] != 1 || b->rb[b->n - 1] != 1)
+        return fail(QTN_EINVAL, "qtn_mps_overlap: boundary bonds must be 1");
+    int rc = device_ready();
+    if (rc) return rc;
+    const int64_t cap = std::max(a->cap, b->cap);
+    DevBuf E, E2, Y;
+    if ((rc = E.alloc(cap * cap * 16)) || (rc = E2.alloc(cap * cap * 16)) || (rc = Y.alloc(2 * cap * cap * 16))) return rc;
+    const double2 one = make_double2(1.0, 0.0);
+    CUDA_TRY(cudaMemcpyAsync(E.p, &one, 16, cudaMemcpyHostToDevice, stream()));
+    void *e = E.p, *e2 = E2.p;
+    for (int i = 0; i < a->n; ++i) {
+        const int64_t la = a->lb[i], ra = a->rb[i], lb = b->lb[i], rb = b->rb[i];
+        // Y (la x 2rb) = E (la x lb) B_i (lb x 2rb);  E' (ra x rb) = A_i^H (ra x 2la) Y (2la x rb)
+        if ((rc = qtn_zgemm_device('N', 'N', la, 2 * rb, lb, e, la, b->site[i], lb, Y.p, la))) return rc;
+        if ((rc = qtn_zgemm_device('C', 'N', ra, rb, 2 * la, a->site[i], 2 * la, Y.p, 2 * la, e2, ra))) return rc;
+        std::swap(e, e2);
+    }
+    double2 res;
+    CUDA_TRY(cudaMemcpyAsync(&res, e, 16, cudaMemcpyDeviceToHost, stream()));
+    CUDA_TRY(cudaStreamSynchronize(stream()));
+    out[0] = res.x;
+    out[1] = res.y;
+    return QTN_OK;
+}
+
+}  // extern "C"

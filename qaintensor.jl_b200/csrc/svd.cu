@@ -1,16 +1,616 @@
-// Truncated SVD / MPS entry points (filled in below as the SVD path lands).
+// K5/K6: truncated SVD on the device (replaces LinearAlgebra.svd -> LAPACK zgesdd at
+// src/svd.jl:26-27, src/switch.jl:39, src/mps.jl:63,73, src/mpo.jl:53,62,
+// src/decompose.jl:26,38 and the tail-norm rule of src/svd.jl:29-33).
+//
+// Algorithm: blocked one-sided (Hestenes) Jacobi, batched over independent matrices.
+//   A (m x n, m >= n) is orthogonalised in place, V accumulates the column rotations.
+//   Columns are grouped in blocks of 16; a round-robin schedule pairs the blocks, and
+//   one CTA owns one (matrix, block pair) per round:
+//     1. Gram   G = P^H P of its 32-column panel P, on the FP64 tensor pipe (DMMA),
+//     2. eig    two-sided cyclic Jacobi on the 32x32 Hermitian G in shared memory
+//               (parallel ordering, de Rijk-style sorting), accumulating W,
+//     3. update P <- P W and the matching V panel <- V W, again on DMMA.
+//   Sweeps repeat until no CTA applied a rotation (scaled off-diagonal <= tol).
+//   Finalisation: sigma_j = ||a_j||, stable descending sort, U = A/sigma, Vh = V^H.
+//   Truncation (K6): k = n - r* + 1 with r* the first r whose reverse-cumulated tail
+//   sqrt(s_n^2 + ... + s_{n-r+1}^2) exceeds er (strict), then k <- min(k, maxdim).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#define QTN_SVD_TU
+#include "kernels.cuh"
 #include "qtn_internal.h"
-using namespace qtn;
-extern "C" {
-int qtn_svd_trunc(const void*, int64_t, int64_t, double, int64_t, void*, double*, void*, int64_t*) { return fail(QTN_EINVAL, "qtn_svd_trunc: not implemented yet"); }
-int qtn_svd_trunc_batched(int32_t, const void* const*, const int64_t*, const int64_t*, double, int64_t, void* const*, double* const*, void* const*, int64_t*) { return fail(QTN_EINVAL, "not implemented yet"); }
-int qtn_svd_trunc_device(void*, int64_t, int64_t, double, int64_t, void*, double*, void*, int64_t*, int32_t*) { return fail(QTN_EINVAL, "not implemented yet"); }
-int qtn_contract_svd(const void*, int32_t, const int64_t*, int32_t, const void*, int32_t, const int64_t*, int32_t, double, void*) { return fail(QTN_EINVAL, "not implemented yet"); }
-int qtn_mps_create(int32_t, const void* const*, const int64_t*, const int64_t*, int64_t, qtn_mps**) { return fail(QTN_EINVAL, "not implemented yet"); }
-int qtn_mps_destroy(qtn_mps*) { return QTN_OK; }
-int qtn_mps_bonds(const qtn_mps*, int64_t*, int64_t*) { return fail(QTN_EINVAL, "not implemented yet"); }
-int qtn_mps_download(const qtn_mps*, void* const*) { return fail(QTN_EINVAL, "not implemented yet"); }
-int qtn_mps_apply_gate2(qtn_mps*, int32_t, const void*, double, int64_t, double*) { return fail(QTN_EINVAL, "not implemented yet"); }
-int qtn_mps_apply_layer(qtn_mps*, int32_t, const int32_t*, const void*, double, int64_t, double*) { return fail(QTN_EINVAL, "not implemented yet"); }
-int qtn_mps_overlap(const qtn_mps*, const qtn_mps*, double*) { return fail(QTN_EINVAL, "not implemented yet"); }
+
+namespace qtn {
+cudaStream_t stream();
+void count_launch(int64_t n);
+int permutedims_device(const void* in, int rank, const int64_t* dims, const int32_t* perm, void* out);
+int launch_gemm(GemmArgs& g, int variant, int split_k, cudaStream_t st);
+
+#define CUDA_TRY(expr)                                                                          \
+    do {                                                                                        \
+        cudaError_t _e = (expr);                                                                \
+        if (_e != cudaSuccess)                                                                  \
+            return fail(QTN_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+constexpr int JB = 16;        // column block width
+constexpr int JP = 2 * JB;    // panel width (columns per CTA)
+constexpr int JPITCH = JP + 2;
+constexpr int JROWS = 64;     // panel rows staged per chunk
+constexpr int JTHREADS = 256;
+
+struct SvdProblem {
+    double2* A;   // m x n (lda = m), overwritten with U * diag(S) (unsorted)
+    double2* V;   // n x n
+    int m, n;
+    int nblocks;  // ceil(n / JB), rounded up to even
+};
+
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
+
+// column index of panel slot c (0..31) or -1 when outside the matrix
+__device__ __forceinline__ int panel_col(int c, int bi, int bj, int n) {
+    const int col = (c < JB ? bi * JB + c : bj * JB + (c - JB));
+    return col < n ? col : -1;
+}
+
+// One round of the block schedule.  grid = (max pairs, batch).
+__global__ void __launch_bounds__(JTHREADS, 2)
+jacobi_round_kernel(const SvdProblem* __restrict__ probs, int round, double tol, int* __restrict__ rotated,
+                    const double* __restrict__ fro2) {
+    const SvdProblem pr = probs[blockIdx.y];
+    // deflation: a column below 1e-15 * ||A||_F is rounding noise (LAPACK resolves nothing there
+    // either); rotating it against a large, exactly parallel column would only shrink it by eps
+    // per sweep until it underflows (rank-deficient product states hit exactly this)
+    const double dthr = 1e-30 * fro2[blockIdx.y];
+    const int nb = pr.nblocks;
+    if (nb < 2 || (int)blockIdx.x >= nb / 2 || round >= nb - 1) return;
+    // circle method: pair 0 = (nb-1, round); pair k = ((round+k) % (nb-1), (round-k) % (nb-1))
+    int bi, bj;
+    if (blockIdx.x == 0) { bi = nb - 1; bj = round; }
+    else { bi = (round + blockIdx.x) % (nb - 1); bj = (round - (int)blockIdx.x + (nb - 1)) % (nb - 1); }
+    if (bi > bj) { int t = bi; bi = bj; bj = t; }
+    if (bi * JB >= pr.n) return;  // padding block only
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double2* Ps = reinterpret_cast<double2*>(smem_raw);   // [JROWS][JPITCH] panel chunk
+    double2* G = Ps + JROWS * JPITCH;                     // [JP][JPITCH]
+    double2* W = G + JP * JPITCH;                         // [JP][JPITCH]
+    double2* rot = W + JP * JPITCH;                       // [JB] (c, s) + phase
+    double2* rph = rot + JB;                              // [JB] e^{i phi}
+    __shared__ int s_any, s_sweep_any;
+    __shared__ int s_cols[JP];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid < JP) s_cols[tid] = panel_col(tid, bi, bj, pr.n);
+    if (tid == 0) s_any = 0;
+    for (int i = tid; i < JP * JPITCH; i += JTHREADS) { G[i] = make_double2(0, 0); W[i] = make_double2(0, 0); }
+    __syncthreads();
+
+    // ---------------- phase 1: G = P^H P (each warp takes rows warp*8.. of every chunk) -----------
+    double gr[4][4][2], gi[4][4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) gr[i][j][0] = gr[i][j][1] = gi[i][j][0] = gi[i][j][1] = 0.0;
+    auto load_chunk = [&](const double2* base, int ld, int r0, int nrows) {
+        // coalesced along rows: 64 rows x 32 columns, thread -> (row = tid % 64, columns tid/64 + 4*i)
+        const int r = tid & (JROWS - 1);
+        for (int c = tid / JROWS; c < JP; c += JTHREADS / JROWS) {
+            const int col = s_cols[c];
+            double2 v = make_double2(0, 0);
+            if (col >= 0 && r0 + r < nrows) v = base[(size_t)col * ld + r0 + r];
+            Ps[r * JPITCH + c] = v;
+        }
+    };
+    for (int r0 = 0; r0 < pr.m; r0 += JROWS) {
+        load_chunk(pr.A, pr.m, r0, pr.m);
+        __syncthreads();
+        // warp w owns k-rows [8w, 8w+8) of the chunk: two k4 steps
+#pragma unroll
+        for (int k4 = 0; k4 < 2; ++k4) {
+            const int kr = warp * 8 + k4 * 4 + (lane & 3);
+            double2 f[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) f[i] = Ps[kr * JPITCH + i * 8 + (lane >> 2)];
+            // G[i][j] += conj(P[k][i]) * P[k][j]:  re = ar*br + ai*bi ; im = ar*bi - ai*br
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (j < i) continue;  // Hermitian: upper block triangle only
+                    dmma(gr[i][j][0], gr[i][j][1], f[i].x, f[j].x);
+                    dmma(gr[i][j][0], gr[i][j][1], f[i].y, f[j].y);
+                    dmma(gi[i][j][0], gi[i][j][1], f[i].x, f[j].y);
+                    dmma(gi[i][j][0], gi[i][j][1], -f[i].y, f[j].x);
+                }
+        }
+        __syncthreads();
+    }
+    // cross-warp reduction into G (shared atomics on doubles; 8 warps)
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (j < i) continue;
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int row = i * 8 + (lane >> 2), col = j * 8 + 2 * (lane & 3) + q;
+                atomicAdd(&G[row * JPITCH + col].x, gr[i][j][q]);
+                atomicAdd(&G[row * JPITCH + col].y, gi[i][j][q]);
+            }
+        }
+    __syncthreads();
+    // mirror the strictly-lower block triangle, set W = I
+    for (int e = tid; e < JP * JP; e += JTHREADS) {
+        const int r = e / JP, c = e % JP;
+        if ((r >> 3) > (c >> 3)) { const double2 v = G[c * JPITCH + r]; G[r * JPITCH + c] = make_double2(v.x, -v.y); }
+        if (r == c) W[r * JPITCH + c] = make_double2(1.0, 0.0);
+    }
+    __syncthreads();
+
+    // ---------------- phase 2: Hermitian Jacobi on G, W accumulates the rotations -------------------
+    for (int sweep = 0; sweep < 12; ++sweep) {
+        if (tid == 0) s_sweep_any = 0;
+        __syncthreads();
+        for (int step = 0; step < JP - 1; ++step) {
+            if (tid < JB) {
+                int p, q;
+                if (tid == 0) { p = JP - 1; q = step; }
+                else { p = (step + tid) % (JP - 1); q = (step - tid + (JP - 1)) % (JP - 1); }
+                if (p > q) { int t = p; p = q; q = t; }
+                const double alpha = G[p * JPITCH + p].x, beta = G[q * JPITCH + q].x;
+                const double2 g = G[p * JPITCH + q];
+                const double ag = hypot(g.x, g.y);
+                double c = 1.0, s = 0.0;
+                double2 ph = make_double2(1.0, 0.0);
+                const bool real_cols = s_cols[p] >= 0 && s_cols[q] >= 0;  // never touch padding slots
+                if (!real_cols) {
+                    // identity
+                } else if (ag > tol * sqrt(fabs(alpha) * fabs(beta)) && ag > 0.0 && alpha > dthr && beta > dthr) {
+                    ph = make_double2(g.x / ag, g.y / ag);
+                    const double zeta = (beta - alpha) / (2.0 * ag);
+                    double t = 1.0 / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+                    if (zeta < 0) t = -t;
+                    c = 1.0 / sqrt(1.0 + t * t);
+                    s = c * t;
+                    // de Rijk ordering: keep the larger diagonal entry at the lower index
+                    const double ap = alpha - t * ag, bq = beta + t * ag;
+                    if (ap < bq) { const double c2 = s, s2 = -c; c = c2; s = s2; }
+                    s_sweep_any = 1;
+                } else if (alpha < beta && beta > dthr) {
+                    c = 0.0; s = -1.0;  // pure swap: a significant column moves in front of a smaller one
+                    s_sweep_any = 1;
+                }
+                rot[tid] = make_double2(c, s);
+                rph[tid] = ph;
+                // store the pair for the appliers
+                reinterpret_cast<int*>(rph + JB)[2 * tid] = p;
+                reinterpret_cast<int*>(rph + JB)[2 * tid + 1] = q;
+            }
+            __syncthreads();
+            const int* pq = reinterpret_cast<const int*>(rph + JB);
+            // column rotations on G and W: x_p' = c x_p - s e^{-i phi} x_q ; x_q' = s e^{i phi} x_p + c x_q
+            for (int e = tid; e < 2 * JP * JB; e += JTHREADS) {
+                const int which = e / (JP * JB), r = (e % (JP * JB)) / JB, k = e % JB;
+                const double c = rot[k].x, s = rot[k].y;
+                if (c == 1.0 && s == 0.0) continue;
+                const double2 ph = rph[k];
+                double2* Mx = which ? W : G;
+                const int p = pq[2 * k], q = pq[2 * k + 1];
+                const double2 xp = Mx[r * JPITCH + p], xq = Mx[r * JPITCH + q];
+                // e^{-i phi} xq and e^{i phi} xp
+                const double2 eq = make_double2(ph.x * xq.x + ph.y * xq.y, ph.x * xq.y - ph.y * xq.x);
+                const double2 ep = make_double2(ph.x * xp.x - ph.y * xp.y, ph.x * xp.y + ph.y * xp.x);
+                Mx[r * JPITCH + p] = make_double2(c * xp.x - s * eq.x, c * xp.y - s * eq.y);
+                Mx[r * JPITCH + q] = make_double2(s * ep.x + c * xq.x, s * ep.y + c * xq.y);
+            }
+            __syncthreads();
+            // row rotations on G (J^H from the left): y_p' = c y_p - s e^{i phi} y_q ; y_q' = s e^{-i phi} y_p + c y_q
+            for (int e = tid; e < JP * JB; e += JTHREADS) {
+                const int col = e / JB, k = e % JB;
+                const double c = rot[k].x, s = rot[k].y;
+                if (c == 1.0 && s == 0.0) continue;
+                const double2 ph = rph[k];
+                const int p = pq[2 * k], q = pq[2 * k + 1];
+                const double2 yp = G[p * JPITCH + col], yq = G[q * JPITCH + col];
+                const double2 eq = make_double2(ph.x * yq.x - ph.y * yq.y, ph.x * yq.y + ph.y * yq.x);
+                const double2 ep = make_double2(ph.x * yp.x + ph.y * yp.y, ph.x * yp.y - ph.y * yp.x);
+                G[p * JPITCH + col] = make_double2(c * yp.x - s * eq.x, c * yp.y - s * eq.y);
+                G[q * JPITCH + col] = make_double2(s * ep.x + c * yq.x, s * ep.y + c * yq.y);
+            }
+            __syncthreads();
+        }
+        const int any_now = s_sweep_any;
+        if (any_now && tid == 0) s_any = 1;
+        __syncthreads();
+        if (!any_now) break;
+    }
+    if (!s_any) return;  // panel already orthogonal and ordered: nothing to update
+    if (tid == 0) rotated[blockIdx.y] = 1;
+
+    // ---------------- phase 3: P <- P W for the A panel and the V panel ---------------------------------
+    // warp w owns rows [8w, 8w+8) of each 64-row chunk: C(8 x 32) = P(8 x 32) W(32 x 32)
+    for (int which = 0; which < 2; ++which) {
+        double2* base = which ? pr.V : pr.A;
+        const int nrows = which ? pr.n : pr.m;
+        for (int r0 = 0; r0 < nrows; r0 += JROWS) {
+            __syncthreads();
+            load_chunk(base, nrows, r0, nrows);
+            __syncthreads();
+            double cr[4][2], ci[4][2];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) cr[j][0] = cr[j][1] = ci[j][0] = ci[j][1] = 0.0;
+#pragma unroll
+            for (int k4 = 0; k4 < JP / 4; ++k4) {
+                const double2 a = Ps[(warp * 8 + (lane >> 2)) * JPITCH + k4 * 4 + (lane & 3)];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const double2 b = W[(k4 * 4 + (lane & 3)) * JPITCH + j * 8 + (lane >> 2)];
+                    dmma(cr[j][0], cr[j][1], a.x, b.x);
+                    dmma(cr[j][0], cr[j][1], -a.y, b.y);
+                    dmma(ci[j][0], ci[j][1], a.x, b.y);
+                    dmma(ci[j][0], ci[j][1], a.y, b.x);
+                }
+            }
+            const int row = r0 + warp * 8 + (lane >> 2);
+            if (row < nrows) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        const int col = s_cols[j * 8 + 2 * (lane & 3) + q];
+                        if (col >= 0) base[(size_t)col * nrows + row] = make_double2(cr[j][q], ci[j][q]);
+                    }
+            }
+        }
+    }
+}
+
+// fro2[b] = ||A_b||_F^2
+__global__ void fro_norm_kernel(const SvdProblem* probs, double* fro2) {
+    const SvdProblem pr = probs[blockIdx.y];
+    const size_t tot = (size_t)pr.m * pr.n;
+    double s = 0;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < tot; e += (size_t)gridDim.x * blockDim.x) {
+        const double2 v = pr.A[e];
+        s += v.x * v.x + v.y * v.y;
+    }
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&fro2[blockIdx.y], s);
+}
+
+__global__ void set_identity_kernel(const SvdProblem* probs) {
+    const SvdProblem pr = probs[blockIdx.y];
+    const size_t nn = (size_t)pr.n * pr.n;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < nn; e += (size_t)gridDim.x * blockDim.x)
+        pr.V[e] = make_double2((e % pr.n) == (e / pr.n) ? 1.0 : 0.0, 0.0);
+}
+
+// sigma_j = ||a_j||  (one warp per column)
+__global__ void column_norms_kernel(const SvdProblem* probs, double* const* sig) {
+    const SvdProblem pr = probs[blockIdx.y];
+    const int lane = threadIdx.x & 31;
+    for (int col = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); col < pr.n; col += gridDim.x * (blockDim.x >> 5)) {
+        const double2* a = pr.A + (size_t)col * pr.m;
+        // scaled accumulation is unnecessary here: |a| <= ||A||_F which the callers keep O(1..1e150)
+        double s = 0;
+        for (int r = lane; r < pr.m; r += 32) s += a[r].x * a[r].x + a[r].y * a[r].y;
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) sig[blockIdx.y][col] = sqrt(s);
+    }
+}
+
+struct FinishArgs {
+    double2* U;    // m x r
+    double* S;     // r
+    double2* Vh;   // r x n
+    int64_t* k;    // kept count
+    double* disc;  // 2-norm of the discarded tail (may be null)
+    int transposed;  // the Jacobi ran on A^H: U <-> V roles swap
+    int m0, n0;      // caller's shape
+};
+
+// rank[j] = position of sigma_j in descending order (stable); S sorted; truncation rule (K6).
+__global__ void sort_truncate_kernel(const SvdProblem* probs, double* const* sig, int* const* rank,
+                                     const FinishArgs* fin, double er, long long maxdim) {
+    const SvdProblem pr = probs[blockIdx.x];
+    const FinishArgs f = fin[blockIdx.x];
+    const double* s = sig[blockIdx.x];
+    int* rk = rank[blockIdx.x];
+    const int n = pr.n;
+    for (int j = threadIdx.x; j < n; j += blockDim.x) {
+        const double sj = s[j];
+        int r = 0;
+        for (int k = 0; k < n; ++k) r += (s[k] > sj) || (s[k] == sj && k < j);
+        rk[j] = r;
+        f.S[r] = sj;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        // src/svd.jl:29-33: cumsum of the reversed squares, first tail > er (strict)
+        long long k = 0;
+        if (er < 0) k = n;
+        else {
+            double acc = 0;
+            for (int r = 1; r <= n; ++r) {
+                const double v = f.S[n - r];
+                acc += v * v;
+                if (sqrt(acc) > er) { k = n - r + 1; break; }
+            }
+        }
+        if (maxdim > 0 && k > maxdim) k = maxdim;
+        double d = 0;
+        for (int j = n - 1; j >= (int)k; --j) d += f.S[j] * f.S[j];
+        *f.k = k;
+        if (f.disc) *f.disc = sqrt(d);
+    }
+}
+
+// U[:, rank[j]] = a_j / sigma_j ; Vh[rank[j], :] = conj(V[:, j])   (roles swapped if transposed)
+__global__ void scatter_factors_kernel(const SvdProblem* probs, double* const* sig, int* const* rank, const FinishArgs* fin) {
+    const SvdProblem pr = probs[blockIdx.y];
+    const FinishArgs f = fin[blockIdx.y];
+    const int n = pr.n, m = pr.m;
+    const int* rk = rank[blockIdx.y];
+    const double* s = sig[blockIdx.y];
+    const size_t tot = (size_t)(m + n) * n;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < tot; e += (size_t)gridDim.x * blockDim.x) {
+        const int j = (int)(e / (m + n)), r = (int)(e % (m + n)), dst = rk[j];
+        if (r < m) {
+            const double sj = s[j];
+            double2 v = pr.A[(size_t)j * m + r];
+            if (sj > 0) { v.x /= sj; v.y /= sj; } else { v = make_double2(0, 0); }
+            if (!f.transposed) f.U[(size_t)dst * m + r] = v;              // U is m x n
+            else f.Vh[(size_t)r * n + dst] = make_double2(v.x, -v.y);     // Vh (n x m0=m) row dst = conj(column)
+        } else {
+            const int rr = r - m;
+            const double2 v = pr.V[(size_t)j * n + rr];
+            if (!f.transposed) f.Vh[(size_t)rr * n + dst] = make_double2(v.x, -v.y);  // Vh is n x n
+            else f.U[(size_t)dst * n + rr] = v;                                        // U (m0=n x n)
+        }
+    }
+}
+
+// B = A^H (n x m from m x n)
+__global__ void conj_transpose_kernel(const double2* __restrict__ A, double2* __restrict__ B, int m, int n) {
+    __shared__ double2 t[32][33];
+    const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int r = bx + threadIdx.x, c = by + j;
+        if (r < m && c < n) t[j][threadIdx.x] = A[(size_t)c * m + r];
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int r = by + threadIdx.x, c = bx + j;  // B[r, c] = conj(A[c, r])
+        if (r < n && c < m) { const double2 v = t[threadIdx.x][j]; B[(size_t)c * n + r] = make_double2(v.x, -v.y); }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host driver (device-resident inputs): batch of problems
+// ---------------------------------------------------------------------------------------------
+struct SvdWork {
+    void* dev = nullptr;
+    size_t bytes = 0;
+    void* host = nullptr;
+    size_t hbytes = 0;
+};
+static SvdWork g_work;
+
+static int work_reserve(size_t bytes, size_t hbytes) {
+    if (bytes > g_work.bytes) {
+        cudaStreamSynchronize(stream());
+        if (g_work.dev) cudaFree(g_work.dev);
+        g_work.bytes = std::max(bytes, (size_t)1 << 22);
+        if (cudaMalloc(&g_work.dev, g_work.bytes) != cudaSuccess) { g_work.dev = nullptr; g_work.bytes = 0; return fail(QTN_ENOMEM, "SVD workspace of %zu bytes", bytes); }
+    }
+    if (hbytes > g_work.hbytes) {
+        cudaStreamSynchronize(stream());
+        if (g_work.host) cudaFreeHost(g_work.host);
+        g_work.hbytes = std::max(hbytes, (size_t)1 << 16);
+        if (cudaMallocHost(&g_work.host, g_work.hbytes) != cudaSuccess) { g_work.host = nullptr; g_work.hbytes = 0; return fail(QTN_ENOMEM, "SVD pinned workspace"); }
+    }
+    return QTN_OK;
+}
+
+struct SvdJob {
+    double2* A;  // m0 x n0 device, overwritten
+    int64_t m0, n0;
+    double2* U;  // m0 x r
+    double* S;   // r
+    double2* Vh; // r x n0
+};
+
+// Runs the batch; k_out / disc_out are host arrays (batch).  Synchronises the stream.
+int svd_batched_device(int batch, const SvdJob* jobs, double er, int64_t maxdim, int64_t* k_out, double* disc_out,
+                       int* sweeps_out) {
+    if (batch <= 0) return QTN_OK;
+    cudaStream_t st = stream();
+    // workspace layout (device): per problem: [At (if transposed) m*n] [V n*n] [sig n] [rank n]
+    size_t dev_bytes = 0;
+    std::vector<size_t> offAt(batch), offV(batch), offSig(batch), offRank(batch);
+    std::vector<int> tr(batch);
+    int maxn = 0, maxm = 0;
+    for (int b = 0; b < batch; ++b) {
+        const int64_t m0 = jobs[b].m0, n0 = jobs[b].n0;
+        if (m0 < 1 || n0 < 1) return fail(QTN_EINVAL, "svd: empty matrix");
+        if (m0 > 32768 || n0 > 32768) return fail(QTN_EINVAL, "svd: matrix too large");
+        tr[b] = m0 < n0;
+        const int64_t m = tr[b] ? n0 : m0, n = tr[b] ? m0 : n0;
+        auto al = [&](size_t bytes) { size_t o = dev_bytes; dev_bytes += (bytes + 255) / 256 * 256; return o; };
+        offAt[b] = tr[b] ? al((size_t)m * n * 16) : 0;
+        offV[b] = al((size_t)n * n * 16);
+        offSig[b] = al((size_t)n * 8);
+        offRank[b] = al((size_t)n * 4);
+        maxn = std::max<int>(maxn, (int)n);
+        maxm = std::max<int>(maxm, (int)m);
+    }
+    size_t tab = dev_bytes;
+    size_t tab_bytes = (size_t)batch * (sizeof(SvdProblem) + sizeof(FinishArgs) + 2 * sizeof(void*) + 8 + 8 + 8 + 4) + 1024;
+    dev_bytes += (tab_bytes + 255) / 256 * 256;
+    int rc = work_reserve(dev_bytes, tab_bytes);
+    if (rc) return rc;
+    char* base = (char*)g_work.dev;
+    // host-side table image
+    CUDA_TRY(cudaStreamSynchronize(st));
+    char* h = (char*)g_work.host;
+    SvdProblem* hp = (SvdProblem*)h;
+    FinishArgs* hf = (FinishArgs*)(hp + batch);
+    double** hsig = (double**)(hf + batch);
+    int** hrank = (int**)(hsig + batch);
+    int64_t* hk = (int64_t*)(hrank + batch);
+    double* hdisc = (double*)(hk + batch);
+    double* hfro = hdisc + batch;
+    int* hrot = (int*)(hfro + batch);
+    char* dtab = base + tab;
+    auto dptr = [&](void* hostp) { return dtab + ((char*)hostp - h); };
+    for (int b = 0; b < batch; ++b) {
+        const int64_t m0 = jobs[b].m0, n0 = jobs[b].n0;
+        const int m = (int)(tr[b] ? n0 : m0), n = (int)(tr[b] ? m0 : n0);
+        hp[b].A = tr[b] ? (double2*)(base + offAt[b]) : jobs[b].A;
+        hp[b].V = (double2*)(base + offV[b]);
+        hp[b].m = m;
+        hp[b].n = n;
+        int nbk = (n + JB - 1) / JB;
+        if (nbk & 1) ++nbk;
+        hp[b].nblocks = nbk;
+        hf[b].U = jobs[b].U; hf[b].S = jobs[b].S; hf[b].Vh = jobs[b].Vh;
+        hf[b].k = (int64_t*)dptr(hk + b);
+        hf[b].disc = (double*)dptr(hdisc + b);
+        hf[b].transposed = tr[b];
+        hf[b].m0 = (int)m0; hf[b].n0 = (int)n0;
+        hsig[b] = (double*)(base + offSig[b]);
+        hrank[b] = (int*)(base + offRank[b]);
+        hrot[b] = 0;
+        hfro[b] = 0.0;
+    }
+    CUDA_TRY(cudaMemcpyAsync(dtab, h, tab_bytes - 1024, cudaMemcpyHostToDevice, st));
+    const SvdProblem* dp = (const SvdProblem*)dtab;
+    const FinishArgs* df = (const FinishArgs*)dptr(hf);
+    double* const* dsig = (double* const*)dptr(hsig);
+    int* const* drank = (int* const*)dptr(hrank);
+    int* drot = (int*)dptr(hrot);
+    double* dfro = (double*)dptr(hfro);
+    for (int b = 0; b < batch; ++b)
+        if (tr[b]) {
+            dim3 g((unsigned)((jobs[b].m0 + 31) / 32), (unsigned)((jobs[b].n0 + 31) / 32));
+            conj_transpose_kernel<<<g, dim3(32, 8), 0, st>>>(jobs[b].A, hp[b].A, (int)jobs[b].m0, (int)jobs[b].n0);
+            count_launch(1);
+        }
+    set_identity_kernel<<<dim3(std::min(148 * 4, (maxn * maxn + 255) / 256), batch), 256, 0, st>>>(dp);
+    fro_norm_kernel<<<dim3(std::min(148, (maxn * maxm + 255) / 256), batch), 256, 0, st>>>(dp, dfro);
+    count_launch(2);
+    const size_t smem = (size_t)(JROWS * JPITCH + 2 * JP * JPITCH + 2 * JB) * 16 + JB * 8 + 64;
+    static bool attr = false;
+    if (!attr) { CUDA_TRY(cudaFuncSetAttribute(jacobi_round_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+    int max_nb = (maxn + JB - 1) / JB;
+    if (max_nb & 1) ++max_nb;
+    const double tol = 1e-15 * std::sqrt((double)std::max(maxm, 1)) * 0.5 + 2.3e-16;
+    int sweeps = 0;
+    const int kMaxSweeps = 40;
+    if (max_nb >= 2) {
+        for (; sweeps < kMaxSweeps; ++sweeps) {
+            CUDA_TRY(cudaMemsetAsync(drot, 0, (size_t)batch * 4, st));
+            for (int round = 0; round < max_nb - 1; ++round)
+                jacobi_round_kernel<<<dim3(max_nb / 2, batch), JTHREADS, smem, st>>>(dp, round, tol, drot, dfro);
+            count_launch(max_nb - 1);
+            CUDA_TRY(cudaMemcpyAsync(hrot, drot, (size_t)batch * 4, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
+            bool any = false;
+            for (int b = 0; b < batch; ++b) any |= hrot[b] != 0;
+            if (!any) { ++sweeps; break; }
+        }
+    }
+    column_norms_kernel<<<dim3(std::min(148 * 2, (maxn + 7) / 8), batch), 256, 0, st>>>(dp, dsig);
+    sort_truncate_kernel<<<batch, 256, 0, st>>>(dp, dsig, drank, df, er, (long long)maxdim);
+    scatter_factors_kernel<<<dim3(148 * 2, batch), 256, 0, st>>>(dp, dsig, drank, df);
+    count_launch(3);
+    CUDA_TRY(cudaMemcpyAsync(hk, dptr(hk), (size_t)batch * 16, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    CUDA_TRY(cudaGetLastError());
+    for (int b = 0; b < batch; ++b) {
+        if (k_out) k_out[b] = hk[b];
+        if (disc_out) disc_out[b] = hdisc[b];
+    }
+    if (sweeps_out) *sweeps_out = sweeps;
+    if (sweeps >= kMaxSweeps) return fail(QTN_ECUDA, "Jacobi SVD did not converge in %d sweeps", kMaxSweeps);
+    return QTN_OK;
+}
+
+}  // namespace qtn
+
+using namespace qtn;
+
+extern "C" {
+
+int qtn_svd_trunc_device(void* dev_a, int64_t m, int64_t n, double er, int64_t maxdim, void* dev_u, double* dev_s,
+                         void* dev_vh, int64_t* k_out, int32_t* sweeps_out) {
+    int rc = device_ready();
+    if (rc) return rc;
+    if (!dev_a || !dev_u || !dev_s || !dev_vh) return fail(QTN_EINVAL, "qtn_svd_trunc_device: null argument");
+    SvdJob job{(double2*)dev_a, m, n, (double2*)dev_u, dev_s, (double2*)dev_vh};
+    int sw = 0;
+    rc = svd_batched_device(1, &job, er, maxdim, k_out, nullptr, &sw);
+    if (sweeps_out) *sweeps_out = sw;
+    return rc;
+}
+
+int qtn_svd_trunc_batched(int32_t batch, const void* const* host_a, const int64_t* m, const int64_t* n, double er,
+                          int64_t maxdim, void* const* host_u, double* const* host_s, void* const* host_vh,
+                          int64_t* k_out) {
+    int rc = device_ready();
+    if (rc) return rc;
+    if (batch < 0 || !host_a || !m || !n || !host_u || !host_s || !host_vh) return fail(QTN_EINVAL, "qtn_svd_trunc_batched: null argument");
+    if (batch == 0) return QTN_OK;
+    cudaStream_t st = stream();
+    size_t total = 0;
+    std::vector<size_t> oA(batch), oU(batch), oS(batch), oV(batch);
+    for (int b = 0; b < batch; ++b) {
+        if (m[b] < 1 || n[b] < 1) return fail(QTN_EINVAL, "qtn_svd_trunc: matrix %d is empty", b);
+        const int64_t r = std::min(m[b], n[b]);
+        auto al = [&](size_t bytes) { size_t o = total; total += (bytes + 255) / 256 * 256; return o; };
+        oA[b] = al((size_t)m[b] * n[b] * 16);
+        oU[b] = al((size_t)m[b] * r * 16);
+        oS[b] = al((size_t)r * 8);
+        oV[b] = al((size_t)r * n[b] * 16);
+    }
+    char* buf = nullptr;
+    if (cudaMalloc((void**)&buf, total) != cudaSuccess) return fail(QTN_ENOMEM, "qtn_svd_trunc: cudaMalloc(%zu) failed", total);
+    std::vector<SvdJob> jobs(batch);
+    for (int b = 0; b < batch; ++b) {
+        cudaMemcpyAsync(buf + oA[b], host_a[b], (size_t)m[b] * n[b] * 16, cudaMemcpyHostToDevice, st);
+        jobs[b] = SvdJob{(double2*)(buf + oA[b]), m[b], n[b], (double2*)(buf + oU[b]), (double*)(buf + oS[b]), (double2*)(buf + oV[b])};
+    }
+    rc = svd_batched_device(batch, jobs.data(), er, maxdim, k_out, nullptr, nullptr);
+    if (!rc) {
+        for (int b = 0; b < batch; ++b) {
+            const int64_t r = std::min(m[b], n[b]);
+            cudaMemcpyAsync(host_u[b], buf + oU[b], (size_t)m[b] * r * 16, cudaMemcpyDeviceToHost, st);
+            cudaMemcpyAsync(host_s[b], buf + oS[b], (size_t)r * 8, cudaMemcpyDeviceToHost, st);
+            cudaMemcpyAsync(host_vh[b], buf + oV[b], (size_t)r * n[b] * 16, cudaMemcpyDeviceToHost, st);
+        }
+        cudaError_t e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) rc = fail(QTN_ECUDA, "qtn_svd_trunc: %s", cudaGetErrorString(e));
+    }
+    cudaFree(buf);
+    return rc;
+}
+
+int qtn_svd_trunc(const void* host_a, int64_t m, int64_t n, double er, int64_t maxdim, void* host_u, double* host_s,
+                  void* host_vh, int64_t* k_out) {
+    const void* a[1] = {host_a};
+    void* u[1] = {host_u};
+    double* s[1] = {host_s};
+    void* v[1] = {host_vh};
+    return qtn_svd_trunc_batched(1, a, &m, &n, er, maxdim, u, s, v, k_out);
+}
+
+}  // extern "C"

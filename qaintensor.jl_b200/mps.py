@@ -1,0 +1,184 @@
+"""``MPS`` and friends (src/mps.jl, src/switch.jl).  Every SVD goes through the library's
+Jacobi SVD (``qtn_svd_trunc``), every two-site contraction through ``qtn_contract_svd``."""
+import numpy as np
+
+from .svd import contract_svd, svd
+from .tensor_network import Summation, Tensor, TensorNetwork, is_power_two
+
+_E_FIRST = "Tensor objects first leg must contract with last leg of previous Tensor object"
+_E_LAST = "Tensor objects last leg must contract with first leg of next Tensor object"
+_E_LEGS = "Each Tensor object in MPS form can only have 2 or 3 legs"
+
+
+def _check(tensors, contractions):
+    for c in contractions:
+        if len(c.idx) != 2:
+            raise AssertionError("MPS contractions join exactly two legs")
+        if c.idx[0][1] != tensors[c.idx[0][0] - 1].ndims():
+            raise ValueError(_E_FIRST)
+        if c.idx[1][1] != 1:
+            raise ValueError(_E_LAST)
+
+
+class MPS(TensorNetwork):
+    """``MPS <: TensorNetwork`` with the validating constructor of src/mps.jl:7-29."""
+
+    def __init__(self, tensors, contractions=None, openidx=None):
+        if contractions is None:  # MPS(psi::Vector{ComplexF64})
+            built = _from_vector(tensors)
+            tensors, contractions, openidx = built
+        _check(tensors, contractions)
+        for t in tensors:
+            if t.ndims() not in (2, 3):
+                raise ValueError(_E_LEGS)
+        self.tensors = list(tensors)
+        self.contractions = list(contractions)
+        self.openidx = [(int(a), int(b)) for (a, b) in openidx]
+
+    def copy(self):  # shallow (src/mps.jl:203)
+        return MPS(list(self.tensors), list(self.contractions), list(self.openidx))
+
+
+def check_mps(mps):  # src/mps.jl:37-48
+    for t in mps.tensors:
+        if t.ndims() not in (2, 3):
+            raise ValueError(_E_LEGS)
+    _check(mps.tensors, mps.contractions)
+
+
+def _from_vector(psi):  # src/mps.jl:55-89: sequential thin SVD, no truncation
+    psi = np.asarray(psi, dtype=np.complex128).reshape(-1)
+    if not is_power_two(psi.size):
+        raise ValueError("Input state must have length 2^N")
+    M = psi.size.bit_length() - 1
+    tensors, contractions, openidx = [], [], [(1, 1)]
+    U, S, Vh = svd(np.reshape(psi, (2, -1), order="F"))
+    tensors.append(Tensor(U))
+    rest = S[:, None] * Vh
+    lbond, lastleg = len(S), 2
+    for bit in range(2, M):
+        U, S, Vh = svd(np.reshape(rest, (lbond * 2, -1), order="F"))
+        tensors.append(Tensor(np.reshape(U, (lbond, 2, len(S)), order="F")))
+        contractions.append(Summation([(bit - 1, lastleg), (bit, 1)]))
+        openidx.append((bit, 2))
+        rest = S[:, None] * Vh
+        lbond, lastleg = len(S), 3
+    tensors.append(Tensor(rest))
+    contractions.append(Summation([(M - 1, lastleg), (M, 1)]))
+    openidx.append((M, 2))
+    return tensors, contractions, openidx
+
+
+def OpenMPS(T, N=None):  # src/mps.jl:99-121
+    T = [T] * N if N is not None else list(T)
+    if any(t.ndims() != 3 for t in T):
+        raise ValueError("Tensors must have 3 legs")
+    n = len(T)
+    return MPS(T, [Summation([(i, 3), (i + 1, 1)]) for i in range(1, n)],
+               [(1, 1)] + [(i, 2) for i in range(1, n + 1)] + [(n, 3)])
+
+
+def ClosedMPS(T, Tmiddle=None, Tend=None, N=None):  # src/mps.jl:130-155
+    T = [T] + [Tmiddle] * (N - 2) + [Tend] if Tmiddle is not None else list(T)
+    n = len(T)
+    if T[0].ndims() != 2:
+        raise ValueError("First tensor must have 2 legs")
+    if any(t.ndims() != 3 for t in T[1:-1]):
+        raise ValueError("Tensors must have 3 legs, except the first and last one")
+    if T[-1].ndims() != 2:
+        raise ValueError("Last tensor must have 2 legs")
+    cons = [Summation([(1, 2), (2, 1)])] + [Summation([(i, 3), (i + 1, 1)]) for i in range(2, n)]
+    return MPS(T, cons, [(1, 1)] + [(i, 2) for i in range(2, n + 1)])
+
+
+def PeriodicMPS(T, N=None):  # src/mps.jl:163-182
+    T = [T] * N if N is not None else list(T)
+    if any(t.ndims() != 3 for t in T):
+        raise AssertionError("PeriodicMPS tensors must have 3 legs")
+    n = len(T)
+    cons = [Summation([(i, 3), (i + 1, 1)]) for i in range(1, n)] + [Summation([(n, 3), (1, 1)])]
+    return MPS(T, cons, [(i, 2) for i in range(1, n + 1)])
+
+
+def contract_svd_mps(tn, er=0.0):  # src/mps.jl:190-201
+    if not er >= 0:
+        raise ValueError("Error must be positive")
+    n = len(tn.tensors)
+    periodic = (Summation([(n, 3), (1, 1)]), Summation([(1, 1), (n, 3)]))
+    if any(s in periodic for s in tn.contractions):
+        raise ValueError("Function doesn't support periodic boundary conditions for now")
+    acc = tn.tensors[0]
+    for j in range(1, n):
+        acc = contract_svd(acc, tn.tensors[j], (acc.ndims(), 1), er=er)
+    return acc.data
+
+
+# ---- src/switch.jl ---------------------------------------------------------------------
+def _switch_adjacent(mps, i):  # switch!(mps, i) src/switch.jl:18-56
+    from .contract import permutedims
+    if i < 1 or i + 1 > len(mps.tensors):
+        raise IndexError("BoundsError: attempt to access %d-element MPS at index %d" % (len(mps.tensors), i + 1))
+    T1, T2 = mps.tensors[i - 1], mps.tensors[i]
+    d1, d2 = T1.size(), T2.size()
+    T = contract_svd(T1, T2, (T1.ndims(), 1)).data
+    if T1.ndims() == 2:
+        T = np.reshape(permutedims(T, [2, 1, 3]), (2, 2 * d2[-1]), order="F")
+    elif T2.ndims() == 2:
+        T = np.reshape(permutedims(T, [1, 3, 2]), (2 * d1[0], 2), order="F")
+    else:
+        T = np.reshape(permutedims(T, [1, 3, 2, 4]), (2 * d1[0], 2 * d2[-1]), order="F")
+    U, S, Vh = svd(T)
+    bond = len(S)
+    V = S[:, None] * Vh
+    if T1.ndims() == 2:
+        U = np.reshape(U, (2, bond), order="F")
+        V = np.reshape(V, (bond, 2, d2[-1]), order="F")
+    elif T2.ndims() == 2:
+        U = np.reshape(U, (d1[0], 2, bond), order="F")
+    else:
+        U = np.reshape(U, (d1[0], 2, bond), order="F")
+        V = np.reshape(V, (bond, 2, d2[-1]), order="F")
+    mps.tensors[i - 1] = Tensor(U)
+    mps.tensors[i] = Tensor(V)
+
+
+def switch(mps, i, j=None):
+    """``switch!``: adjacent swap (one index), wire swap (two), or a list of (i, j) tuples."""
+    if isinstance(i, (list, tuple)) and j is None:
+        check_mps(mps)
+        for (a, b) in i:
+            switch(mps, a, b)
+        return
+    if j is None:
+        return _switch_adjacent(mps, i)
+    check_mps(mps)
+    if not (i > 0 and j > 0):
+        raise ValueError("Wire indices `i` and `j` must be positive")
+    n = len(mps.tensors)
+    if not (i <= n and j <= n):
+        raise ValueError("Indices to swap `i` and `j` must be less than or equal to the number of open wires in MPS")
+    if i == j:
+        return
+    lo, hi = sorted((n - i + 1, n - j + 1))
+    for a in range(lo, hi):
+        _switch_adjacent(mps, a)
+    for b in range(hi - 2, lo - 1, -1):
+        _switch_adjacent(mps, b)
+
+
+def permute(mps, order):  # Base.permute!(mps, order) src/switch.jl:94-106
+    check_mps(mps)
+    n = len(mps.tensors)
+    if len(order) != n:
+        raise ValueError("Given permutation must be same length as number of Tensors in MPS")
+    if len(set(order)) != len(order):
+        raise ValueError("Permutation order cannot contain repeat values")
+    if not all(x > 0 for x in order):
+        raise ValueError("Permutation order can only contain positive values")
+    if max(order) != n:
+        raise ValueError("Wire numbers in permutation order cannot exceed number of wires in MPS")
+    seq = list(range(1, n + 1))
+    for i in range(1, n + 1):
+        loc = seq.index(order[i - 1]) + 1
+        switch(mps, i, loc)
+        seq[loc - 1], seq[i - 1] = seq[i - 1], seq[loc - 1]

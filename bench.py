@@ -32,7 +32,9 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg3", choices=["cfg3", "cfg2"])
+    ap.add_argument("--workload", default="cfg3", choices=["cfg3", "cfg2", "cfg4"])
+    ap.add_argument("--chi", type=int, default=512, help="cfg4: max bond dimension")
+    ap.add_argument("--sites", type=int, default=50, help="cfg4: number of MPS sites")
     ap.add_argument("--slices-per-step", type=int, default=2)
     ap.add_argument("--max-log2", type=int, default=28, help="slice until the largest tensor has <= 2^k elements")
     ap.add_argument("--cpu-max-log2", type=int, default=26, help="slicing level of the CPU baseline sample")
@@ -126,12 +128,131 @@ def oracle_cfg2_sampler():
     return run, 1, 2.81e9
 
 
+def saturated_mps(nsites, chi, rng):
+    """Random normalised MPS with the saturated bond profile min(2^i, 2^(N-i), chi): the steady
+    state of a brickwork circuit once every bond has hit the cap."""
+    bonds = [min(2 ** min(i, nsites - i), chi) for i in range(nsites + 1)]
+    sites = []
+    for i in range(nsites):
+        a = rng.standard_normal((bonds[i], 2, bonds[i + 1])) + 1j * rng.standard_normal((bonds[i], 2, bonds[i + 1]))
+        sites.append(a / np.linalg.norm(a) * np.sqrt(bonds[i + 1]))
+    return sites
+
+
+def cfg4_name(args):
+    return "cfg4: %d-site 1D brickwork MPS, Haar 2q gates, truncated SVD er=1e-10, chi=%d" % (args.sites, args.chi)
+
+
+def cfg4_model_flops(nsites, chi):
+    """per gate theta GEMM 8*(2l)(2r)(b) + thin-SVD count 4*(14 m n^2 + 8 n^3), m >= n."""
+    bonds = [min(2 ** min(i, nsites - i), chi) for i in range(nsites + 1)]
+    tot = 0.0
+    for i in range(nsites - 1):
+        l, b, r = bonds[i], bonds[i + 1], bonds[i + 2]
+        m, n = max(2 * l, 2 * r), min(2 * l, 2 * r)
+        tot += 8.0 * (2 * l) * (2 * r) * b + 4.0 * (14.0 * m * n * n + 8.0 * n ** 3)
+    return tot
+
+
+def oracle_cfg4_sampler(args, ngates=4):
+    """CPU arm for cfg4: the oracle's gate apply (numpy GEMM + LAPACK zgesdd) on `ngates`
+    central bonds of the saturated MPS; one layer = nsites-1 such gates."""
+    from oracle import mps_sim as osim
+    rng = np.random.default_rng(20261017 + 4000)
+    sites = saturated_mps(args.sites, args.chi, rng)
+    c = args.sites // 2
+    left = [c - 2 * (ngates // 2) + 2 * j for j in range(ngates)]
+    from oracle.circuits import haar_unitary
+
+    def run(_):
+        loc = [s.copy() for s in sites]
+        osim.apply_layer(loc, left, [haar_unitary(4, rng) for _ in left], 1e-10, args.chi)
+    return run, ngates
+
+
+def run_reference_cfg4(args):
+    run, ng = oracle_cfg4_sampler(args)
+    for i in range(min(args.warmup, 1)):
+        run(i)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        run(i)
+    dt = time.perf_counter() - t0
+    val = args.steps * ng / (args.sites - 1) / dt
+    line = {"impl": "reference", "metric": "MPS brickwork layers/s", "value": val, "unit": "layers/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": cfg4_name(args), "note": "oracle port (numpy zgemm + LAPACK zgesdd); each step = %d central gates, "
+                       "value = gates/(sites-1)/time" % ng},
+            "cpu_baseline": {"value": val, "unit": "layers/s", "cores": cpu_threads(), "kind": "port",
+                             "sample": "%d of %d gates of one layer per step" % (ng, args.sites - 1)},
+            "e2e": {"value": val, "unit": "layers/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def run_cfg4(args, q, _lib, torch, ext):
+    """MPS path (single GPU: it does not shard -- replicas only)."""
+    rng = np.random.default_rng(20261017 + 4000)
+    N, chi = args.sites, args.chi
+    mps = q.DeviceMPS(saturated_mps(N, chi, rng), chi)
+    halves = [q.brickwork_layer_sites(N, 0), q.brickwork_layer_sites(N, 1)]
+
+    def layer():
+        for h in halves:
+            mps.apply_layer(h, [q.circuits.haar_unitary(4, rng) for _ in h], er=1e-10, maxdim=chi)
+    for _ in range(args.warmup):
+        layer()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
+    _lib.launch_count(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(ext)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        layer()
+    e1.record(ext)
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    ms = e0.elapsed_time(e1)
+    launches = _lib.launch_count(True)
+    clocks = sampler.stop()
+    lb, rb = mps.bonds()
+    flops = cfg4_model_flops(N, chi)
+    dmma_peak = _lib.dmma_peak_tflops()
+    ach = flops * args.steps / (ms * 1e-3) / 1e12
+    cpu = None
+    if not args.no_cpu_baseline:
+        run, ng = oracle_cfg4_sampler(args)
+        t1 = time.perf_counter()
+        run(0)
+        cdt = time.perf_counter() - t1
+        cpu = {"value": ng / (N - 1) / cdt, "unit": "layers/s", "cores": cpu_threads(), "kind": "port",
+               "sample": "%d of %d gates of one layer (numpy zgemm + LAPACK zgesdd), %.2f s" % (ng, N - 1, cdt)}
+    line = {"metric": "MPS brickwork layers/s", "value": args.steps / (ms * 1e-3), "unit": "layers/s", "n_gpus": 1, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": cfg4_name(args), "initial_state": "random MPS with the saturated bond profile min(2^i, 2^(N-i), chi)",
+                       "max_bond_after": max(rb), "gates_per_layer": N - 1, "model_flops_per_layer": flops,
+                       "l2": "theta/U/V scratch of one half-layer (%.1f GB) exceeds the 126 MB L2; no explicit flush" % (25 * 3 * 4 * chi * chi * 16 / 1e9),
+                       "parallelism": "single GPU (sequential sweep dependence; replicas only)"},
+            "clocks": clocks,
+            "e2e": {"value": args.steps / wall, "unit": "layers/s", "h2d_bytes_per_step": (N - 1) * 256, "d2h_bytes_per_step": (N - 1) * 16},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "tensor", "achieved": ach, "peak": dmma_peak, "unit": "TFLOP/s", "frac": ach / dmma_peak, "traffic": None,
+                         "kernel": "jacobi_round_kernel", "peak_source": "FP64 DMMA ceiling measured in this run",
+                         "note": "achieved = SURVEY 8(d) model flops per layer (sweep-independent SVD count) / time"},
+            "cpu_baseline": cpu}
+    print(json.dumps(line))
+
+
 def run_reference(args):
     """`--impl reference`: the reference's CPU path.  Julia cannot run here (no `julia` binary,
     arithmetic in un-vendored packages), so this times the oracle restatement -- the same
     algorithm class (pairwise TTGT, OpenBLAS zgemm) -- on the host cores.  Rank 0 only."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
+    if args.workload == "cfg4":
+        return run_reference_cfg4(args)
     if args.workload == "cfg3":
         run, nsl, flops = oracle_cfg3_sampler(args.cpu_max_log2)
         sample = "1 of %d slices per step (oracle slicing to <=2^%d elements), all host BLAS threads" % (nsl, args.cpu_max_log2)
@@ -188,6 +309,13 @@ def main():
         ub = uid.cpu().numpy()
         _lib.check(_lib.lib.qtn_nccl_init(rank, world, ub.ctypes.data))
     ext = torch.cuda.ExternalStream(_lib.stream_ptr())
+    if args.workload == "cfg4":
+        if rank == 0:
+            run_cfg4(args, q, _lib, torch, ext)
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
 
     # ---- workload ----------------------------------------------------------------------
     if args.workload == "cfg3":

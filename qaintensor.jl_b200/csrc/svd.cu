@@ -43,6 +43,7 @@ constexpr int JP = 2 * JB;    // panel width (columns per CTA)
 constexpr int JPITCH = JP + 2;
 constexpr int JROWS = 64;     // panel rows staged per chunk
 constexpr int JTHREADS = 256;
+constexpr int kInnerSweeps = 6;  // inner eigen-sweeps per Gram block (outer sweeps finish the job)
 
 struct SvdProblem {
     double2* A;   // m x n (lda = m), overwritten with U * diag(S) (unsorted)
@@ -85,12 +86,12 @@ jacobi_round_kernel(const SvdProblem* __restrict__ probs, int round, double tol,
     double2* W = G + JP * JPITCH;                         // [JP][JPITCH]
     double2* rot = W + JP * JPITCH;                       // [JB] (c, s) + phase
     double2* rph = rot + JB;                              // [JB] e^{i phi}
-    __shared__ int s_any, s_sweep_any;
+    __shared__ int s_any, s_sweep_any, s_rot;
     __shared__ int s_cols[JP];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid < JP) s_cols[tid] = panel_col(tid, bi, bj, pr.n);
-    if (tid == 0) s_any = 0;
+    if (tid == 0) { s_any = 0; s_rot = 0; }
     for (int i = tid; i < JP * JPITCH; i += JTHREADS) { G[i] = make_double2(0, 0); W[i] = make_double2(0, 0); }
     __syncthreads();
 
@@ -100,19 +101,27 @@ jacobi_round_kernel(const SvdProblem* __restrict__ probs, int round, double tol,
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) gr[i][j][0] = gr[i][j][1] = gi[i][j][0] = gi[i][j][1] = 0.0;
-    auto load_chunk = [&](const double2* base, int ld, int r0, int nrows) {
-        // coalesced along rows: 64 rows x 32 columns, thread -> (row = tid % 64, columns tid/64 + 4*i)
+    // chunk staging is software-pipelined: the global loads of chunk i+1 are issued into
+    // registers before the DMMAs of chunk i and parked in shared memory afterwards
+    double2 pre[JP * JROWS / JTHREADS];
+    auto fetch = [&](const double2* base, int ld, int r0, int nrows) {
         const int r = tid & (JROWS - 1);
-        for (int c = tid / JROWS; c < JP; c += JTHREADS / JROWS) {
-            const int col = s_cols[c];
-            double2 v = make_double2(0, 0);
-            if (col >= 0 && r0 + r < nrows) v = base[(size_t)col * ld + r0 + r];
-            Ps[r * JPITCH + c] = v;
+#pragma unroll
+        for (int i = 0; i < JP * JROWS / JTHREADS; ++i) {
+            const int col = s_cols[tid / JROWS + i * (JTHREADS / JROWS)];
+            pre[i] = (col >= 0 && r0 + r < nrows) ? base[(size_t)col * ld + r0 + r] : make_double2(0, 0);
         }
     };
+    auto stash = [&]() {
+        const int r = tid & (JROWS - 1);
+#pragma unroll
+        for (int i = 0; i < JP * JROWS / JTHREADS; ++i) Ps[r * JPITCH + tid / JROWS + i * (JTHREADS / JROWS)] = pre[i];
+    };
+    fetch(pr.A, pr.m, 0, pr.m);
     for (int r0 = 0; r0 < pr.m; r0 += JROWS) {
-        load_chunk(pr.A, pr.m, r0, pr.m);
+        stash();
         __syncthreads();
+        if (r0 + JROWS < pr.m) fetch(pr.A, pr.m, r0 + JROWS, pr.m);
         // warp w owns k-rows [8w, 8w+8) of the chunk: two k4 steps
 #pragma unroll
         for (int k4 = 0; k4 < 2; ++k4) {
@@ -157,7 +166,7 @@ jacobi_round_kernel(const SvdProblem* __restrict__ probs, int round, double tol,
     __syncthreads();
 
     // ---------------- phase 2: Hermitian Jacobi on G, W accumulates the rotations -------------------
-    for (int sweep = 0; sweep < 12; ++sweep) {
+    for (int sweep = 0; sweep < kInnerSweeps; ++sweep) {
         if (tid == 0) s_sweep_any = 0;
         __syncthreads();
         for (int step = 0; step < JP - 1; ++step) {
@@ -168,23 +177,27 @@ jacobi_round_kernel(const SvdProblem* __restrict__ probs, int round, double tol,
                 if (p > q) { int t = p; p = q; q = t; }
                 const double alpha = G[p * JPITCH + p].x, beta = G[q * JPITCH + q].x;
                 const double2 g = G[p * JPITCH + q];
-                const double ag = hypot(g.x, g.y);
+                const double ag2 = g.x * g.x + g.y * g.y;
                 double c = 1.0, s = 0.0;
                 double2 ph = make_double2(1.0, 0.0);
                 const bool real_cols = s_cols[p] >= 0 && s_cols[q] >= 0;  // never touch padding slots
                 if (!real_cols) {
                     // identity
-                } else if (ag > tol * sqrt(fabs(alpha) * fabs(beta)) && ag > 0.0 && alpha > dthr && beta > dthr) {
-                    ph = make_double2(g.x / ag, g.y / ag);
-                    const double zeta = (beta - alpha) / (2.0 * ag);
-                    double t = 1.0 / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+                } else if (ag2 > tol * tol * fabs(alpha) * fabs(beta) && ag2 > 0.0 && alpha > dthr && beta > dthr) {
+                    // three rsqrt + one division (FP64 sqrt/div chains are the critical path of a step)
+                    const double rg = rsqrt(ag2), ag = ag2 * rg;
+                    ph = make_double2(g.x * rg, g.y * rg);
+                    const double zeta = 0.5 * (beta - alpha) * rg;
+                    const double z1 = 1.0 + zeta * zeta;
+                    double t = 1.0 / (fabs(zeta) + z1 * rsqrt(z1));
                     if (zeta < 0) t = -t;
-                    c = 1.0 / sqrt(1.0 + t * t);
+                    c = rsqrt(1.0 + t * t);
                     s = c * t;
                     // de Rijk ordering: keep the larger diagonal entry at the lower index
                     const double ap = alpha - t * ag, bq = beta + t * ag;
                     if (ap < bq) { const double c2 = s, s2 = -c; c = c2; s = s2; }
                     s_sweep_any = 1;
+                    s_rot = 1;
                 } else if (alpha < beta && beta > dthr) {
                     c = 0.0; s = -1.0;  // pure swap: a significant column moves in front of a smaller one
                     s_sweep_any = 1;
@@ -197,34 +210,52 @@ jacobi_round_kernel(const SvdProblem* __restrict__ probs, int round, double tol,
             }
             __syncthreads();
             const int* pq = reinterpret_cast<const int*>(rph + JB);
-            // column rotations on G and W: x_p' = c x_p - s e^{-i phi} x_q ; x_q' = s e^{i phi} x_p + c x_q
-            for (int e = tid; e < 2 * JP * JB; e += JTHREADS) {
-                const int which = e / (JP * JB), r = (e % (JP * JB)) / JB, k = e % JB;
-                const double c = rot[k].x, s = rot[k].y;
-                if (c == 1.0 && s == 0.0) continue;
-                const double2 ph = rph[k];
-                double2* Mx = which ? W : G;
-                const int p = pq[2 * k], q = pq[2 * k + 1];
-                const double2 xp = Mx[r * JPITCH + p], xq = Mx[r * JPITCH + q];
-                // e^{-i phi} xq and e^{i phi} xp
-                const double2 eq = make_double2(ph.x * xq.x + ph.y * xq.y, ph.x * xq.y - ph.y * xq.x);
-                const double2 ep = make_double2(ph.x * xp.x - ph.y * xp.y, ph.x * xp.y + ph.y * xp.x);
-                Mx[r * JPITCH + p] = make_double2(c * xp.x - s * eq.x, c * xp.y - s * eq.y);
-                Mx[r * JPITCH + q] = make_double2(s * ep.x + c * xq.x, s * ep.y + c * xq.y);
-            }
-            __syncthreads();
-            // row rotations on G (J^H from the left): y_p' = c y_p - s e^{i phi} y_q ; y_q' = s e^{-i phi} y_p + c y_q
-            for (int e = tid; e < JP * JB; e += JTHREADS) {
-                const int col = e / JB, k = e % JB;
-                const double c = rot[k].x, s = rot[k].y;
-                if (c == 1.0 && s == 0.0) continue;
-                const double2 ph = rph[k];
-                const int p = pq[2 * k], q = pq[2 * k + 1];
-                const double2 yp = G[p * JPITCH + col], yq = G[q * JPITCH + col];
-                const double2 eq = make_double2(ph.x * yq.x - ph.y * yq.y, ph.x * yq.y + ph.y * yq.x);
-                const double2 ep = make_double2(ph.x * yp.x + ph.y * yp.y, ph.x * yp.y - ph.y * yp.x);
-                G[p * JPITCH + col] = make_double2(c * yp.x - s * eq.x, c * yp.y - s * eq.y);
-                G[q * JPITCH + col] = make_double2(s * ep.x + c * yq.x, s * ep.y + c * yq.y);
+            {
+                // fused two-sided update: thread (k1, k2) owns the 2x2 block G[{p1,q1}][{p2,q2}]:
+                // G' = J1^H G J2 with J = [[c, s e^{i phi}], [-s e^{-i phi}, c]] acting on columns
+                const int k1 = tid >> 4, k2 = tid & 15;
+                const double c1 = rot[k1].x, s1 = rot[k1].y, c2 = rot[k2].x, s2 = rot[k2].y;
+                const bool id1 = (c1 == 1.0 && s1 == 0.0), id2 = (c2 == 1.0 && s2 == 0.0);
+                if (!(id1 && id2)) {
+                    const double2 ph1 = rph[k1], ph2 = rph[k2];
+                    const int p1 = pq[2 * k1], q1 = pq[2 * k1 + 1], p2 = pq[2 * k2], q2 = pq[2 * k2 + 1];
+                    double2 g00 = G[p1 * JPITCH + p2], g01 = G[p1 * JPITCH + q2];
+                    double2 g10 = G[q1 * JPITCH + p2], g11 = G[q1 * JPITCH + q2];
+                    auto mulph = [](double2 ph, double2 v) { return make_double2(ph.x * v.x - ph.y * v.y, ph.x * v.y + ph.y * v.x); };
+                    auto mulphc = [](double2 ph, double2 v) { return make_double2(ph.x * v.x + ph.y * v.y, ph.x * v.y - ph.y * v.x); };
+                    if (!id1) {  // rows: y_p' = c y_p - s e^{i phi} y_q ; y_q' = s e^{-i phi} y_p + c y_q
+                        const double2 e10 = mulph(ph1, g10), e11 = mulph(ph1, g11), f00 = mulphc(ph1, g00), f01 = mulphc(ph1, g01);
+                        const double2 n00 = make_double2(c1 * g00.x - s1 * e10.x, c1 * g00.y - s1 * e10.y);
+                        const double2 n01 = make_double2(c1 * g01.x - s1 * e11.x, c1 * g01.y - s1 * e11.y);
+                        const double2 n10 = make_double2(s1 * f00.x + c1 * g10.x, s1 * f00.y + c1 * g10.y);
+                        const double2 n11 = make_double2(s1 * f01.x + c1 * g11.x, s1 * f01.y + c1 * g11.y);
+                        g00 = n00; g01 = n01; g10 = n10; g11 = n11;
+                    }
+                    if (!id2) {  // columns: x_p' = c x_p - s e^{-i phi} x_q ; x_q' = s e^{i phi} x_p + c x_q
+                        const double2 e01 = mulphc(ph2, g01), e11 = mulphc(ph2, g11), f00 = mulph(ph2, g00), f10 = mulph(ph2, g10);
+                        const double2 n00 = make_double2(c2 * g00.x - s2 * e01.x, c2 * g00.y - s2 * e01.y);
+                        const double2 n10 = make_double2(c2 * g10.x - s2 * e11.x, c2 * g10.y - s2 * e11.y);
+                        const double2 n01 = make_double2(s2 * f00.x + c2 * g01.x, s2 * f00.y + c2 * g01.y);
+                        const double2 n11 = make_double2(s2 * f10.x + c2 * g11.x, s2 * f10.y + c2 * g11.y);
+                        g00 = n00; g01 = n01; g10 = n10; g11 = n11;
+                    }
+                    G[p1 * JPITCH + p2] = g00; G[p1 * JPITCH + q2] = g01;
+                    G[q1 * JPITCH + p2] = g10; G[q1 * JPITCH + q2] = g11;
+                }
+                // W <- W J (columns), rows r and r + 16 for pair k2
+                if (!id2) {
+                    const double2 ph2 = rph[k2];
+                    const int p2 = pq[2 * k2], q2 = pq[2 * k2 + 1];
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int r = k1 + 16 * h;
+                        const double2 xp = W[r * JPITCH + p2], xq = W[r * JPITCH + q2];
+                        const double2 eq = make_double2(ph2.x * xq.x + ph2.y * xq.y, ph2.x * xq.y - ph2.y * xq.x);
+                        const double2 ep = make_double2(ph2.x * xp.x - ph2.y * xp.y, ph2.x * xp.y + ph2.y * xp.x);
+                        W[r * JPITCH + p2] = make_double2(c2 * xp.x - s2 * eq.x, c2 * xp.y - s2 * eq.y);
+                        W[r * JPITCH + q2] = make_double2(s2 * ep.x + c2 * xq.x, s2 * ep.y + c2 * xq.y);
+                    }
+                }
             }
             __syncthreads();
         }
@@ -234,17 +265,20 @@ jacobi_round_kernel(const SvdProblem* __restrict__ probs, int round, double tol,
         if (!any_now) break;
     }
     if (!s_any) return;  // panel already orthogonal and ordered: nothing to update
-    if (tid == 0) rotated[blockIdx.y] = 1;
+    if (tid == 0 && s_rot) rotated[blockIdx.y] = 1;  // pure re-ordering swaps do not keep the sweeps going
 
     // ---------------- phase 3: P <- P W for the A panel and the V panel ---------------------------------
     // warp w owns rows [8w, 8w+8) of each 64-row chunk: C(8 x 32) = P(8 x 32) W(32 x 32)
     for (int which = 0; which < 2; ++which) {
         double2* base = which ? pr.V : pr.A;
         const int nrows = which ? pr.n : pr.m;
+        __syncthreads();
+        fetch(base, nrows, 0, nrows);
         for (int r0 = 0; r0 < nrows; r0 += JROWS) {
             __syncthreads();
-            load_chunk(base, nrows, r0, nrows);
+            stash();
             __syncthreads();
+            if (r0 + JROWS < nrows) fetch(base, nrows, r0 + JROWS, nrows);
             double cr[4][2], ci[4][2];
 #pragma unroll
             for (int j = 0; j < 4; ++j) cr[j][0] = cr[j][1] = ci[j][0] = ci[j][1] = 0.0;

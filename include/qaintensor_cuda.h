@@ -196,6 +196,16 @@ int qtn_mps_apply_layer(qtn_mps* mps, int32_t ngates, const int32_t* sites,
                         double* disc_out /* ngates */);
 /* <a|b> by transfer-matrix contraction; result (re, im).                           */
 int qtn_mps_overlap(const qtn_mps* a, const qtn_mps* b, double out[2]);
+/* EXTENSION (SURVEY 8a iii/iv): site-tensor MPO with the layout of src/mpo.jl:66,
+ * W_i = (bond_in, out, in, bond_out) = (dl[i], 2, 2, dr[i]), dl[0] = dr[n-1] = 1.
+ * qtn_mps_apply_mpo: |psi> <- compress(MPO |psi>): site-wise apply (bonds multiply), a
+ * left-to-right SVD sweep that orthogonalises, a right-to-left SVD sweep that truncates with
+ * (er, maxdim).  disc_out[n-1] (may be NULL) = discarded 2-norm per bond of the second sweep.
+ * qtn_mps_expect_mpo: <psi| MPO |psi> by left-environment contraction, result (re, im).  */
+int qtn_mps_apply_mpo(qtn_mps* mps, const void* const* host_mpo_sites, const int64_t* dl,
+                      const int64_t* dr, double er, int64_t maxdim, double* disc_out);
+int qtn_mps_expect_mpo(const qtn_mps* mps, const void* const* host_mpo_sites, const int64_t* dl,
+                       const int64_t* dr, double out[2]);
 
 #ifdef __cplusplus
 }

@@ -55,3 +55,77 @@ def to_vector(sites):
         psi = np.tensordot(psi, A, axes=(psi.ndim - 1, 0))
     psi = psi.reshape(psi.shape[1:-1])
     return np.reshape(psi, (-1,), order="F")
+
+
+# ---- MPO x MPS (EXTENSION iii / iv of SURVEY section 8a) --------------------------------------------
+def tfi_mpo(n, J=1.0, h=1.0):
+    """H = -J sum Z_i Z_{i+1} - h sum X_i as a D = 3 site-tensor MPO, layout (bond_in, out, in,
+    bond_out) of src/mpo.jl:66; boundary bonds 1."""
+    I2 = np.eye(2)
+    X = np.array([[0, 1], [1, 0]], dtype=float)
+    Z = np.diag([1.0, -1.0])
+    Wm = np.zeros((3, 2, 2, 3), dtype=np.complex128)
+    Wm[0, :, :, 0] = I2
+    Wm[1, :, :, 0] = Z
+    Wm[2, :, :, 0] = -h * X
+    Wm[2, :, :, 1] = -J * Z
+    Wm[2, :, :, 2] = I2
+    sites = []
+    for i in range(n):
+        w = Wm
+        if i == 0:
+            w = w[2:3]          # start in the "nothing applied yet" row
+        if i == n - 1:
+            w = w[:, :, :, 0:1]  # end in the "everything applied" column
+        sites.append(np.ascontiguousarray(w))
+    return sites
+
+
+def mpo_to_dense(mpo):
+    """Dense 2^n x 2^n matrix, site 1 = fastest bit (small n only)."""
+    n = len(mpo)
+    T = mpo[0][0]  # (out, in, bond)
+    for w in mpo[1:]:
+        T = np.tensordot(T, w, axes=(T.ndim - 1, 0))
+    T = T[..., 0]
+    outs = [2 * i for i in range(n)]
+    ins = [2 * i + 1 for i in range(n)]
+    T = np.transpose(T, outs + ins)
+    return np.reshape(T, (2 ** n, 2 ** n), order="F")
+
+
+def apply_mpo_compress(sites, mpo, er=0.0, maxdim=None):
+    """In place: site-wise apply, left-to-right SVD orthogonalisation, right-to-left truncating sweep."""
+    n = len(sites)
+    fat = []
+    for A, W in zip(sites, mpo):
+        L, _, R = A.shape
+        Dl, _, _, Dr = W.shape
+        B = np.einsum("aqpb,lpr->laqrb", W, A)            # (l, a, p', r, b)
+        fat.append(np.reshape(B, (L * Dl, 2, R * Dr), order="F"))
+    for i in range(n - 1):
+        l, _, r = fat[i].shape
+        U, S, Vh = svd(np.reshape(fat[i], (2 * l, r), order="F"))
+        k = len(S)
+        fat[i] = np.reshape(U, (l, 2, k), order="F")
+        nxt = fat[i + 1]
+        fat[i + 1] = np.reshape((S[:, None] * Vh) @ np.reshape(nxt, (r, -1), order="F"), (k, 2, nxt.shape[2]), order="F")
+    disc = [0.0] * (n - 1)
+    for i in range(n - 1, 0, -1):
+        l, _, r = fat[i].shape
+        U, S, Vh = svd(np.reshape(fat[i], (l, 2 * r), order="F"))
+        k = max(truncation_rank(S, er, maxdim), 1)
+        disc[i - 1] = float(np.sqrt(np.sum(S[k:] ** 2)))
+        fat[i] = np.reshape(Vh[:k], (k, 2, r), order="F")
+        prv = fat[i - 1]
+        fat[i - 1] = np.reshape(np.reshape(prv, (-1, l), order="F") @ (U[:, :k] * S[:k]), (prv.shape[0], 2, k), order="F")
+    sites[:] = fat
+    return disc
+
+
+def expect_mpo(sites, mpo):
+    """<psi| MPO |psi> by left environments E[la, a, lb]."""
+    E = np.ones((1, 1, 1), dtype=np.complex128)
+    for A, W in zip(sites, mpo):
+        E = np.einsum("xay,xqr,aqpb,yps->rbs", E, np.conj(A), W, A)
+    return complex(E[0, 0, 0])

@@ -78,6 +78,8 @@ _SIGS = {
     "qtn_mps_apply_gate2": [vp, i32, vp, f64, i64, P(f64)],
     "qtn_mps_apply_layer": [vp, i32, P(i32), vp, f64, i64, P(f64)],
     "qtn_mps_overlap": [vp, vp, P(f64)],
+    "qtn_mps_apply_mpo": [vp, P(vp), P(i64), P(i64), f64, i64, P(f64)],
+    "qtn_mps_expect_mpo": [vp, P(vp), P(i64), P(i64), P(f64)],
 }
 for _name, _args in _SIGS.items():
     _f = getattr(lib, _name)
@@ -96,9 +98,16 @@ def device_count():
     return n.value
 
 
+_device_ok = False
+
+
 def require_device():
     """Fail loudly when the CUDA path cannot run (no fallback exists)."""
+    global _device_ok
+    if _device_ok:
+        return
     check(lib.qtn_init(int(os.environ.get("LOCAL_RANK", "0")) if device_count() > 1 else 0))
+    _device_ok = True
 
 
 def dmma_peak_tflops():

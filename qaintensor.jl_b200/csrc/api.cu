@@ -212,18 +212,16 @@ int qtn_nccl_allreduce_sum_f64(void* dev_buf, int64_t count) {
 static int exec_host(Plan* p, const void* const* host_data, int64_t s0, int64_t s1, void* host_out, bool allreduce) {
     int rc = QTN_OK;
     if (host_data) { rc = plan_upload(p, host_data); if (rc) return rc; }
-    double2* out = nullptr;
-    size_t bytes = (size_t)p->out_numel * 16;
-    CUDA_TRY(cudaMalloc((void**)&out, bytes > 256 ? bytes : 256));
-    cudaMemsetAsync(out, 0, bytes, stream());
+    if (!p->dev) return fail(QTN_EINVAL, "plan has no uploaded tensors");
+    void* out = nullptr;
+    if ((rc = plan_result_buffer(p, &out))) return rc;
     rc = plan_execute(p, s0, s1, out);
     if (!rc && allreduce) rc = qtn_nccl_allreduce_sum_f64(out, 2 * p->out_numel);
     if (!rc) {
-        cudaError_t e = cudaMemcpyAsync(host_out, out, bytes, cudaMemcpyDeviceToHost, stream());
+        cudaError_t e = cudaMemcpyAsync(host_out, out, (size_t)p->out_numel * 16, cudaMemcpyDeviceToHost, stream());
         if (e == cudaSuccess) e = cudaStreamSynchronize(stream());
         if (e != cudaSuccess) rc = fail(QTN_ECUDA, "result download failed: %s", cudaGetErrorString(e));
     }
-    cudaFree(out);
     return rc;
 }
 

@@ -48,6 +48,7 @@ int64_t launch_count(int reset) {
 void count_launch(int64_t n) { g_launches += n; }
 
 int device_init(int device) {
+    if (g_inited && g_device == device) { cudaSetDevice(device); return QTN_OK; }  // fast path (no property queries)
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
     if (e != cudaSuccess || n == 0)
@@ -142,6 +143,8 @@ struct DevPlan {
     bool uploaded = false;
     bool invariants_done = false;
     int graph_launches = 0;
+    std::vector<cudaEvent_t> capture_events;
+    double2* host_out = nullptr;  // result buffer of the host-buffer entry points
 };
 
 static TabArg tab_arg(const DevPlan* d, const OffTable& t) {
@@ -202,6 +205,7 @@ void plan_device_free(Plan* p) {
     if (!d) return;
     if (g_stream) cudaStreamSynchronize(g_stream);
     if (d->graph) cudaGraphExecDestroy(d->graph);
+    if (d->host_out) cudaFree(d->host_out);
     cudaFree(d->inputs); cudaFree(d->arena); cudaFree(d->tables); cudaFree(d->sid); cudaFree(d->soff);
     cudaFree(d->slice_dims); cudaFree(d->first); cudaFree(d->pos); cudaFree(d->stride);
     if (d->h_stage) cudaFreeHost(d->h_stage);
@@ -334,19 +338,70 @@ int bench_dmma_peak(double* tflops_out) {
     return QTN_OK;
 }
 
-static int enqueue_slice(Plan* p, DevPlan* d, void* dev_out, cudaStream_t st) {
+// Side streams used to express the step DAG during stream capture (fork/join by events).
+static const int kLanes = 16;
+static cudaStream_t g_lane[kLanes];
+static bool g_lanes_ready = false;
+
+static int lanes_init() {
+    if (g_lanes_ready) return QTN_OK;
+    for (int i = 0; i < kLanes; ++i) CUDA_TRY(cudaStreamCreateWithFlags(&g_lane[i], cudaStreamNonBlocking));
+    g_lanes_ready = true;
+    return QTN_OK;
+}
+
+// Enqueue one slice.  dag == true (only under stream capture): every step goes to the lane of one of
+// its producers and waits on the other producer's event, so the captured graph carries the true
+// dependencies of the contraction tree instead of a chain.
+static int enqueue_slice(Plan* p, DevPlan* d, void* dev_out, cudaStream_t st, bool dag) {
     if (p->nslices > 1) {
         slice_offsets_kernel<<<1, 256, 0, st>>>(d->sid, (int)p->slice_dims.size(), d->slice_dims, p->nt, d->first,
                                                 d->pos, d->stride, d->soff);
         CUDA_TRY(cudaGetLastError());
         count_launch(1);
     }
+    if (!dag) {
+        for (const Step& s : p->steps) {
+            if (s.invariant) continue;
+            int rc = run_step(p, d, s, dev_out, st);
+            if (rc) return rc;
+        }
+        return QTN_OK;
+    }
+    int rc = lanes_init();
+    if (rc) return rc;
+    std::vector<int> lane_of(p->nodes.size(), -1);       // lane that produced the node (-1: input / invariant)
+    std::vector<cudaEvent_t> done(p->nodes.size(), nullptr);
+    std::vector<cudaEvent_t>& events = d->capture_events;  // destroyed after cudaStreamEndCapture
+    auto new_event = [&](cudaEvent_t* e) { cudaEventCreateWithFlags(e, cudaEventDisableTiming); events.push_back(*e); };
+    cudaEvent_t fork;
+    new_event(&fork);
+    CUDA_TRY(cudaEventRecord(fork, st));
+    bool used[kLanes] = {false};
+    int next_lane = 0;
     for (const Step& s : p->steps) {
         if (s.invariant) continue;
-        int rc = run_step(p, d, s, dev_out, st);
-        if (rc) return rc;
+        int lane = -1;
+        for (int x : {s.a, s.b}) if (x >= 0 && lane_of[x] >= 0) { lane = lane_of[x]; break; }
+        if (lane < 0) { lane = next_lane; next_lane = (next_lane + 1) % kLanes; }
+        cudaStream_t ls = g_lane[lane];
+        if (!used[lane]) { CUDA_TRY(cudaStreamWaitEvent(ls, fork, 0)); used[lane] = true; }
+        for (int x : {s.a, s.b})
+            if (x >= 0 && lane_of[x] >= 0 && lane_of[x] != lane) CUDA_TRY(cudaStreamWaitEvent(ls, done[x], 0));
+        rc = run_step(p, d, s, dev_out, ls);
+        if (rc) break;
+        lane_of[s.out] = lane;
+        new_event(&done[s.out]);
+        CUDA_TRY(cudaEventRecord(done[s.out], ls));
     }
-    return QTN_OK;
+    for (int i = 0; i < kLanes && !rc; ++i)
+        if (used[i]) {
+            cudaEvent_t j;
+            new_event(&j);
+            CUDA_TRY(cudaEventRecord(j, g_lane[i]));
+            CUDA_TRY(cudaStreamWaitEvent(st, j, 0));
+        }
+    return rc;
 }
 
 int plan_execute(Plan* p, int64_t s0, int64_t s1, void* dev_out) {
@@ -370,16 +425,17 @@ int plan_execute(Plan* p, int64_t s0, int64_t s1, void* dev_out) {
         if (d->graph) { cudaGraphExecDestroy(d->graph); d->graph = nullptr; }
         // make sure every kernel's max-smem attribute is set outside capture: warm-run slice s0 directly
         int64_t before = launch_count(0);
-        int rc = enqueue_slice(p, d, dev_out, g_stream);
+        int rc = enqueue_slice(p, d, dev_out, g_stream, false);
         if (rc) return rc;
         d->graph_launches = (int)(launch_count(0) - before);
         ++s0;
-        if (s0 == s1) return QTN_OK;
         cudaGraph_t graph;
         CUDA_TRY(cudaStreamBeginCapture(g_stream, cudaStreamCaptureModeThreadLocal));
         int64_t keep = launch_count(0);
-        rc = enqueue_slice(p, d, dev_out, g_stream);
+        rc = enqueue_slice(p, d, dev_out, g_stream, p->dag);
         cudaError_t e = cudaStreamEndCapture(g_stream, &graph);
+        for (auto ev : d->capture_events) cudaEventDestroy(ev);
+        d->capture_events.clear();
         launch_count(1);
         count_launch(keep);
         if (rc) return rc;
@@ -391,6 +447,17 @@ int plan_execute(Plan* p, int64_t s0, int64_t s1, void* dev_out) {
     }
     for (int64_t s = s0; s < s1; ++s) CUDA_TRY(cudaGraphLaunch(d->graph, g_stream));
     count_launch((s1 - s0) * d->graph_launches);
+    return QTN_OK;
+}
+
+// Device buffer (zeroed, on the stream) for the result of the host-buffer entry points.
+int plan_result_buffer(Plan* p, void** out) {
+    DevPlan* d = (DevPlan*)p->dev;
+    if (!d) return fail(QTN_EINVAL, "plan has no device state");
+    const size_t bytes = std::max<size_t>((size_t)p->out_numel * 16, 256);
+    if (!d->host_out) CUDA_TRY(cudaMalloc((void**)&d->host_out, bytes));
+    CUDA_TRY(cudaMemsetAsync(d->host_out, 0, bytes, g_stream));
+    *out = d->host_out;
     return QTN_OK;
 }
 

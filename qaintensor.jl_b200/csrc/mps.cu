@@ -73,6 +73,44 @@ __global__ void apply_gate2_kernel(double2* __restrict__ theta, int64_t L, int64
     }
 }
 
+// B[(l,a), p', (r,b)] = sum_p W[a,p',p,b] A[l,p,r]   (MPO site applied to an MPS site; l and r fastest)
+__global__ void mpo_apply_site_kernel(const double2* __restrict__ A, int64_t L, int64_t R, const double2* __restrict__ W,
+                                      int64_t Dl, int64_t Dr, double2* __restrict__ B) {
+    const int64_t LB = L * Dl, tot = LB * 2 * R * Dr;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < tot; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t la = e % LB, pp = (e / LB) % 2, rb = e / (2 * LB);
+        const int64_t l = la % L, a = la / L, r = rb % R, b = rb / R;
+        double re = 0, im = 0;
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+            const double2 w = W[a + Dl * (pp + 2 * (p + 2 * b))];
+            const double2 x = A[l + L * (p + 2 * r)];
+            re += w.x * x.x - w.y * x.y;
+            im += w.x * x.y + w.y * x.x;
+        }
+        B[e] = make_double2(re, im);
+    }
+}
+
+// T2[la, p', b, rb] = sum_{a,p} W[a,p',p,b] T1[la, a, p, rb]      (environment update, middle step)
+__global__ void env_apply_w_kernel(const double2* __restrict__ T1, int64_t La, int64_t Rb, const double2* __restrict__ W,
+                                   int64_t Dl, int64_t Dr, double2* __restrict__ T2) {
+    const int64_t tot = La * 2 * Dr * Rb;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < tot; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t la = e % La, pp = (e / La) % 2, b = (e / (2 * La)) % Dr, rb = e / (2 * La * Dr);
+        double re = 0, im = 0;
+        for (int64_t a = 0; a < Dl; ++a)
+#pragma unroll
+            for (int p = 0; p < 2; ++p) {
+                const double2 w = W[a + Dl * (pp + 2 * (p + 2 * b))];
+                const double2 x = T1[la + La * (a + Dl * (p + 2 * rb))];
+                re += w.x * x.x - w.y * x.y;
+                im += w.x * x.y + w.y * x.x;
+            }
+        T2[e] = make_double2(re, im);
+    }
+}
+
 static int scale_copy(const double2* in, int64_t ldi, double2* out, int64_t ldo, int64_t rows, int64_t cols, const double* s, int by_col) {
     if (rows * cols == 0) return QTN_OK;
     int blocks = (int)std::min<int64_t>((rows * cols + 255) / 256, 148 * 8);
@@ -309,6 +347,131 @@ int qtn_mps_overlap(const qtn_mps* a, const qtn_mps* b, double out[2]) {
     double2 res;
     CUDA_TRY(cudaMemcpyAsync(&res, e, 16, cudaMemcpyDeviceToHost, stream()));
     CUDA_TRY(cudaStreamSynchronize(stream()));
+    out[0] = res.x;
+    out[1] = res.y;
+    return QTN_OK;
+}
+
+// ---------------- MPO x MPS (EXTENSION iii / iv) ------------------------------------------------------
+static int check_mpo(const qtn_mps* m, const void* const* sites, const int64_t* dl, const int64_t* dr) {
+    if (!m || !sites || !dl || !dr) return fail(QTN_EINVAL, "qtn_mps mpo: null argument");
+    if (dl[0] != 1 || dr[m->n - 1] != 1) return fail(QTN_EINVAL, "MPO boundary bonds must be 1");
+    for (int i = 0; i < m->n; ++i) {
+        if (dl[i] < 1 || dr[i] < 1 || !sites[i]) return fail(QTN_EINVAL, "MPO site %d malformed", i + 1);
+        if (i > 0 && dl[i] != dr[i - 1]) return fail(QTN_EINVAL, "MPO bonds of sites %d and %d do not match", i, i + 1);
+    }
+    return QTN_OK;
+}
+
+int qtn_mps_apply_mpo(qtn_mps* m, const void* const* host_mpo_sites, const int64_t* dl, const int64_t* dr, double er,
+                      int64_t maxdim, double* disc_out) {
+    int rc = check_mpo(m, host_mpo_sites, dl, dr);
+    if (rc) return rc;
+    if ((rc = device_ready())) return rc;
+    if (maxdim <= 0 || maxdim > m->cap) maxdim = m->cap;
+    cudaStream_t st = stream();
+    const int n = m->n;
+    int64_t Dmax = 1, wtot = 0;
+    for (int i = 0; i < n; ++i) { Dmax = std::max(Dmax, std::max(dl[i], dr[i])); wtot += dl[i] * 4 * dr[i]; }
+    // 1. site-wise apply into fat sites (bonds multiply)
+    std::vector<DevBuf> fat(n);
+    std::vector<int64_t> lb(n), rb(n);
+    DevBuf W;
+    if ((rc = W.alloc(wtot * 16))) return rc;
+    int64_t woff = 0;
+    for (int i = 0; i < n; ++i) {
+        const int64_t L = m->lb[i], R = m->rb[i];
+        lb[i] = L * dl[i];
+        rb[i] = R * dr[i];
+        if ((rc = fat[i].alloc((size_t)lb[i] * 2 * rb[i] * 16))) return rc;
+        double2* w = (double2*)W.p + woff;
+        CUDA_TRY(cudaMemcpyAsync(w, host_mpo_sites[i], (size_t)dl[i] * 4 * dr[i] * 16, cudaMemcpyHostToDevice, st));
+        woff += dl[i] * 4 * dr[i];
+        const int64_t tot = lb[i] * 2 * rb[i];
+        mpo_apply_site_kernel<<<(int)std::min<int64_t>((tot + 255) / 256, 148 * 8), 256, 0, st>>>(m->site[i], L, R, w, dl[i], dr[i], (double2*)fat[i].p);
+        count_launch(1);
+    }
+    CUDA_TRY(cudaGetLastError());
+    // 2. left-to-right sweep: orthogonalise (SVD without truncation), carry S*Vh to the right
+    int64_t big = 0;
+    for (int i = 0; i < n; ++i) big = std::max(big, lb[i] * 2 * rb[i]);
+    DevBuf U, S, Vh, C, T;
+    if ((rc = U.alloc(big * 16)) || (rc = S.alloc(std::max<int64_t>(big, 16) * 8)) || (rc = Vh.alloc(big * 16)) || (rc = C.alloc(big * 16)) ||
+        (rc = T.alloc(big * 16)))
+        return rc;
+    for (int i = 0; i + 1 < n; ++i) {
+        const int64_t mm = lb[i] * 2, nn = rb[i], r = std::min(mm, nn);
+        SvdJob job{(double2*)fat[i].p, mm, nn, (double2*)U.p, (double*)S.p, (double2*)Vh.p};
+        int64_t k = 0;
+        if ((rc = svd_batched_device(1, &job, -1.0, 0, &k, nullptr, nullptr))) return rc;
+        // site i <- U (mm x r); C = diag(S) Vh (r x nn); site i+1 <- C * site_{i+1} (nn x 2 rb[i+1])
+        if ((rc = scale_copy((double2*)U.p, mm, (double2*)fat[i].p, mm, mm, r, nullptr, 1))) return rc;
+        if ((rc = scale_copy((double2*)Vh.p, r, (double2*)C.p, r, r, nn, (double*)S.p, 0))) return rc;
+        const int64_t ncols = 2 * rb[i + 1];
+        if ((rc = qtn_zgemm_device('N', 'N', r, ncols, nn, C.p, r, fat[i + 1].p, nn, T.p, r))) return rc;
+        CUDA_TRY(cudaMemcpyAsync(fat[i + 1].p, T.p, (size_t)r * ncols * 16, cudaMemcpyDeviceToDevice, st));
+        rb[i] = r;
+        lb[i + 1] = r;
+    }
+    // 3. right-to-left sweep: truncate (er, maxdim); site i <- Vh[:k], site i-1 <- site_{i-1} * (U[:, :k] S)
+    for (int i = n - 1; i >= 1; --i) {
+        const int64_t mm = lb[i], nn = 2 * rb[i], r = std::min(mm, nn);
+        SvdJob job{(double2*)fat[i].p, mm, nn, (double2*)U.p, (double*)S.p, (double2*)Vh.p};
+        int64_t k = 0;
+        double disc = 0;
+        if ((rc = svd_batched_device(1, &job, er, maxdim, &k, &disc, nullptr))) return rc;
+        k = std::max<int64_t>(k, 1);
+        if (disc_out) disc_out[i - 1] = disc;
+        if ((size_t)k * nn > (size_t)2 * m->cap * m->cap) return fail(QTN_ENOMEM, "compressed site %d exceeds the MPS capacity", i + 1);
+        if ((rc = scale_copy((double2*)Vh.p, r, m->site[i], k, k, nn, nullptr, 0))) return rc;     // (k, 2, rb)
+        if ((rc = scale_copy((double2*)U.p, mm, (double2*)C.p, mm, mm, k, (double*)S.p, 1))) return rc;  // U[:, :k] S
+        const int64_t rows = lb[i - 1] * 2;
+        if ((rc = qtn_zgemm_device('N', 'N', rows, k, mm, fat[i - 1].p, rows, C.p, mm, T.p, rows))) return rc;
+        CUDA_TRY(cudaMemcpyAsync(fat[i - 1].p, T.p, (size_t)rows * k * 16, cudaMemcpyDeviceToDevice, st));
+        m->lb[i] = k;
+        m->rb[i] = rb[i];
+        rb[i - 1] = k;
+    }
+    if ((size_t)lb[0] * 2 * rb[0] > (size_t)2 * m->cap * m->cap) return fail(QTN_ENOMEM, "compressed site 1 exceeds the MPS capacity");
+    CUDA_TRY(cudaMemcpyAsync(m->site[0], fat[0].p, (size_t)lb[0] * 2 * rb[0] * 16, cudaMemcpyDeviceToDevice, st));
+    m->lb[0] = lb[0];
+    m->rb[0] = rb[0];
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return QTN_OK;
+}
+
+int qtn_mps_expect_mpo(const qtn_mps* m, const void* const* host_mpo_sites, const int64_t* dl, const int64_t* dr, double out[2]) {
+    int rc = check_mpo(m, host_mpo_sites, dl, dr);
+    if (rc) return rc;
+    if (!out) return fail(QTN_EINVAL, "null argument");
+    if ((rc = device_ready())) return rc;
+    if (m->lb[0] != 1 || m->rb[m->n - 1] != 1) return fail(QTN_EINVAL, "qtn_mps_expect_mpo: boundary bonds must be 1");
+    cudaStream_t st = stream();
+    int64_t Dmax = 1;
+    for (int i = 0; i < m->n; ++i) Dmax = std::max(Dmax, std::max(dl[i], dr[i]));
+    const int64_t cap = m->cap;
+    DevBuf E, E2, T1, T2, W;
+    if ((rc = E.alloc(cap * Dmax * cap * 16)) || (rc = E2.alloc(cap * Dmax * cap * 16)) || (rc = T1.alloc(cap * Dmax * 2 * cap * 16)) ||
+        (rc = T2.alloc(cap * 2 * Dmax * cap * 16)) || (rc = W.alloc(Dmax * 4 * Dmax * 16)))
+        return rc;
+    const double2 one = make_double2(1.0, 0.0);
+    CUDA_TRY(cudaMemcpyAsync(E.p, &one, 16, cudaMemcpyHostToDevice, st));
+    void *e = E.p, *e2 = E2.p;
+    for (int i = 0; i < m->n; ++i) {
+        const int64_t L = m->lb[i], R = m->rb[i];
+        CUDA_TRY(cudaMemcpyAsync(W.p, host_mpo_sites[i], (size_t)dl[i] * 4 * dr[i] * 16, cudaMemcpyHostToDevice, st));
+        // T1[(la,a), (p,rb)] = E[(la,a), lb] A[lb, (p,rb)]
+        if ((rc = qtn_zgemm_device('N', 'N', L * dl[i], 2 * R, L, e, L * dl[i], m->site[i], L, T1.p, L * dl[i]))) return rc;
+        const int64_t tot = L * 2 * dr[i] * R;
+        env_apply_w_kernel<<<(int)std::min<int64_t>((tot + 255) / 256, 148 * 8), 256, 0, st>>>((const double2*)T1.p, L, R, (const double2*)W.p, dl[i], dr[i], (double2*)T2.p);
+        count_launch(1);
+        // E'[ra, (b,rb)] = A^H[ra, (la,p')] T2[(la,p'), (b,rb)]
+        if ((rc = qtn_zgemm_device('C', 'N', R, dr[i] * R, 2 * L, m->site[i], 2 * L, T2.p, 2 * L, e2, R))) return rc;
+        std::swap(e, e2);
+    }
+    double2 res;
+    CUDA_TRY(cudaMemcpyAsync(&res, e, 16, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
     out[0] = res.x;
     out[1] = res.y;
     return QTN_OK;

@@ -538,11 +538,17 @@ int build_plan(int nt, const int32_t* ranks, const int64_t* const* dims, const i
     int64_t pers = 0;
     for (auto& s : pl.steps)
         if (s.invariant) { Node& o = pl.nodes[s.out]; o.persistent = true; o.offset = pers; pers += Arena::round(o.numel); }
+    // Small plans are latency-bound: give every intermediate its own buffer (no WAR hazards) so
+    // the executor can run independent steps concurrently (DAG capture).  Large plans re-use memory.
+    int64_t no_reuse = 0;
+    for (auto& s : pl.steps) if (!s.invariant && !s.final_step) no_reuse += Arena::round(pl.nodes[s.out].numel);
+    pl.dag = no_reuse <= ((int64_t)1 << 26);  // <= 1 GiB of intermediates
     Arena ar;
     for (size_t i = 0; i < pl.steps.size(); ++i) {
         Step& s = pl.steps[i];
         Node& o = pl.nodes[s.out];
         if (!s.invariant && !s.final_step) o.offset = pers + ar.alloc(o.numel);
+        if (pl.dag) continue;
         for (int x : {s.a, s.b}) {
             if (x < 0) continue;
             Node& n = pl.nodes[x];

@@ -85,6 +85,7 @@ struct Plan {
     int64_t max_elems = 1;
     double flops = 0, bytes = 0;          // per slice (all steps)
     int launches_per_slice = 0;
+    bool dag = false;                     // intermediates never alias: independent steps may overlap
     // device state (exec.cu)
     void* dev = nullptr;
 };
@@ -108,5 +109,6 @@ void plan_device_free(Plan* p);
 int plan_upload(Plan* p, const void* const* host_data);
 int plan_execute(Plan* p, int64_t s0, int64_t s1, void* dev_out);
 int plan_time_steps(Plan* p, int64_t sid, float* ms);
+int plan_result_buffer(Plan* p, void** out);
 
 }  // namespace qtn

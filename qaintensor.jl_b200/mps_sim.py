@@ -75,3 +75,49 @@ class DeviceMPS:
 def brickwork_layer_sites(nsites, half):
     """1-based left sites of the gates of half-layer 0 (bonds 1,3,5,...) or 1 (bonds 2,4,...)."""
     return list(range(1 + half, nsites, 2))
+
+
+# ---- MPO x MPS (EXTENSION iii / iv): site-tensor MPO, apply + compress, expectation value ------------
+def tfi_mpo(n, J=1.0, h=1.0):
+    """Transverse-field Ising H = -J sum Z_i Z_{i+1} - h sum X_i as a D = 3 MPO of site tensors
+    (bond_in, out, in, bond_out) (layout of src/mpo.jl:66); the reference's own MPO constructor
+    needs the dense 2^n matrix (src/mpo.jl:27) and its site-tensor constructor errors (:16-19)."""
+    W = np.zeros((3, 2, 2, 3), dtype=np.complex128)
+    W[0, :, :, 0] = np.eye(2)
+    W[1, :, :, 0] = np.diag([1.0, -1.0])
+    W[2, :, :, 0] = -h * np.array([[0, 1], [1, 0]])
+    W[2, :, :, 1] = -J * np.diag([1.0, -1.0])
+    W[2, :, :, 2] = np.eye(2)
+    return [np.asfortranarray(W[(2 if i == 0 else 0):(3 if i == 0 else 3), :, :, :(1 if i == n - 1 else 3)]) for i in range(n)]
+
+
+def _mpo_args(mpo):
+    arrs = [as_c128(w) for w in mpo]
+    for w in arrs:
+        if w.ndim != 4 or w.shape[1] != 2 or w.shape[2] != 2:
+            raise ValueError("MPO site tensors must have shape (bond_in, 2, 2, bond_out)")
+    ptrs = (C.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
+    return arrs, ptrs, _lib.arr_i64([a.shape[0] for a in arrs]), _lib.arr_i64([a.shape[3] for a in arrs])
+
+
+def _apply_mpo(self, mpo, er=0.0, maxdim=0):
+    """|psi> <- compress(MPO |psi>) with cutoff `er` and bond cap `maxdim` (default: capacity)."""
+    if len(mpo) != self.n:
+        raise ValueError("MPO and MPS lengths differ")
+    arrs, ptrs, dl, dr = _mpo_args(mpo)
+    disc = (C.c_double * max(self.n - 1, 1))()
+    check(lib.qtn_mps_apply_mpo(self._h, ptrs, dl, dr, float(er), int(maxdim), disc))
+    return [float(disc[i]) for i in range(self.n - 1)]
+
+
+def _expect_mpo(self, mpo):
+    if len(mpo) != self.n:
+        raise ValueError("MPO and MPS lengths differ")
+    arrs, ptrs, dl, dr = _mpo_args(mpo)
+    out = (C.c_double * 2)()
+    check(lib.qtn_mps_expect_mpo(self._h, ptrs, dl, dr, out))
+    return complex(out[0], out[1])
+
+
+DeviceMPS.apply_mpo = _apply_mpo
+DeviceMPS.expect_mpo = _expect_mpo

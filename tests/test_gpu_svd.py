@@ -273,3 +273,50 @@ def test_device_mps_truncated_fidelity_vs_oracle(gpu):  # EXTENSION: chi cap + c
     fid = abs(osim.overlap(got, ref)) ** 2 / (nrm_g * nrm_r)
     assert abs(fid - 1) < 1e-9 and abs(nrm_g - nrm_r) < 1e-9
     assert abs(mps.overlap(mps).real - nrm_g) < 1e-10
+
+
+def random_open_mps(rng, bonds):
+    return [crand(rng, bonds[i], 2, bonds[i + 1]) / np.sqrt(2 * bonds[i]) for i in range(len(bonds) - 1)]
+
+
+def test_mpo_expectation_and_apply_exact(gpu):  # EXTENSION iii/iv, cfg 5 algorithm at an oracle-checkable size
+    q = gpu
+    rng = np.random.default_rng(13)
+    n = 8
+    sites = random_open_mps(rng, [1, 2, 4, 8, 8, 8, 4, 2, 1])
+    mpo = q.tfi_mpo(n, 1.0, 0.7)
+    for a, b in zip(mpo, osim.tfi_mpo(n, 1.0, 0.7)):
+        assert np.array_equal(a, b)
+    H = osim.mpo_to_dense(mpo)
+    psi = osim.to_vector(sites)
+    mps = q.DeviceMPS(sites, 64)
+    want = np.vdot(psi, H @ psi)
+    got = mps.expect_mpo(mpo)
+    assert abs(got - want) < 1e-10 * abs(want) and abs(got - osim.expect_mpo(sites, mpo)) < 1e-10 * abs(want)
+    mps.apply_mpo(mpo, er=0.0, maxdim=0)
+    out = osim.to_vector(mps.download())
+    ref = H @ psi
+    ov = np.vdot(out, ref)
+    assert abs(abs(ov) ** 2 / (np.vdot(out, out).real * np.vdot(ref, ref).real) - 1) < 1e-9
+    assert rel_err(out * (ov / abs(ov)), ref) < 1e-9
+    assert abs(mps.overlap(mps).real - np.vdot(ref, ref).real) < 1e-9 * np.vdot(ref, ref).real
+
+
+def test_mpo_apply_compress_truncated_vs_oracle(gpu):  # fidelity 1e-9, bonds and discarded weights
+    q = gpu
+    rng = np.random.default_rng(14)
+    n, chi = 12, 12
+    bonds = [min(2 ** min(i, n - i), chi) for i in range(n + 1)]
+    sites = random_open_mps(rng, bonds)
+    mpo = q.tfi_mpo(n, 1.0, 1.0)
+    ref = [s.copy() for s in sites]
+    d_ref = osim.apply_mpo_compress(ref, mpo, 1e-10, chi)
+    mps = q.DeviceMPS(sites, chi)
+    d_gpu = mps.apply_mpo(mpo, er=1e-10, maxdim=chi)
+    got = mps.download()
+    assert [g.shape for g in got] == [r.shape for r in ref]
+    assert np.abs(np.array(d_gpu) - np.array(d_ref)).max() < 1e-9 * max(1.0, max(d_ref))
+    ng, nr = osim.overlap(got, got).real, osim.overlap(ref, ref).real
+    assert abs(abs(osim.overlap(got, ref)) ** 2 / (ng * nr) - 1) < 1e-9 and abs(ng / nr - 1) < 1e-9
+    e_gpu, e_ref = mps.expect_mpo(mpo), osim.expect_mpo(ref, mpo)
+    assert abs(e_gpu - e_ref) < 1e-9 * abs(e_ref)

@@ -14,6 +14,7 @@
 //   Finalisation: sigma_j = ||a_j||, stable descending sort, U = A/sigma, Vh = V^H.
 //   Truncation (K6): k = n - r* + 1 with r* the first r whose reverse-cumulated tail
 //   sqrt(s_n^2 + ... + s_{n-r+1}^2) exceeds er (strict), then k <- min(k, maxdim).
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -43,7 +44,7 @@ constexpr int JP = 2 * JB;    // panel width (columns per CTA)
 constexpr int JPITCH = JP + 2;
 constexpr int JROWS = 64;     // panel rows staged per chunk
 constexpr int JTHREADS = 256;
-constexpr int kInnerSweeps = 6;  // inner eigen-sweeps per Gram block (outer sweeps finish the job)
+constexpr int kInnerSweeps = 1;  // one eigen-sweep per Gram visit measured fastest (1: 108 ms, 2: 153, 3: 165, 6: 187 ms for 1024^2)
 
 struct SvdProblem {
     double2* A;   // m x n (lda = m), overwritten with U * diag(S) (unsorted)
@@ -62,21 +63,30 @@ __device__ __forceinline__ int panel_col(int c, int bi, int bj, int n) {
     return col < n ? col : -1;
 }
 
-// One round of the block schedule.  grid = (max pairs, batch).
+namespace cg = cooperative_groups;
+
+// One round of the block schedule.  grid = (max pairs * CL, batch); a thread-block cluster of CL CTAs
+// shares one (matrix, block pair): the panel rows are dealt out chunk-wise over the cluster, the
+// partial Gram matrices are summed through distributed shared memory, every CTA then runs the
+// identical eigensolve (same W, no broadcast) and updates its own row chunks.
 __global__ void __launch_bounds__(JTHREADS, 2)
 jacobi_round_kernel(const SvdProblem* __restrict__ probs, int round, double tol, int* __restrict__ rotated,
-                    const double* __restrict__ fro2) {
+                    const double* __restrict__ fro2, int inner_sweeps) {
+    cg::cluster_group cluster = cg::this_cluster();
+    const int CL = (int)cluster.num_blocks(), crank = (int)cluster.block_rank();
+    const int pair = blockIdx.x / CL;
+    if (rotated[blockIdx.y] < 0) return;  // this matrix converged in an earlier sweep (cluster-uniform)
     const SvdProblem pr = probs[blockIdx.y];
     // deflation: a column below 1e-15 * ||A||_F is rounding noise (LAPACK resolves nothing there
     // either); rotating it against a large, exactly parallel column would only shrink it by eps
     // per sweep until it underflows (rank-deficient product states hit exactly this)
     const double dthr = 1e-30 * fro2[blockIdx.y];
     const int nb = pr.nblocks;
-    if (nb < 2 || (int)blockIdx.x >= nb / 2 || round >= nb - 1) return;
+    if (nb < 2 || pair >= nb / 2 || round >= nb - 1) return;
     // circle method: pair 0 = (nb-1, round); pair k = ((round+k) % (nb-1), (round-k) % (nb-1))
     int bi, bj;
-    if (blockIdx.x == 0) { bi = nb - 1; bj = round; }
-    else { bi = (round + blockIdx.x) % (nb - 1); bj = (round - (int)blockIdx.x + (nb - 1)) % (nb - 1); }
+    if (pair == 0) { bi = nb - 1; bj = round; }
+    else { bi = (round + pair) % (nb - 1); bj = (round - pair + (nb - 1)) % (nb - 1); }
     if (bi > bj) { int t = bi; bi = bj; bj = t; }
     if (bi * JB >= pr.n) return;  // padding block only
 
@@ -84,7 +94,8 @@ jacobi_round_kernel(const SvdProblem* __restrict__ probs, int round, double tol,
     double2* Ps = reinterpret_cast<double2*>(smem_raw);   // [JROWS][JPITCH] panel chunk
     double2* G = Ps + JROWS * JPITCH;                     // [JP][JPITCH]
     double2* W = G + JP * JPITCH;                         // [JP][JPITCH]
-    double2* rot = W + JP * JPITCH;                       // [JB] (c, s) + phase
+    double2* Gpart = W + JP * JPITCH;                     // [JP][JPITCH] this CTA's partial Gram (read by the cluster)
+    double2* rot = Gpart + JP * JPITCH;                   // [JB] (c, s) + phase
     double2* rph = rot + JB;                              // [JB] e^{i phi}
     __shared__ int s_any, s_sweep_any, s_rot;
     __shared__ int s_cols[JP];
@@ -92,7 +103,7 @@ jacobi_round_kernel(const SvdProblem* __restrict__ probs, int round, double tol,
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid < JP) s_cols[tid] = panel_col(tid, bi, bj, pr.n);
     if (tid == 0) { s_any = 0; s_rot = 0; }
-    for (int i = tid; i < JP * JPITCH; i += JTHREADS) { G[i] = make_double2(0, 0); W[i] = make_double2(0, 0); }
+    for (int i = tid; i < JP * JPITCH; i += JTHREADS) { G[i] = make_double2(0, 0); W[i] = make_double2(0, 0); Gpart[i] = make_double2(0, 0); }
     __syncthreads();
 
     // ---------------- phase 1: G = P^H P (each warp takes rows warp*8.. of every chunk) -----------
@@ -117,11 +128,12 @@ jacobi_round_kernel(const SvdProblem* __restrict__ probs, int round, double tol,
 #pragma unroll
         for (int i = 0; i < JP * JROWS / JTHREADS; ++i) Ps[r * JPITCH + tid / JROWS + i * (JTHREADS / JROWS)] = pre[i];
     };
-    fetch(pr.A, pr.m, 0, pr.m);
-    for (int r0 = 0; r0 < pr.m; r0 += JROWS) {
+    const int cstep = CL * JROWS;  // this CTA takes chunks crank, crank + CL, ...
+    if (crank * JROWS < pr.m) fetch(pr.A, pr.m, crank * JROWS, pr.m);
+    for (int r0 = crank * JROWS; r0 < pr.m; r0 += cstep) {
         stash();
         __syncthreads();
-        if (r0 + JROWS < pr.m) fetch(pr.A, pr.m, r0 + JROWS, pr.m);
+        if (r0 + cstep < pr.m) fetch(pr.A, pr.m, r0 + cstep, pr.m);
         // warp w owns k-rows [8w, 8w+8) of the chunk: two k4 steps
 #pragma unroll
         for (int k4 = 0; k4 < 2; ++k4) {
@@ -152,11 +164,21 @@ jacobi_round_kernel(const SvdProblem* __restrict__ probs, int round, double tol,
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
                 const int row = i * 8 + (lane >> 2), col = j * 8 + 2 * (lane & 3) + q;
-                atomicAdd(&G[row * JPITCH + col].x, gr[i][j][q]);
-                atomicAdd(&G[row * JPITCH + col].y, gi[i][j][q]);
+                atomicAdd(&Gpart[row * JPITCH + col].x, gr[i][j][q]);
+                atomicAdd(&Gpart[row * JPITCH + col].y, gi[i][j][q]);
             }
         }
-    __syncthreads();
+    cluster.sync();  // every CTA's partial Gram is complete (also a CTA barrier)
+    for (int e = tid; e < JP * JPITCH; e += JTHREADS) {
+        double2 acc = make_double2(0, 0);
+        for (int r = 0; r < CL; ++r) {  // fixed order: every CTA of the cluster gets bit-identical sums
+            const double2 v = cluster.map_shared_rank(Gpart, r)[e];
+            acc.x += v.x;
+            acc.y += v.y;
+        }
+        G[e] = acc;
+    }
+    cluster.sync();  // remote reads done before anyone may leave
     // mirror the strictly-lower block triangle, set W = I
     for (int e = tid; e < JP * JP; e += JTHREADS) {
         const int r = e / JP, c = e % JP;
@@ -166,7 +188,7 @@ jacobi_round_kernel(const SvdProblem* __restrict__ probs, int round, double tol,
     __syncthreads();
 
     // ---------------- phase 2: Hermitian Jacobi on G, W accumulates the rotations -------------------
-    for (int sweep = 0; sweep < kInnerSweeps; ++sweep) {
+    for (int sweep = 0; sweep < inner_sweeps; ++sweep) {
         if (tid == 0) s_sweep_any = 0;
         __syncthreads();
         for (int step = 0; step < JP - 1; ++step) {
@@ -265,7 +287,7 @@ jacobi_round_kernel(const SvdProblem* __restrict__ probs, int round, double tol,
         if (!any_now) break;
     }
     if (!s_any) return;  // panel already orthogonal and ordered: nothing to update
-    if (tid == 0 && s_rot) rotated[blockIdx.y] = 1;  // pure re-ordering swaps do not keep the sweeps going
+    if (tid == 0 && s_rot && crank == 0) rotated[blockIdx.y] = 1;  // pure re-ordering swaps do not keep the sweeps going
 
     // ---------------- phase 3: P <- P W for the A panel and the V panel ---------------------------------
     // warp w owns rows [8w, 8w+8) of each 64-row chunk: C(8 x 32) = P(8 x 32) W(32 x 32)
@@ -273,12 +295,12 @@ jacobi_round_kernel(const SvdProblem* __restrict__ probs, int round, double tol,
         double2* base = which ? pr.V : pr.A;
         const int nrows = which ? pr.n : pr.m;
         __syncthreads();
-        fetch(base, nrows, 0, nrows);
-        for (int r0 = 0; r0 < nrows; r0 += JROWS) {
+        if (crank * JROWS < nrows) fetch(base, nrows, crank * JROWS, nrows);
+        for (int r0 = crank * JROWS; r0 < nrows; r0 += cstep) {
             __syncthreads();
             stash();
             __syncthreads();
-            if (r0 + JROWS < nrows) fetch(base, nrows, r0 + JROWS, nrows);
+            if (r0 + cstep < nrows) fetch(base, nrows, r0 + cstep, nrows);
             double cr[4][2], ci[4][2];
 #pragma unroll
             for (int j = 0; j < 4; ++j) cr[j][0] = cr[j][1] = ci[j][0] = ci[j][1] = 0.0;
@@ -542,24 +564,51 @@ int svd_batched_device(int batch, const SvdJob* jobs, double er, int64_t maxdim,
     set_identity_kernel<<<dim3(std::min(148 * 4, (maxn * maxn + 255) / 256), batch), 256, 0, st>>>(dp);
     fro_norm_kernel<<<dim3(std::min(148, (maxn * maxm + 255) / 256), batch), 256, 0, st>>>(dp, dfro);
     count_launch(2);
-    const size_t smem = (size_t)(JROWS * JPITCH + 2 * JP * JPITCH + 2 * JB) * 16 + JB * 8 + 64;
+    const size_t smem = (size_t)(JROWS * JPITCH + 3 * JP * JPITCH + 2 * JB) * 16 + JB * 8 + 64;
     static bool attr = false;
     if (!attr) { CUDA_TRY(cudaFuncSetAttribute(jacobi_round_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
     int max_nb = (maxn + JB - 1) / JB;
     if (max_nb & 1) ++max_nb;
     const double tol = 1e-15 * std::sqrt((double)std::max(maxm, 1)) * 0.5 + 2.3e-16;
+    // cluster size: split the panel rows over up to 8 CTAs when the (pairs x batch) grid alone cannot
+    // fill the 148 SMs (single large matrices, e.g. the sequential MPO compression sweeps)
+    int cl = 1;
+    {
+        const long ctas = (long)(max_nb / 2) * batch;
+        const int chunks = (maxm + JROWS - 1) / JROWS;
+        while (cl < 8 && ctas * cl * 2 <= 2 * 148 && cl * 2 <= chunks) cl *= 2;
+    }
+    int inner = kInnerSweeps;
+    if (const char* e = getenv("QTN_JACOBI_INNER")) inner = std::max(1, atoi(e));
     int sweeps = 0;
-    const int kMaxSweeps = 40;
+    const int kMaxSweeps = 60;
     if (max_nb >= 2) {
         for (; sweeps < kMaxSweeps; ++sweeps) {
-            CUDA_TRY(cudaMemsetAsync(drot, 0, (size_t)batch * 4, st));
-            for (int round = 0; round < max_nb - 1; ++round)
-                jacobi_round_kernel<<<dim3(max_nb / 2, batch), JTHREADS, smem, st>>>(dp, round, tol, drot, dfro);
+            // flags: 0 = no rotation yet this sweep, 1 = rotated, -1 = converged (its CTAs exit at once)
+            CUDA_TRY(cudaMemcpyAsync(drot, hrot, (size_t)batch * 4, cudaMemcpyHostToDevice, st));
+            for (int round = 0; round < max_nb - 1; ++round) {
+                cudaLaunchConfig_t cfg = {};
+                cfg.gridDim = dim3((unsigned)(max_nb / 2 * cl), (unsigned)batch, 1);
+                cfg.blockDim = dim3(JTHREADS, 1, 1);
+                cfg.dynamicSmemBytes = smem;
+                cfg.stream = st;
+                cudaLaunchAttribute at[1];
+                at[0].id = cudaLaunchAttributeClusterDimension;
+                at[0].val.clusterDim.x = (unsigned)cl;
+                at[0].val.clusterDim.y = 1;
+                at[0].val.clusterDim.z = 1;
+                cfg.attrs = at;
+                cfg.numAttrs = 1;
+                CUDA_TRY(cudaLaunchKernelEx(&cfg, jacobi_round_kernel, dp, round, tol, drot, (const double*)dfro, inner));
+            }
             count_launch(max_nb - 1);
             CUDA_TRY(cudaMemcpyAsync(hrot, drot, (size_t)batch * 4, cudaMemcpyDeviceToHost, st));
             CUDA_TRY(cudaStreamSynchronize(st));
             bool any = false;
-            for (int b = 0; b < batch; ++b) any |= hrot[b] != 0;
+            for (int b = 0; b < batch; ++b) {
+                if (hrot[b] > 0) { any = true; hrot[b] = 0; }
+                else hrot[b] = -1;
+            }
             if (!any) { ++sweeps; break; }
         }
     }

@@ -1,0 +1,105 @@
+# QaintensorCUDA.jl -- `ccall` glue that lets Qaintensor.jl drive libqaintensor_cuda.
+#
+# Drop this file next to the reference's sources and apply the edits listed in INTEGRATION.md.
+# It could not be executed in the build environment (no `julia` binary); every call below is the
+# 1:1 transcription of the ctypes signatures in qaintensor.jl_b200/_lib.py, which the GPU tests run.
+module QaintensorCUDA
+
+const LIB = get(ENV, "QAINTENSOR_CUDA_LIB", "libqaintensor_cuda")
+const QTN_C128 = Cint(0)
+const QTN_EDOMAIN = Cint(-6)
+
+struct QtnError <: Exception
+    code::Cint
+    msg::String
+end
+
+last_error() = unsafe_string(ccall((:qtn_last_error, LIB), Cstring, ()))
+
+function check(rc::Cint)
+    rc == 0 && return nothing
+    msg = last_error()
+    # QTN_EDOMAIN carries the reference's own error() strings (src/svd.jl:9, :16): re-raise unchanged
+    rc == QTN_EDOMAIN ? error(msg) : throw(QtnError(rc, msg))
+end
+
+function __init__()
+    # no CPU fallback: this throws QtnError(-2, ...) when no sm_100 device is usable
+    check(ccall((:qtn_init, LIB), Cint, (Cint,), parse(Cint, get(ENV, "LOCAL_RANK", "0"))))
+end
+
+# ---- TensorOperations.ncon replacement (src/contract.jl:257, :263) ---------------------------------
+function ncon(tensors::Vector{<:Array{ComplexF64}}, network::Vector{Vector{Int}}; order=nothing)
+    nt = length(tensors)
+    ranks = Cint[ndims(t) for t in tensors]
+    dims = [Int64[size(t)...] for t in tensors]
+    labs = [Cint.(l) for l in network]
+    nout = 1
+    for (t, l) in zip(tensors, network), j in 1:ndims(t)
+        l[j] < 0 && (nout *= size(t, j))
+    end
+    out = Vector{ComplexF64}(undef, max(nout, 1))
+    rank = Ref{Cint}(0)
+    odims = zeros(Int64, 64)
+    ord = order === nothing ? Cint[] : Cint.(order)
+    tptr = Ptr{Cvoid}[pointer(t) for t in tensors]
+    dptr = Ptr{Int64}[pointer(d) for d in dims]
+    lptr = Ptr{Cint}[pointer(l) for l in labs]
+    GC.@preserve tensors dims labs ord out begin
+        check(ccall((:qtn_contract, LIB), Cint,
+            (Cint, Ptr{Ptr{Cvoid}}, Ptr{Cint}, Ptr{Ptr{Int64}}, Ptr{Ptr{Cint}}, Ptr{Cint}, Cint, Cint,
+             Ptr{Cvoid}, Ref{Cint}, Ptr{Int64}),
+            nt, tptr, ranks, dptr, lptr, order === nothing ? C_NULL : pointer(ord), length(ord), QTN_C128,
+            out, rank, odims))
+    end
+    r = Int(rank[])
+    r == 0 ? fill(out[1]) : reshape(out[1:nout], Tuple(odims[1:r]))
+end
+
+# ---- contraction_order(net) replacement (src/network2graph.jl:429-446) --------------------------------
+function treewidth_perm(ntensors::Integer, pairs::Vector{NTuple{4,Int}})
+    nc = length(pairs)
+    flat = Cint[x for p in pairs for x in p]
+    perm = Vector{Cint}(undef, max(nc, 1))
+    tw = Ref{Cint}(0)
+    check(ccall((:qtn_order_treewidth, LIB), Cint, (Cint, Cint, Ptr{Cint}, Ptr{Cint}, Ref{Cint}),
+                ntensors, nc, flat, perm, tw))
+    Int.(perm[1:nc]), Int(tw[])
+end
+
+# ---- LinearAlgebra.svd + tail-norm rule (src/svd.jl:26-33) + max-bond cap (extension) ------------------
+function svd_trunc(A::Matrix{ComplexF64}; er::Float64=-1.0, maxdim::Integer=0)
+    m, n = size(A)
+    r = min(m, n)
+    U = Matrix{ComplexF64}(undef, m, r)
+    S = Vector{Float64}(undef, r)
+    Vh = Matrix{ComplexF64}(undef, r, n)
+    k = Ref{Int64}(0)
+    check(ccall((:qtn_svd_trunc, LIB), Cint,
+        (Ptr{Cvoid}, Int64, Int64, Cdouble, Int64, Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cvoid}, Ref{Int64}),
+        A, m, n, er, maxdim, U, S, Vh, k))
+    U, S, Vh, Int(k[])
+end
+
+# ---- contract_svd (src/svd.jl:7-38) -------------------------------------------------------------------
+function contract_svd(T1::Array{ComplexF64}, T2::Array{ComplexF64}, indx::NTuple{2,Int}; er=0.0)
+    i1, i2 = indx
+    d1, d2 = Int64[size(T1)...], Int64[size(T2)...]
+    newdim = (d1[1:i1-1]..., d1[i1+1:end]..., d2[1:i2-1]..., d2[i2+1:end]...)
+    out = Array{ComplexF64}(undef, newdim...)
+    check(ccall((:qtn_contract_svd, LIB), Cint,
+        (Ptr{Cvoid}, Cint, Ptr{Int64}, Cint, Ptr{Cvoid}, Cint, Ptr{Int64}, Cint, Cdouble, Ptr{Cvoid}),
+        T1, ndims(T1), d1, i1, T2, ndims(T2), d2, i2, Float64(er), out))
+    out
+end
+
+# ---- permutedims (src/contract.jl:244, src/switch.jl:29-35) ----------------------------------------------
+function permutedims_gpu(A::Array{ComplexF64}, perm)
+    p = collect(Int, perm)
+    out = Array{ComplexF64}(undef, size(A)[p]...)
+    check(ccall((:qtn_permutedims, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Int64}, Ptr{Cint}, Cint, Ptr{Cvoid}),
+                A, ndims(A), Int64[size(A)...], Cint.(p), QTN_C128, out))
+    out
+end
+
+end # module

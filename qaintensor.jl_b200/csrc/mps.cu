@@ -19,6 +19,7 @@ struct SvdJob {
     double2* U;
     double* S;
     double2* Vh;
+    bool need_v = true;
 };
 int svd_batched_device(int batch, const SvdJob* jobs, double er, int64_t maxdim, int64_t* k_out, double* disc_out,
                        int* sweeps_out);
@@ -304,6 +305,12 @@ int qtn_mps_apply_layer(qtn_mps* m, int32_t ngates, const int32_t* sites, const 
         apply_gate2_kernel<<<blocks, 256, 0, st>>>(th, L, R, m->gates + 16 * g);
         count_launch(1);
         jobs[g] = SvdJob{th, 2 * L, 2 * R, m->ubuf + mat * g, m->sbuf + 2 * m->cap * g, m->vbuf + mat * g};
+        if (L >= R) {
+            // U-only SVD: the right site S*V'[:k] equals U[:, :k]^H theta exactly, so V is never accumulated
+            // (halves the rotation updates); theta is saved in the V scratch because the Jacobi overwrites it
+            jobs[g].need_v = false;
+            CUDA_TRY(cudaMemcpyAsync(m->vbuf + mat * g, th, (size_t)4 * L * R * 16, cudaMemcpyDeviceToDevice, st));
+        }
     }
     std::vector<int64_t> k(ngates);
     if ((rc = svd_batched_device(ngates, jobs.data(), er, maxdim, k.data(), disc_out, nullptr))) return rc;
@@ -313,7 +320,11 @@ int qtn_mps_apply_layer(qtn_mps* m, int32_t ngates, const int32_t* sites, const 
         int64_t kk = std::max<int64_t>(k[g], 1);  // keep at least one state
         // T_i <- U[:, :k] (L,2,k);  T_{i+1} <- diag(S) V'[:k, :] (k,2,R)      (src/switch.jl:50-52)
         if ((rc = scale_copy(m->ubuf + mat * g, 2 * L, m->site[i], 2 * L, 2 * L, kk, nullptr, 1))) return rc;
-        if ((rc = scale_copy(m->vbuf + mat * g, rfull, m->site[i + 1], kk, kk, 2 * R, m->sbuf + 2 * m->cap * g, 0))) return rc;
+        if (jobs[g].need_v) {
+            if ((rc = scale_copy(m->vbuf + mat * g, rfull, m->site[i + 1], kk, kk, 2 * R, m->sbuf + 2 * m->cap * g, 0))) return rc;
+        } else {
+            if ((rc = qtn_zgemm_device('C', 'N', kk, 2 * R, 2 * L, m->ubuf + mat * g, 2 * L, m->vbuf + mat * g, 2 * L, m->site[i + 1], kk))) return rc;
+        }
         m->rb[i] = kk;
         m->lb[i + 1] = kk;
     }

@@ -291,7 +291,7 @@ jacobi_round_kernel(const SvdProblem* __restrict__ probs, int round, double tol,
 
     // ---------------- phase 3: P <- P W for the A panel and the V panel ---------------------------------
     // warp w owns rows [8w, 8w+8) of each 64-row chunk: C(8 x 32) = P(8 x 32) W(32 x 32)
-    for (int which = 0; which < 2; ++which) {
+    for (int which = 0; which < (pr.V ? 2 : 1); ++which) {
         double2* base = which ? pr.V : pr.A;
         const int nrows = which ? pr.n : pr.m;
         __syncthreads();
@@ -345,6 +345,7 @@ __global__ void fro_norm_kernel(const SvdProblem* probs, double* fro2) {
 
 __global__ void set_identity_kernel(const SvdProblem* probs) {
     const SvdProblem pr = probs[blockIdx.y];
+    if (!pr.V) return;
     const size_t nn = (size_t)pr.n * pr.n;
     for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < nn; e += (size_t)gridDim.x * blockDim.x)
         pr.V[e] = make_double2((e % pr.n) == (e / pr.n) ? 1.0 : 0.0, 0.0);
@@ -428,6 +429,7 @@ __global__ void scatter_factors_kernel(const SvdProblem* probs, double* const* s
             else f.Vh[(size_t)r * n + dst] = make_double2(v.x, -v.y);     // Vh (n x m0=m) row dst = conj(column)
         } else {
             const int rr = r - m;
+            if (!pr.V) continue;
             const double2 v = pr.V[(size_t)j * n + rr];
             if (!f.transposed) f.Vh[(size_t)rr * n + dst] = make_double2(v.x, -v.y);  // Vh is n x n
             else f.U[(size_t)dst * n + rr] = v;                                        // U (m0=n x n)
@@ -482,7 +484,8 @@ struct SvdJob {
     int64_t m0, n0;
     double2* U;  // m0 x r
     double* S;   // r
-    double2* Vh; // r x n0
+    double2* Vh; // r x n0 (ignored when !need_v)
+    bool need_v = true;  // false: sigma and U only (m0 >= n0); callers form S*Vh = U^H A themselves
 };
 
 // Runs the batch; k_out / disc_out are host arrays (batch).  Synchronises the stream.
@@ -532,7 +535,7 @@ int svd_batched_device(int batch, const SvdJob* jobs, double er, int64_t maxdim,
         const int64_t m0 = jobs[b].m0, n0 = jobs[b].n0;
         const int m = (int)(tr[b] ? n0 : m0), n = (int)(tr[b] ? m0 : n0);
         hp[b].A = tr[b] ? (double2*)(base + offAt[b]) : jobs[b].A;
-        hp[b].V = (double2*)(base + offV[b]);
+        hp[b].V = (jobs[b].need_v || tr[b]) ? (double2*)(base + offV[b]) : nullptr;
         hp[b].m = m;
         hp[b].n = n;
         int nbk = (n + JB - 1) / JB;

@@ -39,6 +39,7 @@ def parse():
     ap.add_argument("--max-log2", type=int, default=28, help="slice until the largest tensor has <= 2^k elements")
     ap.add_argument("--cpu-max-log2", type=int, default=26, help="slicing level of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--precision", default="c128", choices=["c128", "c64"], help="c64 = optional ComplexF32 mode (cfg2/cfg3)")
     return ap.parse_args()
 
 
@@ -395,16 +396,19 @@ def main():
     arrays = [t.data for t in net.tensors]
     shapes = [a.shape for a in arrays]
     S = q.choose_slices(shapes, il, None, args.max_log2, 1) if args.workload == "cfg3" else []
-    plan = q.ContractionPlan(shapes, il, None, S)
+    plan = q.ContractionPlan(shapes, il, None, S, precision=args.precision)
     sps = args.slices_per_step if plan.nslices > 1 else 1
     plan.upload(arrays)
-    out = torch.zeros(2 * plan.out_numel, dtype=torch.float64, device="cuda")
+    out = torch.zeros(2 * plan.out_numel, dtype=torch.float64 if args.precision == "c128" else torch.float32, device="cuda")
 
     def device_step(i):
         base = ((i * world + rank) * sps) % max(plan.nslices - sps + 1, 1)
         plan.execute_device(out.data_ptr(), base, base + sps)
         if world > 1:
-            _lib.check(_lib.lib.qtn_nccl_allreduce_sum_f64(out.data_ptr(), 2 * plan.out_numel))
+            if args.precision == "c128":
+                _lib.check(_lib.lib.qtn_nccl_allreduce_sum_f64(out.data_ptr(), 2 * plan.out_numel))
+            else:
+                dist.all_reduce(out)
 
     def sync_all():
         torch.cuda.synchronize()
@@ -495,7 +499,7 @@ def main():
                    "sample": sample + "; %.2f s per sample" % cdt}
         line = {"metric": "amplitudes/s", "value": value, "unit": "amplitudes/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "vs_baseline": None, "dtype": "f64" if args.precision == "c128" else "f32", "data": "synthetic",
                 "config": {"workload": name, "slices_per_amplitude": plan.nslices, "slices_per_step_per_gpu": sps,
                            "slice_labels": len(S), "max_tensor_elems_log2": int(np.log2(plan.max_elems)),
                            "flops_per_slice": plan.flops_per_slice, "pairwise_steps_per_slice": plan.nsteps - plan.n_invariant,

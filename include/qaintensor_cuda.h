@@ -83,7 +83,8 @@ int qtn_order_exhaustive(int32_t nt, const int32_t* ranks, const int32_t* const*
  * executed many times with new tensor data of the same shapes.
  *   order == NULL  -> ascending positive labels (ncon default).
  *   slice_labels   -> EXTENSION (no reference counterpart): labels fixed per slice.
- *   dtype          -> QTN_C128 (ComplexF64) or QTN_C64 (ComplexF32 mode).        */
+ *   dtype          -> QTN_C128 (ComplexF64, FP64 tensor pipe) or QTN_C64 (optional
+ *                     ComplexF32 mode on the FP32 pipes; buffers are then float pairs). */
 #define QTN_C128 0
 #define QTN_C64 1
 int qtn_plan_create(int32_t nt, const int32_t* ranks, const int64_t* const* dims,

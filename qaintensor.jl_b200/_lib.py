@@ -13,6 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libqaintensor_cuda.so")
 
 QTN_C128 = 0
+QTN_C64 = 1
 QTN_ENODEVICE = -2
 QTN_EDOMAIN = -6
 
@@ -128,6 +129,19 @@ def launch_count(reset=False):
 def as_c128(a):
     """Column-major ComplexF64 copy/view of ``a`` (the ABI's memory layout)."""
     return np.asfortranarray(np.asarray(a, dtype=np.complex128))
+
+
+def as_cx(a, dtype_code):
+    """Column-major complex array in the precision of `dtype_code` (QTN_C128 / QTN_C64)."""
+    return np.asfortranarray(np.asarray(a, dtype=np.complex64 if dtype_code == QTN_C64 else np.complex128))
+
+
+def dtype_code(precision):
+    if precision in (None, "c128", "ComplexF64", QTN_C128):
+        return QTN_C128
+    if precision in ("c64", "ComplexF32", QTN_C64):
+        return QTN_C64
+    raise ValueError("precision must be 'c128' (ComplexF64) or 'c64' (ComplexF32 mode)")
 
 
 def arr_i32(v):

@@ -50,7 +50,9 @@ def contract_order(net, leg_costs, indexlist):
 class ContractionPlan:
     """Reusable plan: ``qtn_plan_create`` ... ``qtn_plan_destroy``."""
 
-    def __init__(self, shapes, labels, order=None, slice_labels=()):
+    def __init__(self, shapes, labels, order=None, slice_labels=(), precision="c128"):
+        self.dtype = _lib.dtype_code(precision)
+        self.np_dtype = np.complex64 if self.dtype == _lib.QTN_C64 else np.complex128
         self.shapes = [tuple(int(d) for d in s) for s in shapes]
         self.labels = [list(l) for l in labels]
         self._args = NetworkArgs(self.shapes, self.labels)
@@ -58,7 +60,7 @@ class ContractionPlan:
         ord_arr = arr_i32(order) if order is not None else None
         check(lib.qtn_plan_create(self._args.nt, self._args.ranks, self._args.dims, self._args.labels, ord_arr,
                                   len(order) if order is not None else 0, arr_i32(list(slice_labels)),
-                                  len(slice_labels), _lib.QTN_C128, C.byref(self._h)))
+                                  len(slice_labels), self.dtype, C.byref(self._h)))
         info = (C.c_int64 * 8)()
         cost = (C.c_double * 2)()
         check(lib.qtn_plan_info(self._h, info, cost))
@@ -77,7 +79,7 @@ class ContractionPlan:
         return [(int(mnk[3 * i]), int(mnk[3 * i + 1]), int(mnk[3 * i + 2]), int(flags[i])) for i in range(self.nsteps)]
 
     def _marshal(self, arrays):
-        arrs = [as_c128(a) for a in arrays]
+        arrs = [_lib.as_cx(a, self.dtype) for a in arrays]
         for a, s in zip(arrs, self.shapes):
             if tuple(a.shape) != s:
                 raise ValueError("tensor shape %r does not match the plan's %r" % (a.shape, s))
@@ -96,7 +98,7 @@ class ContractionPlan:
     def execute(self, arrays=None, slice_begin=0, slice_end=None):
         """Host in, host out (sum over the requested slices)."""
         _lib.require_device()
-        out = np.zeros(self.out_dims, dtype=np.complex128, order="F")
+        out = np.zeros(self.out_dims, dtype=self.np_dtype, order="F")
         ptrs = None
         if arrays is not None:
             arrs = self._marshal(arrays)
@@ -109,7 +111,7 @@ class ContractionPlan:
         """Slice-parallel contraction of the window [first_slice, first_slice + nslices)
         (default: all slices): this rank's contiguous block + one NCCL allreduce."""
         _lib.require_device()
-        out = np.zeros(self.out_dims, dtype=np.complex128, order="F")
+        out = np.zeros(self.out_dims, dtype=self.np_dtype, order="F")
         ptrs = None
         if arrays is not None:
             arrs = self._marshal(arrays)
@@ -147,10 +149,12 @@ def choose_slices(shapes, labels, order=None, max_log2_elems=28, min_slices=1):
     return [int(out[i]) for i in range(n.value)]
 
 
-def ncon(arrays, indexlist, order=None):
-    """``TensorOperations.ncon(tensors, indexlist; order)`` on the GPU (one-shot)."""
+def ncon(arrays, indexlist, order=None, precision="c128"):
+    """``TensorOperations.ncon(tensors, indexlist; order)`` on the GPU (one-shot).
+    ``precision="c64"`` selects the optional ComplexF32 mode (EXTENSION vii)."""
     _lib.require_device()
-    arrs = [as_c128(a) for a in arrays]
+    code = _lib.dtype_code(precision)
+    arrs = [_lib.as_cx(a, code) for a in arrays]
     args = NetworkArgs([a.shape for a in arrs], indexlist)
     nopen = sum(1 for l in indexlist for x in l if x < 0)
     out_n = 1
@@ -158,14 +162,14 @@ def ncon(arrays, indexlist, order=None):
         for d, x in zip(a.shape, l):
             if x < 0:
                 out_n *= d
-    out = np.zeros(max(out_n, 1), dtype=np.complex128)
+    out = np.zeros(max(out_n, 1), dtype=np.complex64 if code == _lib.QTN_C64 else np.complex128)
     rank = C.c_int32(0)
     dims = (C.c_int64 * 64)()
     if nopen > 64:
         raise ValueError("more than 64 open legs")
     ord_arr = arr_i32(order) if order is not None else None
     check(lib.qtn_contract(args.nt, data_ptrs(arrs), args.ranks, args.dims, args.labels, ord_arr,
-                           len(order) if order is not None else 0, _lib.QTN_C128, out.ctypes.data_as(C.c_void_p),
+                           len(order) if order is not None else 0, code, out.ctypes.data_as(C.c_void_p),
                            C.byref(rank), dims))
     shape = tuple(int(dims[i]) for i in range(rank.value))
     return np.reshape(out[:out_n], shape, order="F")
@@ -182,10 +186,12 @@ def permutedims(a, perm):
     return out
 
 
-def contract(net, optimize=False):
-    """``contract(net::TensorNetwork, optimize::Bool=false)`` (src/contract.jl:242-264)."""
+def contract(net, optimize=False, precision="c128"):
+    """``contract(net::TensorNetwork, optimize::Bool=false)`` (src/contract.jl:242-264).
+    ``precision`` is an EXTENSION keyword with the reference-preserving default ComplexF64."""
     if len(net.tensors) == 1:
-        return permutedims(net.tensors[0].data, [l for (_, l) in net.openidx])
+        out = permutedims(net.tensors[0].data, [l for (_, l) in net.openidx])
+        return out.astype(np.complex64) if _lib.dtype_code(precision) == _lib.QTN_C64 else out
     arrays = [t.data for t in net.tensors]
     if optimize:
         leg_costs, indexlist = contract_rep(net, True)
@@ -196,5 +202,5 @@ def contract(net, optimize=False):
             for j, x in enumerate(lab):
                 if x > 0:
                     lab[j] = sequence.index(x) + 1
-        return ncon(arrays, indexlist, order=sequence)
-    return ncon(arrays, contract_rep(net))
+        return ncon(arrays, indexlist, order=sequence, precision=precision)
+    return ncon(arrays, contract_rep(net), precision=precision)

@@ -202,12 +202,13 @@ int qtn_nccl_init(int32_t rank, int32_t nranks, const void* id) {
     if (e) return fail(QTN_ENCCL, "ncclCommInitRank: %s", p_ncclGetErrorString ? p_ncclGetErrorString(e) : "?");
     return QTN_OK;
 }
-int qtn_nccl_allreduce_sum_f64(void* dev_buf, int64_t count) {
+static int nccl_allreduce(void* dev_buf, int64_t count, int nccl_dtype) {
     if (!g_comm) return fail(QTN_ENCCL, "qtn_nccl_init has not been called");
-    int e = p_ncclAllReduce(dev_buf, dev_buf, (size_t)count, /*ncclFloat64*/ 8, /*ncclSum*/ 0, g_comm, stream());
+    int e = p_ncclAllReduce(dev_buf, dev_buf, (size_t)count, nccl_dtype, /*ncclSum*/ 0, g_comm, stream());
     if (e) return fail(QTN_ENCCL, "ncclAllReduce: %s", p_ncclGetErrorString ? p_ncclGetErrorString(e) : "?");
     return QTN_OK;
 }
+int qtn_nccl_allreduce_sum_f64(void* dev_buf, int64_t count) { return nccl_allreduce(dev_buf, count, /*ncclFloat64*/ 8); }
 
 static int exec_host(Plan* p, const void* const* host_data, int64_t s0, int64_t s1, void* host_out, bool allreduce) {
     int rc = QTN_OK;
@@ -216,9 +217,10 @@ static int exec_host(Plan* p, const void* const* host_data, int64_t s0, int64_t 
     void* out = nullptr;
     if ((rc = plan_result_buffer(p, &out))) return rc;
     rc = plan_execute(p, s0, s1, out);
-    if (!rc && allreduce) rc = qtn_nccl_allreduce_sum_f64(out, 2 * p->out_numel);
+    const size_t es = p->dtype == QTN_C64 ? 8 : 16;
+    if (!rc && allreduce) rc = p->dtype == QTN_C64 ? nccl_allreduce(out, 2 * p->out_numel, /*ncclFloat32*/ 7) : qtn_nccl_allreduce_sum_f64(out, 2 * p->out_numel);
     if (!rc) {
-        cudaError_t e = cudaMemcpyAsync(host_out, out, (size_t)p->out_numel * 16, cudaMemcpyDeviceToHost, stream());
+        cudaError_t e = cudaMemcpyAsync(host_out, out, (size_t)p->out_numel * es, cudaMemcpyDeviceToHost, stream());
         if (e == cudaSuccess) e = cudaStreamSynchronize(stream());
         if (e != cudaSuccess) rc = fail(QTN_ECUDA, "result download failed: %s", cudaGetErrorString(e));
     }
@@ -278,9 +280,9 @@ int qtn_zgemm_device(char opa, char opb, int64_t m, int64_t n, int64_t k, const 
     if (m <= 0 || n <= 0) return QTN_OK;
     GemmArgs g;
     memset(&g, 0, sizeof(g));
-    g.A = (const double2*)dev_a;
-    g.B = (const double2*)dev_b;
-    g.C = (double2*)dev_c;
+    g.A = dev_a;
+    g.B = dev_b;
+    g.C = dev_c;
     auto lin = [](int64_t stride) { TabArg t; t.lo = nullptr; t.hi = nullptr; t.L = stride; t.shift = -1; return t; };
     g.a_row = lin(opa == 'N' ? 1 : lda);
     g.a_k = lin(opa == 'N' ? lda : 1);

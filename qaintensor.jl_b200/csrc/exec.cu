@@ -83,6 +83,8 @@ int device_ready() {
 // ---------------------------------------------------------------------------
 // GEMM launch (shared by plans and the dense qtn_zgemm_device entry point)
 // ---------------------------------------------------------------------------
+int launch_cgemm(GemmArgs& g, int variant, int split_k, cudaStream_t st);
+
 template <int BM, int BN, int WM, int WN, int BK, int STAGES>
 static int launch_gemm_t(GemmArgs& g, int split_k, cudaStream_t st) {
     constexpr int NT = (BM / WM) * (BN / WN) * 32;
@@ -114,7 +116,7 @@ int launch_gemm(GemmArgs& g, int variant, int split_k, cudaStream_t st) {
     if (variant == 2) {
         int blocks = (int)std::min<int64_t>(2 * 148, (g.K + 255) / 256);
         if (blocks < 1) blocks = 1;
-        zdot_gather_kernel<<<blocks, 256, 0, st>>>(g);
+        zdot_gather_kernel<double2><<<blocks, 256, 0, st>>>(g);
         CUDA_TRY(cudaGetLastError());
         count_launch(1);
         return QTN_OK;
@@ -123,12 +125,39 @@ int launch_gemm(GemmArgs& g, int variant, int split_k, cudaStream_t st) {
     return launch_gemm_t<64, 64, 32, 32, 16, 3>(g, split_k, st);
 }
 
+// ComplexF32 mode: one FP32-pipe tile kernel for every GEMM shape, the streaming dot for the rest.
+int launch_cgemm(GemmArgs& g, int variant, int split_k, cudaStream_t st) {
+    if (g.M <= 0 || g.N <= 0) return QTN_OK;
+    if (variant == 2) {
+        int blocks = (int)std::min<int64_t>(2 * 148, (g.K + 255) / 256);
+        zdot_gather_kernel<float2><<<std::max(blocks, 1), 256, 0, st>>>(g);
+        CUDA_TRY(cudaGetLastError());
+        count_launch(1);
+        return QTN_OK;
+    }
+    const int BM = 64, BN = 64, BK = 16;
+    int64_t tm = (g.M + BM - 1) / BM, tn = (g.N + BN - 1) / BN;
+    if (tm * tn > 2147483647LL) return fail(QTN_EINVAL, "GEMM grid too large");
+    g.tiles_m = (int)tm;
+    g.tiles_n = (int)tn;
+    g.group_n = 16;
+    int64_t kps = (g.K + split_k - 1) / split_k;
+    kps = (kps + BK - 1) / BK * BK;
+    g.k_per_split = kps;
+    dim3 grid((unsigned)(tm * tn), (unsigned)((g.K + kps - 1) / kps), 1);
+    cgemm_gather_kernel<<<grid, 256, 0, st>>>(g);
+    CUDA_TRY(cudaGetLastError());
+    count_launch(1);
+    return QTN_OK;
+}
+
 // ---------------------------------------------------------------------------
 // per-plan device state
 // ---------------------------------------------------------------------------
 struct DevPlan {
-    double2* inputs = nullptr;
-    double2* arena = nullptr;
+    char* inputs = nullptr;   // element size = 16 (ComplexF64) or 8 (ComplexF32 mode)
+    char* arena = nullptr;
+    size_t es = 16;
     i64* tables = nullptr;
     i64* sid = nullptr;
     i64* soff = nullptr;
@@ -144,7 +173,7 @@ struct DevPlan {
     bool invariants_done = false;
     int graph_launches = 0;
     std::vector<cudaEvent_t> capture_events;
-    double2* host_out = nullptr;  // result buffer of the host-buffer entry points
+    char* host_out = nullptr;  // result buffer of the host-buffer entry points
 };
 
 static TabArg tab_arg(const DevPlan* d, const OffTable& t) {
@@ -164,6 +193,7 @@ int plan_device_init(Plan* p) {
     rc = materialize_tables(p);
     if (rc) return rc;
     DevPlan* d = new DevPlan();
+    d->es = p->dtype == QTN_C64 ? 8 : 16;
     p->dev = d;
     auto guard_fail = [&](int code) { plan_device_free(p); return code; };
     cudaError_t e;
@@ -171,8 +201,8 @@ int plan_device_init(Plan* p) {
     if ((e = cudaMalloc((void**)&(ptr), std::max<size_t>((size_t)(bytes), 256))) != cudaSuccess) \
         return guard_fail(fail(e == cudaErrorMemoryAllocation ? QTN_ENOMEM : QTN_ECUDA,          \
                                "cudaMalloc(%zu bytes) failed: %s", (size_t)(bytes), cudaGetErrorString(e)));
-    ALLOC(d->inputs, (size_t)p->input_elems * 16);
-    ALLOC(d->arena, (size_t)p->arena_elems * 16);
+    ALLOC(d->inputs, (size_t)p->input_elems * d->es);
+    ALLOC(d->arena, (size_t)p->arena_elems * d->es);
     ALLOC(d->tables, p->tables.size() * 8);
     ALLOC(d->sid, 8);
     ALLOC(d->soff, (size_t)p->nt * 8);
@@ -195,7 +225,7 @@ int plan_device_init(Plan* p) {
         CUDA_TRY(cudaMemcpy(d->slice_dims, p->slice_dims.data(), p->slice_dims.size() * 8, cudaMemcpyHostToDevice));
     }
     CUDA_TRY(cudaMemset(d->soff, 0, (size_t)p->nt * 8));
-    d->h_stage_bytes = (size_t)p->input_elems * 16;
+    d->h_stage_bytes = (size_t)p->input_elems * d->es;
     CUDA_TRY(cudaMallocHost(&d->h_stage, std::max<size_t>(d->h_stage_bytes, 256)));
     return QTN_OK;
 }
@@ -223,7 +253,7 @@ int plan_upload(Plan* p, const void* const* host_data) {
         int64_t full = n.numel;
         for (auto& ps : n.slice_strides) full *= p->slice_dims[ps.first];
         if (!host_data[t] && full > 0) return fail(QTN_EINVAL, "tensor %d: null data pointer", t + 1);
-        memcpy((char*)d->h_stage + (size_t)n.offset * 16, host_data[t], (size_t)full * 16);
+        memcpy((char*)d->h_stage + (size_t)n.offset * d->es, host_data[t], (size_t)full * d->es);
     }
     CUDA_TRY(cudaMemcpyAsync(d->inputs, d->h_stage, d->h_stage_bytes, cudaMemcpyHostToDevice, g_stream));
     d->uploaded = true;
@@ -231,15 +261,15 @@ int plan_upload(Plan* p, const void* const* host_data) {
     return QTN_OK;
 }
 
-static const double2* node_ptr(const Plan* p, const DevPlan* d, int n, const i64** soff, void* dev_out) {
+static const void* node_ptr(const Plan* p, const DevPlan* d, int n, const i64** soff, void* dev_out) {
     const Node& nd = p->nodes[n];
     *soff = nullptr;
     if (nd.is_input) {
         if (!nd.slice_strides.empty()) *soff = d->soff + nd.input_index;
-        return d->inputs + nd.offset;
+        return d->inputs + (size_t)nd.offset * d->es;
     }
-    if (n == p->final_node) return (const double2*)dev_out;
-    return d->arena + nd.offset;
+    if (n == p->final_node) return dev_out;
+    return d->arena + (size_t)nd.offset * d->es;
 }
 
 static int run_step(Plan* p, DevPlan* d, const Step& s, void* dev_out, cudaStream_t st) {
@@ -249,7 +279,7 @@ static int run_step(Plan* p, DevPlan* d, const Step& s, void* dev_out, cudaStrea
         memset(&g, 0, sizeof(g));
         g.A = node_ptr(p, d, s.a, &sa, dev_out);
         g.B = node_ptr(p, d, s.b, &sb, dev_out);
-        g.C = const_cast<double2*>(node_ptr(p, d, s.out, &sc, dev_out));
+        g.C = const_cast<void*>(node_ptr(p, d, s.out, &sc, dev_out));
         g.a_soff = sa;
         g.b_soff = sb;
         g.a_row = tab_arg(d, s.a_row);
@@ -264,14 +294,14 @@ static int run_step(Plan* p, DevPlan* d, const Step& s, void* dev_out, cudaStrea
         if (s.final_step) g.mode = atomic ? 2 : 1;
         else {
             g.mode = atomic ? 2 : 0;
-            if (atomic) CUDA_TRY(cudaMemsetAsync(g.C, 0, (size_t)s.M * s.N * 16, st));
+            if (atomic) CUDA_TRY(cudaMemsetAsync(g.C, 0, (size_t)s.M * s.N * d->es, st));
         }
-        return launch_gemm(g, variant, split, st);
+        return p->dtype == QTN_C64 ? launch_cgemm(g, variant, split, st) : launch_gemm(g, variant, split, st);
     }
     UnaryArgs u;
     memset(&u, 0, sizeof(u));
     u.A = node_ptr(p, d, s.a, &sa, dev_out);
-    u.C = const_cast<double2*>(node_ptr(p, d, s.out, &sc, dev_out));
+    u.C = const_cast<void*>(node_ptr(p, d, s.out, &sc, dev_out));
     u.a_soff = sa;
     u.a_row = tab_arg(d, s.a_row);
     u.M = s.M;
@@ -281,10 +311,12 @@ static int run_step(Plan* p, DevPlan* d, const Step& s, void* dev_out, cudaStrea
     if (s.kind == STEP_PERMUTE) {
         u.c_row = tab_arg(d, s.c_row);
         u.mode = 1;
-        permute_gather_kernel<<<blocks, 256, 0, st>>>(u);
+        if (p->dtype == QTN_C64) permute_gather_kernel<float2><<<blocks, 256, 0, st>>>(u);
+        else permute_gather_kernel<double2><<<blocks, 256, 0, st>>>(u);
     } else {
         u.a_k = tab_arg(d, s.a_k);
-        trace_gather_kernel<<<blocks, 256, 0, st>>>(u);
+        if (p->dtype == QTN_C64) trace_gather_kernel<float2><<<blocks, 256, 0, st>>>(u);
+        else trace_gather_kernel<double2><<<blocks, 256, 0, st>>>(u);
     }
     CUDA_TRY(cudaGetLastError());
     count_launch(1);
@@ -454,7 +486,7 @@ int plan_execute(Plan* p, int64_t s0, int64_t s1, void* dev_out) {
 int plan_result_buffer(Plan* p, void** out) {
     DevPlan* d = (DevPlan*)p->dev;
     if (!d) return fail(QTN_EINVAL, "plan has no device state");
-    const size_t bytes = std::max<size_t>((size_t)p->out_numel * 16, 256);
+    const size_t bytes = std::max<size_t>((size_t)p->out_numel * d->es, 256);
     if (!d->host_out) CUDA_TRY(cudaMalloc((void**)&d->host_out, bytes));
     CUDA_TRY(cudaMemsetAsync(d->host_out, 0, bytes, g_stream));
     *out = d->host_out;
@@ -465,9 +497,9 @@ int plan_time_steps(Plan* p, int64_t sid, float* ms) {
     DevPlan* d = (DevPlan*)p->dev;
     if (!d || !d->uploaded) return fail(QTN_EINVAL, "qtn_plan_time_steps: call qtn_plan_upload first");
     cudaSetDevice(g_device);
-    double2* scratch = nullptr;
+    char* scratch = nullptr;
     CUDA_TRY(cudaMalloc((void**)&scratch, std::max<size_t>((size_t)p->out_numel * 16, 256)));
-    CUDA_TRY(cudaMemsetAsync(scratch, 0, (size_t)p->out_numel * 16, g_stream));
+    CUDA_TRY(cudaMemsetAsync(scratch, 0, (size_t)p->out_numel * d->es, g_stream));
     if (p->nslices > 1) {
         set_i64_kernel<<<1, 1, 0, g_stream>>>(d->sid, sid);
         slice_offsets_kernel<<<1, 256, 0, g_stream>>>(d->sid, (int)p->slice_dims.size(), d->slice_dims, p->nt, d->first,

@@ -35,9 +35,9 @@ __device__ __forceinline__ i64 tab_off(const TabArg& t, i64 i) {
 }
 
 struct GemmArgs {
-    const double2* A;
-    const double2* B;
-    double2* C;
+    const void* A;  // double2 (ComplexF64) or float2 (ComplexF32 mode) elements
+    const void* B;
+    void* C;
     const i64* a_soff;  // per-slice base offset (elements) or nullptr
     const i64* b_soff;
     TabArg a_row, a_k, b_k, b_col, c_row, c_col;
@@ -64,6 +64,23 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                  : "d"(a), "d"(b));
 }
 
+// Element traits of the two precisions (ComplexF64 = double2, ComplexF32 mode = float2).
+template <typename T> struct Elem;
+template <> struct Elem<double2> { typedef double real; static __device__ __forceinline__ double2 make(double a, double b) { return make_double2(a, b); } };
+template <> struct Elem<float2> { typedef float real; static __device__ __forceinline__ float2 make(double a, double b) { return make_float2((float)a, (float)b); } };
+
+__device__ __forceinline__ void store_c(float2* p, float re, float im, int mode) {
+    if (mode == 0) {
+        *p = make_float2(re, im);
+    } else if (mode == 1) {
+        float2 o = *p;
+        *p = make_float2(o.x + re, o.y + im);
+    } else {
+        atomicAdd(&p->x, re);
+        atomicAdd(&p->y, im);
+    }
+}
+
 __device__ __forceinline__ void store_c(double2* p, double re, double im, int mode) {
     if (mode == 0) {
         *p = make_double2(re, im);
@@ -77,8 +94,8 @@ __device__ __forceinline__ void store_c(double2* p, double re, double im, int mo
 }
 
 struct UnaryArgs {
-    const double2* A;
-    double2* C;
+    const void* A;
+    void* C;
     const i64* a_soff;
     TabArg a_row, a_k, c_row;
     i64 M, K;
@@ -117,8 +134,9 @@ zgemm_gather_kernel(const __grid_constant__ GemmArgs g) {
     const i64 kb = (i64)blockIdx.y * g.k_per_split;
     const i64 ke = min(g.K, kb + g.k_per_split);
 
-    const double2* A = g.A + (g.a_soff ? *g.a_soff : 0);
-    const double2* B = g.B + (g.b_soff ? *g.b_soff : 0);
+    const double2* A = static_cast<const double2*>(g.A) + (g.a_soff ? *g.a_soff : 0);
+    const double2* B = static_cast<const double2*>(g.B) + (g.b_soff ? *g.b_soff : 0);
+    double2* const Cbase = static_cast<double2*>(g.C);
 
     for (int i = tid; i < BM; i += NT) sRow[i] = (m0 + i < g.M) ? tab_off(g.a_row, m0 + i) : -1;
     for (int i = tid; i < BN; i += NT) sCol[i] = (n0 + i < g.N) ? tab_off(g.b_col, n0 + i) : -1;
@@ -229,16 +247,120 @@ zgemm_gather_kernel(const __grid_constant__ GemmArgs g) {
             const i64 co = g.c_dense ? c * g.M : tab_off(g.c_col, c);
 #pragma unroll
             for (int i = 0; i < MI; ++i)
-                if (crow[i] >= 0) store_c(g.C + crow[i] + co, cr[i][j][q], ci[i][j][q], g.mode);
+                if (crow[i] >= 0) store_c(Cbase + crow[i] + co, cr[i][j][q], ci[i][j][q], g.mode);
         }
+}
+
+// K3: ComplexF32 mode on the FP32 pipes (optional precision; tensor cores would need TF32, whose
+// 10-bit mantissa misses the 1e-4 amplitude bar).  Same gather/scatter addressing as the FP64
+// kernel; 64x64 CTA tile, 256 threads, 4x4 complex outputs per thread, BK = 16, 2-stage cp.async (8 B).
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc, bool valid) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    int sz = valid ? 8 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(s), "l"(gsrc), "r"(sz));
+}
+
+__global__ void __launch_bounds__(256) cgemm_gather_kernel(const __grid_constant__ GemmArgs g) {
+    constexpr int BM = 64, BN = 64, BK = 16, NT = 256, PA = BM + 2, PB = BN + 2, STAGES = 2;
+    __shared__ __align__(16) float2 sA[STAGES][BK][PA];
+    __shared__ __align__(16) float2 sB[STAGES][BK][PB];
+    __shared__ i64 sRow[BM], sCol[BN];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const i64 tile = blockIdx.x;
+    const i64 per_group = (i64)g.group_n * g.tiles_m;
+    const i64 grp = tile / per_group, in_grp = tile - grp * per_group;
+    const i64 gsz = min((i64)g.group_n, (i64)g.tiles_n - grp * g.group_n);
+    const i64 m0 = (in_grp / gsz) * BM, n0 = (grp * g.group_n + in_grp % gsz) * BN;
+    const i64 kb = (i64)blockIdx.y * g.k_per_split;
+    const i64 ke = min(g.K, kb + g.k_per_split);
+    const float2* A = static_cast<const float2*>(g.A) + (g.a_soff ? *g.a_soff : 0);
+    const float2* B = static_cast<const float2*>(g.B) + (g.b_soff ? *g.b_soff : 0);
+    float2* const Cbase = static_cast<float2*>(g.C);
+    for (int i = tid; i < BM; i += NT) sRow[i] = (m0 + i < g.M) ? tab_off(g.a_row, m0 + i) : -1;
+    for (int i = tid; i < BN; i += NT) sCol[i] = (n0 + i < g.N) ? tab_off(g.b_col, n0 + i) : -1;
+    __syncthreads();
+    const int lk = tid >> 4, lr = tid & 15;
+    auto load_stage = [&](int stage, i64 k0) {
+        const i64 k = k0 + lk;
+        const bool kv = k < ke;
+        const i64 ka = kv ? tab_off(g.a_k, k) : 0, kbo = kv ? tab_off(g.b_k, k) : 0;
+#pragma unroll
+        for (int i = 0; i < BM / 16; ++i) {
+            const int m = lr + 16 * i;
+            const i64 ro = sRow[m];
+            const bool v = kv && ro >= 0;
+            cp_async8(&sA[stage][lk][m], v ? (A + ro + ka) : A, v);
+        }
+#pragma unroll
+        for (int i = 0; i < BN / 16; ++i) {
+            const int n = lr + 16 * i;
+            const i64 co = sCol[n];
+            const bool v = kv && co >= 0;
+            cp_async8(&sB[stage][lk][n], v ? (B + co + kbo) : B, v);
+        }
+    };
+    float cr[4][4], ci[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) cr[i][j] = ci[i][j] = 0.f;
+    const int nk = (int)((ke - kb + BK - 1) / BK);
+    if (nk > 0) load_stage(0, kb);
+    cp_async_commit();
+    for (int it = 0; it < nk; ++it) {
+        if (it + 1 < nk) load_stage((it + 1) & 1, kb + (i64)(it + 1) * BK);
+        cp_async_commit();
+        cp_async_wait<1>();
+        __syncthreads();
+        const int st = it & 1;
+#pragma unroll
+        for (int k = 0; k < BK; ++k) {
+            // rows tx + 16 i (coalesced 128-B row runs in the epilogue), columns ty * 4 + j (broadcast reads)
+            float2 a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = sA[st][k][tx + 16 * i];
+            const float4 b01 = *reinterpret_cast<const float4*>(&sB[st][k][ty * 4]);
+            const float4 b23 = *reinterpret_cast<const float4*>(&sB[st][k][ty * 4 + 2]);
+            b[0] = make_float2(b01.x, b01.y); b[1] = make_float2(b01.z, b01.w); b[2] = make_float2(b23.x, b23.y); b[3] = make_float2(b23.z, b23.w);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float ax = a[i].x, ay = g.conj_a ? -a[i].y : a[i].y;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float bx = b[j].x, by = g.conj_b ? -b[j].y : b[j].y;
+                    cr[i][j] = fmaf(ax, bx, cr[i][j]);
+                    cr[i][j] = fmaf(-ay, by, cr[i][j]);
+                    ci[i][j] = fmaf(ax, by, ci[i][j]);
+                    ci[i][j] = fmaf(ay, bx, ci[i][j]);
+                }
+            }
+        }
+        __syncthreads();
+    }
+    cp_async_wait<0>();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const i64 c = n0 + ty * 4 + j;
+        if (c >= g.N) continue;
+        const i64 co = g.c_dense ? c * g.M : tab_off(g.c_col, c);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const i64 r = m0 + tx + 16 * i;
+            if (r >= g.M) continue;
+            const i64 ro = g.c_dense ? r : tab_off(g.c_row, r);
+            store_c(Cbase + ro + co, cr[i][j], ci[i][j], g.mode);
+        }
+    }
 }
 
 // C[m, n] += sum_k A[m, k] B[k, n] for M*N <= 16 and huge K (the closing dot products):
 // every thread strides over k, block-reduces, one atomic per (m, n) per CTA.  C must
 // be pre-zeroed (or hold the running sum when accumulating).
+template <typename T>
 __global__ void __launch_bounds__(256) zdot_gather_kernel(const __grid_constant__ GemmArgs g) {
-    const double2* A = g.A + (g.a_soff ? *g.a_soff : 0);
-    const double2* B = g.B + (g.b_soff ? *g.b_soff : 0);
+    typedef typename Elem<T>::real real;
+    const T* A = static_cast<const T*>(g.A) + (g.a_soff ? *g.a_soff : 0);
+    const T* B = static_cast<const T*>(g.B) + (g.b_soff ? *g.b_soff : 0);
     const int M = (int)g.M, N = (int)g.N;
     __shared__ double red[8][2];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -249,17 +371,17 @@ __global__ void __launch_bounds__(256) zdot_gather_kernel(const __grid_constant_
         const i64 stride = (i64)gridDim.x * blockDim.x;
         i64 k = (i64)blockIdx.x * blockDim.x + threadIdx.x;
         for (; k + stride < g.K; k += 2 * stride) {
-            const double2 a0 = __ldg(A + ro + tab_off(g.a_k, k)), b0 = __ldg(B + co + tab_off(g.b_k, k));
-            const double2 a1 = __ldg(A + ro + tab_off(g.a_k, k + stride)), b1 = __ldg(B + co + tab_off(g.b_k, k + stride));
-            r0 += a0.x * b0.x - a0.y * b0.y;
-            i0 += a0.x * b0.y + a0.y * b0.x;
-            r1 += a1.x * b1.x - a1.y * b1.y;
-            i1 += a1.x * b1.y + a1.y * b1.x;
+            const T a0 = __ldg(A + ro + tab_off(g.a_k, k)), b0 = __ldg(B + co + tab_off(g.b_k, k));
+            const T a1 = __ldg(A + ro + tab_off(g.a_k, k + stride)), b1 = __ldg(B + co + tab_off(g.b_k, k + stride));
+            r0 += (double)a0.x * b0.x - (double)a0.y * b0.y;   // always accumulated in double
+            i0 += (double)a0.x * b0.y + (double)a0.y * b0.x;
+            r1 += (double)a1.x * b1.x - (double)a1.y * b1.y;
+            i1 += (double)a1.x * b1.y + (double)a1.y * b1.x;
         }
         if (k < g.K) {
-            const double2 a0 = __ldg(A + ro + tab_off(g.a_k, k)), b0 = __ldg(B + co + tab_off(g.b_k, k));
-            r0 += a0.x * b0.x - a0.y * b0.y;
-            i0 += a0.x * b0.y + a0.y * b0.x;
+            const T a0 = __ldg(A + ro + tab_off(g.a_k, k)), b0 = __ldg(B + co + tab_off(g.b_k, k));
+            r0 += (double)a0.x * b0.x - (double)a0.y * b0.y;
+            i0 += (double)a0.x * b0.y + (double)a0.y * b0.x;
         }
         double r = r0 + r1, i = i0 + i1;
         for (int o = 16; o > 0; o >>= 1) {
@@ -273,33 +395,35 @@ __global__ void __launch_bounds__(256) zdot_gather_kernel(const __grid_constant_
             double s = 0;
             for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[w][threadIdx.x];
             const i64 off = g.c_dense ? (m + (i64)n * g.M) : (tab_off(g.c_row, m) + tab_off(g.c_col, n));
-            atomicAdd(reinterpret_cast<double*>(g.C + off) + threadIdx.x, s);
+            atomicAdd(reinterpret_cast<real*>(static_cast<T*>(g.C) + off) + threadIdx.x, (real)s);
         }
     }
 }
 
 
 // out[c_row(i)] (+)= in[a_row(i)]; i enumerates the OUTPUT layout (coalesced writes).
+template <typename T>
 __global__ void __launch_bounds__(256) permute_gather_kernel(const __grid_constant__ UnaryArgs g) {
-    const double2* A = g.A + (g.a_soff ? *g.a_soff : 0);
+    const T* A = static_cast<const T*>(g.A) + (g.a_soff ? *g.a_soff : 0);
     for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < g.M; i += (i64)gridDim.x * blockDim.x) {
-        const double2 v = __ldg(A + tab_off(g.a_row, i));
-        store_c(g.C + tab_off(g.c_row, i), v.x, v.y, g.mode);
+        const T v = __ldg(A + tab_off(g.a_row, i));
+        store_c(static_cast<T*>(g.C) + tab_off(g.c_row, i), v.x, v.y, g.mode);
     }
 }
 
 // out[i] = sum_t in[a_row(i) + a_k(t)]  (partial trace, src/network2graph.jl:436-445 networks)
+template <typename T>
 __global__ void __launch_bounds__(256) trace_gather_kernel(const __grid_constant__ UnaryArgs g) {
-    const double2* A = g.A + (g.a_soff ? *g.a_soff : 0);
+    const T* A = static_cast<const T*>(g.A) + (g.a_soff ? *g.a_soff : 0);
     for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < g.M; i += (i64)gridDim.x * blockDim.x) {
         const i64 ro = tab_off(g.a_row, i);
         double re = 0, im = 0;
         for (i64 t = 0; t < g.K; ++t) {
-            const double2 v = __ldg(A + ro + tab_off(g.a_k, t));
+            const T v = __ldg(A + ro + tab_off(g.a_k, t));
             re += v.x;
             im += v.y;
         }
-        g.C[i] = make_double2(re, im);
+        static_cast<T*>(g.C)[i] = Elem<T>::make(re, im);
     }
 }
 

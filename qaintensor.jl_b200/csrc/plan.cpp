@@ -278,7 +278,7 @@ int build_plan(int nt, const int32_t* ranks, const int64_t* const* dims, const i
     Parsed P;
     int rc = parse(nt, ranks, dims, labels, order, norder, P);
     if (rc) return rc;
-    if (dtype != QTN_C128) return fail(QTN_EINVAL, "only QTN_C128 (ComplexF64) is implemented in this build");
+    if (dtype != QTN_C128 && dtype != QTN_C64) return fail(QTN_EINVAL, "dtype must be QTN_C128 or QTN_C64");
     std::unique_ptr<Plan> plan(new Plan());
     Plan& pl = *plan;
     pl.dtype = dtype;

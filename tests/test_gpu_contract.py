@@ -164,3 +164,27 @@ def test_open_legs_many_amplitudes(gpu):  # open output legs (SURVEY section 8f 
     # non-decomposed tensor_circuit! contracts the row bits: it applies U^T (quirk Q2)
     ref = og.apply(psi, [og.CircuitGate(g.iwire, g.matrix.T) for g in gates])
     assert rel_err(got.reshape(-1, order="F"), ref) < TOL
+
+
+def test_complex_f32_mode(gpu):  # EXTENSION vii: ComplexF32 mode, amplitudes within 1e-4 relative
+    q = gpu
+    net, _ = q.circuits.cfg1_qft_network(12)
+    got = q.contract(net, precision="c64")
+    want = oc.contract(to_oracle(net))
+    assert got.dtype == np.complex64 and rel_err(got, want) < 1e-4
+    for args in ((10, 8, 7), (24, 20, None)):
+        net, _, _ = q.circuits.cfg2_network(*args)
+        q.optimize_contraction_order(net)
+        want = complex(oc.contract(to_oracle(net)))
+        got = complex(q.contract(net, precision="c64"))
+        assert abs(got - want) < 1e-4 * abs(want)
+    il = q.contract_rep(net)
+    arrays = [t.data for t in net.tensors]
+    S = q.choose_slices([a.shape for a in arrays], il, None, 14, 8)
+    sp = q.ContractionPlan([a.shape for a in arrays], il, None, S, precision="c64")
+    assert abs(complex(sp.execute(arrays)) - want) < 1e-4 * abs(want)
+    rng = np.random.default_rng(3)
+    a = rng.standard_normal((3, 5, 4)) + 1j * rng.standard_normal((3, 5, 4))
+    b = rng.standard_normal((4, 7, 5)) + 1j * rng.standard_normal((4, 7, 5))
+    got = q.ncon([a, b], [[-1, 1, 2], [2, -2, 1]], precision="c64")
+    assert rel_err(got, np.einsum("ijk,klj->il", a, b)) < 1e-5

@@ -85,12 +85,12 @@ int device_ready() {
 // ---------------------------------------------------------------------------
 int launch_cgemm(GemmArgs& g, int variant, int split_k, cudaStream_t st);
 
-template <int BM, int BN, int WM, int WN, int BK, int STAGES>
+template <int BM, int BN, int WM, int WN, int BK, int STAGES, int MINB = 1>
 static int launch_gemm_t(GemmArgs& g, int split_k, cudaStream_t st) {
     constexpr int NT = (BM / WM) * (BN / WN) * 32;
     constexpr size_t smem = (size_t)STAGES * BK * (BM + 2 + BN + 2) * 16 + (BM + BN) * 8;
     static bool attr_done = false;
-    auto kern = zgemm_gather_kernel<BM, BN, WM, WN, BK, STAGES>;
+    auto kern = zgemm_gather_kernel<BM, BN, WM, WN, BK, STAGES, MINB>;
     if (!attr_done) {
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_done = true;
@@ -122,7 +122,14 @@ int launch_gemm(GemmArgs& g, int variant, int split_k, cudaStream_t st) {
         return QTN_OK;
     }
     if (variant == 1) return launch_gemm_t<128, 8, 32, 8, 16, 3>(g, split_k, st);
-    return launch_gemm_t<64, 64, 32, 32, 16, 3>(g, split_k, st);
+    // Measured on the dominant cfg-3 step (M=65536, N=2048, K=4096), TFLOP/s of the 37.1 DMMA ceiling:
+    //   64x64 BK=16 3 stages 31.3 | 128x64 / 64x128 (8 warps, 1 CTA/SM) 25.2 | 64x32 (3 CTAs/SM) 32.6
+    //   64x64 BK=8 3/4/6 stages 35.2 / 35.2 / 35.0 | 64x64 BK=4 8 stages 32.9
+    // -> short K chunks with two independent 4-warp CTAs per SM win; BK=8, 3 stages is the default.
+    static int tune = -1;
+    if (tune < 0) { const char* e = getenv("QTN_GEMM_TILE"); tune = e ? atoi(e) : 0; }
+    if (tune == 16) return launch_gemm_t<64, 64, 32, 32, 16, 3, 2>(g, split_k, st);  // previous default, kept for A/B runs
+    return launch_gemm_t<64, 64, 32, 32, 8, 3, 2>(g, split_k, st);
 }
 
 // ComplexF32 mode: one FP32-pipe tile kernel for every GEMM shape, the streaming dot for the rest.

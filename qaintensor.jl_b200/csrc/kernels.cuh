@@ -104,8 +104,8 @@ struct UnaryArgs {
 
 #ifdef QTN_KERNELS_IMPL
 // CTA tile BM x BN complex, warp tile WM x WN, K chunk BK, STAGES-deep cp.async ring.
-template <int BM, int BN, int WM, int WN, int BK, int STAGES>
-__global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32)
+template <int BM, int BN, int WM, int WN, int BK, int STAGES, int MINB = 1>
+__global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, MINB)
 zgemm_gather_kernel(const __grid_constant__ GemmArgs g) {
     constexpr int WARPS_M = BM / WM;
     constexpr int NT = (BM / WM) * (BN / WN) * 32;
@@ -181,7 +181,7 @@ zgemm_gather_kernel(const __grid_constant__ GemmArgs g) {
         cp_async_commit();
     }
     for (int it = 0; it < nk; ++it) {
-        cp_async_wait<STAGES - 2>();
+        cp_async_wait<(STAGES >= 2 ? STAGES - 2 : 0)>();
         __syncthreads();
         {
             const int nx = it + STAGES - 1;

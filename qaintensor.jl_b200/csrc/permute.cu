@@ -111,13 +111,18 @@ int permutedims_device(const void* in, int rank, const int64_t* dims, const int3
         count_launch(1);
         return cudaGetLastError() == cudaSuccess ? QTN_OK : fail(QTN_ECUDA, "copy kernel launch failed");
     }
-    // split big modes so tiles can take a chunk of them: ext -> (c, ext / c), c = largest divisor <= 32
+    // split big modes into factors <= 32 so tiles can take chunks of them (4096 -> 32 x 32 x 4)
     std::vector<Mode> modes;
     for (auto& m : om) {
-        int64_t c = 1;
-        if (m.ext > 32) for (int64_t d = 32; d >= 2; --d) if (m.ext % d == 0) { c = d; break; }
-        if (c > 1) { modes.push_back({c, m.sin, m.sout}); modes.push_back({m.ext / c, m.sin * c, m.sout * c}); }
-        else modes.push_back(m);
+        int64_t ext = m.ext, sin = m.sin, sout = m.sout;
+        while (ext > 32) {
+            int64_t c = 1;
+            for (int64_t d = 32; d >= 2; --d) if (ext % d == 0) { c = d; break; }
+            if (c == 1) break;  // large prime factor: keep the remainder whole
+            modes.push_back({c, sin, sout});
+            ext /= c; sin *= c; sout *= c;
+        }
+        modes.push_back({ext, sin, sout});
     }
     int nm = (int)modes.size();
     std::vector<int> by_in(nm), by_out(nm);

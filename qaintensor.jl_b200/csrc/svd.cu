@@ -19,6 +19,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstring>
 #include <vector>
 
@@ -51,6 +52,8 @@ struct SvdProblem {
     double2* V;   // n x n
     int m, n;
     int nblocks;  // ceil(n / JB), rounded up to even
+    int* last_mod;  // [nblocks]  launch stamp of the last rotation that touched a column block
+    int* last_ok;   // [nblocks * nblocks] launch stamp at which a block pair was last found converged
 };
 
 __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
@@ -71,7 +74,7 @@ namespace cg = cooperative_groups;
 // identical eigensolve (same W, no broadcast) and updates its own row chunks.
 __global__ void __launch_bounds__(JTHREADS, 2)
 jacobi_round_kernel(const SvdProblem* __restrict__ probs, int round, double tol, int* __restrict__ rotated,
-                    const double* __restrict__ fro2, int inner_sweeps) {
+                    const double* __restrict__ fro2, int inner_sweeps, int* __restrict__ stat, int stamp) {
     cg::cluster_group cluster = cg::this_cluster();
     const int CL = (int)cluster.num_blocks(), crank = (int)cluster.block_rank();
     const int pair = blockIdx.x / CL;
@@ -89,6 +92,12 @@ jacobi_round_kernel(const SvdProblem* __restrict__ probs, int round, double tol,
     else { bi = (round + pair) % (nb - 1); bj = (round - pair + (nb - 1)) % (nb - 1); }
     if (bi > bj) { int t = bi; bi = bj; bj = t; }
     if (bi * JB >= pr.n) return;  // padding block only
+    // a pair verified converged stays converged until one of its two blocks is rotated again:
+    // skipping it saves the whole Gram pass in the tail sweeps (cluster-uniform decision)
+    if (max(pr.last_mod[bi], pr.last_mod[bj]) < pr.last_ok[bi * nb + bj]) {
+        if (stat && threadIdx.x == 0 && crank == 0) atomicAdd(&stat[0], 1);
+        return;
+    }
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double2* Ps = reinterpret_cast<double2*>(smem_raw);   // [JROWS][JPITCH] panel chunk
@@ -286,6 +295,11 @@ jacobi_round_kernel(const SvdProblem* __restrict__ probs, int round, double tol,
         __syncthreads();
         if (!any_now) break;
     }
+    if (stat && tid == 0 && crank == 0) atomicAdd(&stat[s_any ? 1 : 0], 1);
+    if (tid == 0 && crank == 0) {
+        if (s_any) { pr.last_mod[bi] = stamp; pr.last_mod[bj] = stamp; }
+        else pr.last_ok[bi * nb + bj] = stamp;
+    }
     if (!s_any) return;  // panel already orthogonal and ordered: nothing to update
     if (tid == 0 && s_rot && crank == 0) rotated[blockIdx.y] = 1;  // pure re-ordering swaps do not keep the sweeps going
 
@@ -328,6 +342,11 @@ jacobi_round_kernel(const SvdProblem* __restrict__ probs, int round, double tol,
             }
         }
     }
+}
+
+__global__ void set_int_kernel(int* p, int n, int v) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
 }
 
 // fro2[b] = ||A_b||_F^2
@@ -495,7 +514,7 @@ int svd_batched_device(int batch, const SvdJob* jobs, double er, int64_t maxdim,
     cudaStream_t st = stream();
     // workspace layout (device): per problem: [At (if transposed) m*n] [V n*n] [sig n] [rank n]
     size_t dev_bytes = 0;
-    std::vector<size_t> offAt(batch), offV(batch), offSig(batch), offRank(batch);
+    std::vector<size_t> offAt(batch), offV(batch), offSig(batch), offRank(batch), offStamp(batch);
     std::vector<int> tr(batch);
     int maxn = 0, maxm = 0;
     for (int b = 0; b < batch; ++b) {
@@ -509,6 +528,11 @@ int svd_batched_device(int batch, const SvdJob* jobs, double er, int64_t maxdim,
         offV[b] = al((size_t)n * n * 16);
         offSig[b] = al((size_t)n * 8);
         offRank[b] = al((size_t)n * 4);
+        {
+            int nbk = (int)((n + JB - 1) / JB);
+            if (nbk & 1) ++nbk;
+            offStamp[b] = al((size_t)(nbk + (size_t)nbk * nbk) * 4);
+        }
         maxn = std::max<int>(maxn, (int)n);
         maxm = std::max<int>(maxm, (int)m);
     }
@@ -541,6 +565,11 @@ int svd_batched_device(int batch, const SvdJob* jobs, double er, int64_t maxdim,
         int nbk = (n + JB - 1) / JB;
         if (nbk & 1) ++nbk;
         hp[b].nblocks = nbk;
+        hp[b].last_mod = (int*)(base + offStamp[b]);
+        hp[b].last_ok = hp[b].last_mod + nbk;
+        // last_mod = 1, last_ok = 0: every pair starts "modified after its last check"
+        CUDA_TRY(cudaMemsetAsync(hp[b].last_ok, 0, (size_t)nbk * nbk * 4, st));
+        set_int_kernel<<<(nbk + 255) / 256, 256, 0, st>>>(hp[b].last_mod, nbk, 1);
         hf[b].U = jobs[b].U; hf[b].S = jobs[b].S; hf[b].Vh = jobs[b].Vh;
         hf[b].k = (int64_t*)dptr(hk + b);
         hf[b].disc = (double*)dptr(hdisc + b);
@@ -572,7 +601,8 @@ int svd_batched_device(int batch, const SvdJob* jobs, double er, int64_t maxdim,
     if (!attr) { CUDA_TRY(cudaFuncSetAttribute(jacobi_round_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
     int max_nb = (maxn + JB - 1) / JB;
     if (max_nb & 1) ++max_nb;
-    const double tol = 1e-15 * std::sqrt((double)std::max(maxm, 1)) * 0.5 + 2.3e-16;
+    double tol = 1e-15 * std::sqrt((double)std::max(maxm, 1)) * 0.5 + 2.3e-16;
+    if (const char* e = getenv("QTN_JACOBI_TOL")) tol *= atof(e);
     // cluster size: split the panel rows over up to 8 CTAs when the (pairs x batch) grid alone cannot
     // fill the 148 SMs (single large matrices, e.g. the sequential MPO compression sweeps)
     int cl = 1;
@@ -581,9 +611,11 @@ int svd_batched_device(int batch, const SvdJob* jobs, double er, int64_t maxdim,
         const int chunks = (maxm + JROWS - 1) / JROWS;
         while (cl < 8 && ctas * cl * 2 <= 2 * 148 && cl * 2 <= chunks) cl *= 2;
     }
+    int* dstat = nullptr;  // QTN_JACOBI_STATS=1: per-sweep counts of (idle, active) block pairs, printed to stderr
+    if (getenv("QTN_JACOBI_STATS")) { cudaMalloc((void**)&dstat, 2 * 64 * sizeof(int)); cudaMemsetAsync(dstat, 0, 2 * 64 * sizeof(int), st); }
     int inner = kInnerSweeps;
     if (const char* e = getenv("QTN_JACOBI_INNER")) inner = std::max(1, atoi(e));
-    int sweeps = 0;
+    int sweeps = 0, stamp = 1;
     const int kMaxSweeps = 60;
     if (max_nb >= 2) {
         for (; sweeps < kMaxSweeps; ++sweeps) {
@@ -602,7 +634,7 @@ int svd_batched_device(int batch, const SvdJob* jobs, double er, int64_t maxdim,
                 at[0].val.clusterDim.z = 1;
                 cfg.attrs = at;
                 cfg.numAttrs = 1;
-                CUDA_TRY(cudaLaunchKernelEx(&cfg, jacobi_round_kernel, dp, round, tol, drot, (const double*)dfro, inner));
+                CUDA_TRY(cudaLaunchKernelEx(&cfg, jacobi_round_kernel, dp, round, tol, drot, (const double*)dfro, inner, dstat ? dstat + 2 * sweeps : (int*)nullptr, ++stamp));
             }
             count_launch(max_nb - 1);
             CUDA_TRY(cudaMemcpyAsync(hrot, drot, (size_t)batch * 4, cudaMemcpyDeviceToHost, st));
@@ -614,6 +646,14 @@ int svd_batched_device(int batch, const SvdJob* jobs, double er, int64_t maxdim,
             }
             if (!any) { ++sweeps; break; }
         }
+    }
+    if (dstat) {
+        int hs[128];
+        cudaMemcpy(hs, dstat, sizeof(hs), cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[jacobi] batch=%d maxn=%d cl=%d sweeps=%d (idle,active) pairs per sweep:", batch, maxn, cl, sweeps);
+        for (int i = 0; i < sweeps && i < 64; ++i) fprintf(stderr, " (%d,%d)", hs[2 * i], hs[2 * i + 1]);
+        fprintf(stderr, "\n");
+        cudaFree(dstat);
     }
     column_norms_kernel<<<dim3(std::min(148 * 2, (maxn + 7) / 8), batch), 256, 0, st>>>(dp, dsig);
     sort_truncate_kernel<<<batch, 256, 0, st>>>(dp, dsig, drank, df, er, (long long)maxdim);

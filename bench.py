@@ -4,8 +4,8 @@
     python bench.py --gpus N --steps K --warmup W [--workload cfg3|cfg2] [--impl reference]
 
 Default workload = BASELINE config 3 (36-qubit 6x6 random circuit, 16 cycles, single
-amplitude, reference treewidth order, sliced).  One amplitude is 2^16 slices of ~5.6e12
-flop each (3.7e17 flop): a *step* is one batch of `--slices-per-step` slices per GPU of
+amplitude, reference treewidth order, sliced).  One amplitude is 2^11 slices of ~1.5e14
+flop each (3.17e17 flop, 1.05x the un-sliced count): a *step* is `--slices-per-step` slices per GPU of
 that amplitude (partial sum accumulated on the device, one 16-byte NCCL allreduce per
 step when N > 1), and `value` = (slices processed / slices per amplitude) / time, i.e.
 amplitudes/s at the measured slice rate.  `--workload cfg2` times complete 24-qubit
@@ -35,8 +35,9 @@ def parse():
     ap.add_argument("--workload", default="cfg3", choices=["cfg3", "cfg2", "cfg4", "cfg5"])
     ap.add_argument("--chi", type=int, default=512, help="cfg4: max bond dimension")
     ap.add_argument("--sites", type=int, default=50, help="cfg4: number of MPS sites")
-    ap.add_argument("--slices-per-step", type=int, default=2)
-    ap.add_argument("--max-log2", type=int, default=28, help="slice until the largest tensor has <= 2^k elements")
+    ap.add_argument("--slices-per-step", type=int, default=1)
+    ap.add_argument("--max-log2", type=int, default=31,
+                    help="slice until the largest tensor has <= 2^k elements (31: 2048 slices, 1.05x flop overhead, 109 GB arena)")
     ap.add_argument("--cpu-max-log2", type=int, default=26, help="slicing level of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--precision", default="c128", choices=["c128", "c64"], help="c64 = optional ComplexF32 mode (cfg2/cfg3)")

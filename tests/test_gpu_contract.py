@@ -188,3 +188,32 @@ def test_complex_f32_mode(gpu):  # EXTENSION vii: ComplexF32 mode, amplitudes wi
     b = rng.standard_normal((4, 7, 5)) + 1j * rng.standard_normal((4, 7, 5))
     got = q.ncon([a, b], [[-1, 1, 2], [2, -2, 1]], precision="c64")
     assert rel_err(got, np.einsum("ijk,klj->il", a, b)) < 1e-5
+
+
+def test_cfg3_full_size_parity_chain(gpu):  # BASELINE config 3 at full size (see tools/validate_cfg3.py)
+    """oracle(level-28 slice) = sum of its 64 oracle level-24 sub-slices; GPU level-28 slice matches it;
+    GPU level-31 slice (the default bench's tile shapes, 109 GB arena) = sum of its 32 GPU level-28 sub-slices."""
+    q = gpu
+    net, _, _ = q.circuits.cfg3_network()
+    q.optimize_contraction_order(net)
+    il = q.contract_rep(net)
+    arrays = [t.data for t in net.tensors]
+    shapes = [a.shape for a in arrays]
+    S = {lvl: q.choose_slices(shapes, il, None, lvl, 1) for lvl in (24, 28, 31)}
+    assert S[28][:len(S[31])] == S[31] and S[24][:len(S[28])] == S[28]
+    nodes, steps = oplan.contraction_tree(il)
+    dims = oplan.label_dims(arrays, il)
+    n31, n28, n24 = (2 ** len(S[k]) for k in (31, 28, 24))
+    sid28 = 4242
+    want = sum(complex(oplan.execute_tree(arrays, il, nodes, steps, oplan.slice_assignment(S[24], dims, sid28 + n28 * t)))
+               for t in range(n24 // n28))
+    p28 = q.ContractionPlan(shapes, il, None, S[28])
+    got = complex(p28.execute(arrays, sid28, sid28 + 1))
+    assert abs(got - want) < TOL * abs(want)
+    sid31 = 99
+    sub = sum(complex(p28.execute(None, sid31 + n31 * t, sid31 + n31 * t + 1)) for t in range(n28 // n31))
+    p28.close()
+    p31 = q.ContractionPlan(shapes, il, None, S[31])
+    got31 = complex(p31.execute(arrays, sid31, sid31 + 1))
+    p31.close()
+    assert abs(got31 - sub) < TOL * abs(sub)

@@ -29,4 +29,5 @@ for r in sorted(rows, key=lambda r: -r["ms"])[:25]:
     print("M=2^%.1f N=2^%.1f K=2^%.1f inv=%d var=%d split=%d  %.3f ms  %.2f TF/s  %.0f GB/s" % (
         __import__("math").log2(r["M"]), __import__("math").log2(r["N"]), __import__("math").log2(r["K"]), r["invariant"],
         r["variant"], r["split_k"], r["ms"], r["tflops"], r["gbs"]))
+print("DOMINANT_STEP_INDEX", max(range(len(rows)), key=lambda i: rows[i]["ms"]))
 json.dump(rows, open(os.path.join("gpurun_out", "steps_%s.json" % wl), "w"))

@@ -47,6 +47,7 @@ struct GemmArgs {
     int c_dense;
     int mode;  // 0 store, 1 add (single writer), 2 atomic add
     int conj_a, conj_b;  // conjugate the operand on the way into the tensor pipe
+    int use_3m;          // contraction plans may use the 3-multiplication complex product (see zgemm_gather_kernel)
 };
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool valid) {
@@ -104,7 +105,11 @@ struct UnaryArgs {
 
 #ifdef QTN_KERNELS_IMPL
 // CTA tile BM x BN complex, warp tile WM x WN, K chunk BK, STAGES-deep cp.async ring.
-template <int BM, int BN, int WM, int WN, int BK, int STAGES, int MINB = 1>
+// K3M = true: complex products by the 3-multiplication (Gauss / "3M") scheme -- P1 = Ar Br,
+// P2 = Ai Bi, P3 = (Ar + Ai)(Br + Bi); C = (P1 - P2) + i (P3 - P1 - P2) -- i.e. 3 real DMMAs per
+// complex block instead of 4.  Normwise error stays O(eps) (the amplitude bar is 1e-10); the SVD
+// path, which needs componentwise accuracy of tiny columns, never uses it.
+template <int BM, int BN, int WM, int WN, int BK, int STAGES, int MINB = 1, bool K3M = false>
 __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, MINB)
 zgemm_gather_kernel(const __grid_constant__ GemmArgs g) {
     constexpr int WARPS_M = BM / WM;
@@ -168,11 +173,15 @@ zgemm_gather_kernel(const __grid_constant__ GemmArgs g) {
         }
     };
 
-    double cr[MI][NI][2], ci[MI][NI][2];
+    // 4M: cr = Re, ci = Im.  3M: cr = P1, ci = P2, c3 = P3.
+    double cr[MI][NI][2], ci[MI][NI][2], c3[K3M ? MI : 1][K3M ? NI : 1][2];
 #pragma unroll
     for (int i = 0; i < MI; ++i)
 #pragma unroll
-        for (int j = 0; j < NI; ++j) cr[i][j][0] = cr[i][j][1] = ci[i][j][0] = ci[i][j][1] = 0.0;
+        for (int j = 0; j < NI; ++j) {
+            cr[i][j][0] = cr[i][j][1] = ci[i][j][0] = ci[i][j][1] = 0.0;
+            if (K3M) c3[K3M ? i : 0][K3M ? j : 0][0] = c3[K3M ? i : 0][K3M ? j : 0][1] = 0.0;
+        }
 
     const int nk = (int)((ke - kb + BK - 1) / BK);
 #pragma unroll
@@ -210,6 +219,26 @@ zgemm_gather_kernel(const __grid_constant__ GemmArgs g) {
         for (int k4 = 0; k4 < BK / 4; ++k4) {
             const int cur = k4 & 1;
             if (k4 + 1 < BK / 4) load_frags(cur ^ 1, k4 + 1);
+            if (K3M) {
+                double as[MI], bs[NI];
+#pragma unroll
+                for (int i = 0; i < MI; ++i) as[i] = af[cur][i].x + af[cur][i].y;
+#pragma unroll
+                for (int j = 0; j < NI; ++j) bs[j] = bf[cur][j].x + bf[cur][j].y;
+#pragma unroll
+                for (int i = 0; i < MI; ++i)
+#pragma unroll
+                    for (int j = 0; j < NI; ++j) dmma884(cr[i][j][0], cr[i][j][1], af[cur][i].x, bf[cur][j].x);
+#pragma unroll
+                for (int i = 0; i < MI; ++i)
+#pragma unroll
+                    for (int j = 0; j < NI; ++j) dmma884(ci[i][j][0], ci[i][j][1], af[cur][i].y, bf[cur][j].y);
+#pragma unroll
+                for (int i = 0; i < MI; ++i)
+#pragma unroll
+                    for (int j = 0; j < NI; ++j) dmma884(c3[K3M ? i : 0][K3M ? j : 0][0], c3[K3M ? i : 0][K3M ? j : 0][1], as[i], bs[j]);
+                continue;
+            }
             // four passes of MI*NI independent DMMAs (no back-to-back dependent accumulators)
 #pragma unroll
             for (int i = 0; i < MI; ++i)
@@ -247,7 +276,15 @@ zgemm_gather_kernel(const __grid_constant__ GemmArgs g) {
             const i64 co = g.c_dense ? c * g.M : tab_off(g.c_col, c);
 #pragma unroll
             for (int i = 0; i < MI; ++i)
-                if (crow[i] >= 0) store_c(Cbase + crow[i] + co, cr[i][j][q], ci[i][j][q], g.mode);
+                if (crow[i] >= 0) {
+                    double re = cr[i][j][q], im = ci[i][j][q];
+                    if (K3M) {
+                        const double p1 = re, p2 = im, p3 = c3[K3M ? i : 0][K3M ? j : 0][q];
+                        re = p1 - p2;
+                        im = p3 - p1 - p2;
+                    }
+                    store_c(Cbase + crow[i] + co, re, im, g.mode);
+                }
         }
 }
 

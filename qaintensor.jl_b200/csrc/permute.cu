@@ -63,7 +63,6 @@ __global__ void __launch_bounds__(256) copy_kernel(const double2* __restrict__ i
 static void* g_scratch = nullptr;
 static size_t g_scratch_bytes = 0;
 static void* g_hscratch = nullptr;
-static size_t g_hscratch_bytes = 0;
 
 static int scratch_reserve(size_t bytes) {
     if (bytes <= g_scratch_bytes) return QTN_OK;
@@ -72,10 +71,10 @@ static int scratch_reserve(size_t bytes) {
     if (g_hscratch) cudaFreeHost(g_hscratch);
     size_t nb = std::max<size_t>(bytes, 1 << 20);
     if (cudaMalloc(&g_scratch, nb) != cudaSuccess || cudaMallocHost(&g_hscratch, nb) != cudaSuccess) {
-        g_scratch = nullptr; g_hscratch = nullptr; g_scratch_bytes = g_hscratch_bytes = 0;
+        g_scratch = nullptr; g_hscratch = nullptr; g_scratch_bytes = 0;
         return fail(QTN_ENOMEM, "permute scratch allocation of %zu bytes failed", nb);
     }
-    g_scratch_bytes = g_hscratch_bytes = nb;
+    g_scratch_bytes = nb;
     return QTN_OK;
 }
 

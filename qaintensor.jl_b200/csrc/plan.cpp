@@ -74,11 +74,6 @@ int materialize_tables(Plan* p) {
 
 namespace {
 
-struct SymNode {
-    std::vector<int> labels;
-    std::vector<int64_t> dims, strides;
-};
-
 int64_t prod(const std::vector<int64_t>& v) {
     int64_t p = 1;
     for (auto x : v) p *= x;

@@ -23,7 +23,6 @@
 #include <cstring>
 #include <vector>
 
-#define QTN_SVD_TU
 #include "kernels.cuh"
 #include "qtn_internal.h"
 

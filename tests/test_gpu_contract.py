@@ -217,3 +217,18 @@ def test_cfg3_full_size_parity_chain(gpu):  # BASELINE config 3 at full size (se
     got31 = complex(p31.execute(arrays, sid31, sid31 + 1))
     p31.close()
     assert abs(got31 - sub) < TOL * abs(sub)
+
+
+def test_complex_3m_option_matches(gpu):  # opt-in 3-multiplication complex GEMM (QTN_COMPLEX_3M=1), same 1e-10 bar
+    import subprocess, sys, os
+    from conftest import ROOT
+    code = ("import sys; sys.path.insert(0, %r); import __graft_entry__ as g; q = g.load_package();"
+            "net, _, _ = q.circuits.cfg3_network(); q.optimize_contraction_order(net); il = q.contract_rep(net);"
+            "arrs = [t.data for t in net.tensors]; sh = [a.shape for a in arrs];"
+            "p = q.ContractionPlan(sh, il, None, q.choose_slices(sh, il, None, 28, 1));"
+            "v = complex(p.execute(arrs, 7, 8)); print(repr(v))" % ROOT)
+    outs = []
+    for flag in ("0", "1"):
+        env = dict(os.environ, QTN_COMPLEX_3M=flag)
+        outs.append(complex(eval(subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, check=True).stdout.strip().splitlines()[-1])))
+    assert abs(outs[0] - outs[1]) < 1e-10 * abs(outs[0])

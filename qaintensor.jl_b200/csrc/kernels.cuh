@@ -219,7 +219,7 @@ zgemm_gather_kernel(const __grid_constant__ GemmArgs g) {
         for (int k4 = 0; k4 < BK / 4; ++k4) {
             const int cur = k4 & 1;
             if (k4 + 1 < BK / 4) load_frags(cur ^ 1, k4 + 1);
-            if (K3M) {
+            if constexpr (K3M) {
                 double as[MI], bs[NI];
 #pragma unroll
                 for (int i = 0; i < MI; ++i) as[i] = af[cur][i].x + af[cur][i].y;
@@ -237,8 +237,7 @@ zgemm_gather_kernel(const __grid_constant__ GemmArgs g) {
                 for (int i = 0; i < MI; ++i)
 #pragma unroll
                     for (int j = 0; j < NI; ++j) dmma884(c3[K3M ? i : 0][K3M ? j : 0][0], c3[K3M ? i : 0][K3M ? j : 0][1], as[i], bs[j]);
-                continue;
-            }
+            } else {
             // four passes of MI*NI independent DMMAs (no back-to-back dependent accumulators)
 #pragma unroll
             for (int i = 0; i < MI; ++i)
@@ -256,6 +255,7 @@ zgemm_gather_kernel(const __grid_constant__ GemmArgs g) {
             for (int i = 0; i < MI; ++i)
 #pragma unroll
                 for (int j = 0; j < NI; ++j) dmma884(ci[i][j][0], ci[i][j][1], af[cur][i].y, bf[cur][j].x);
+            }
         }
     }
     cp_async_wait<0>();

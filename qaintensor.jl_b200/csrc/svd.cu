@@ -44,6 +44,7 @@ constexpr int JP = 2 * JB;    // panel width (columns per CTA)
 constexpr int JPITCH = JP + 2;
 constexpr int JROWS = 64;     // panel rows staged per chunk
 constexpr int JTHREADS = 256;
+constexpr int JRP = JROWS + 4;  // allocated row pitch of a chunk buffer column (phase 1 uses +4, phase 3 uses +2)
 constexpr int kInnerSweeps = 1;  // one eigen-sweep per Gram visit measured fastest (1: 108 ms, 2: 153, 3: 165, 6: 187 ms for 1024^2)
 
 struct SvdProblem {
@@ -54,6 +55,26 @@ struct SvdProblem {
     int* last_mod;  // [nblocks]  launch stamp of the last rotation that touched a column block
     int* last_ok;   // [nblocks * nblocks] launch stamp at which a block pair was last found converged
 };
+
+// ---- TMA bulk copy (cp.async.bulk, SASS UBLKCP) + mbarrier helpers -----------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    unsigned ok;
+    do {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
 
 __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
     asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
@@ -98,58 +119,80 @@ jacobi_round_kernel(const SvdProblem* __restrict__ probs, int round, double tol,
         return;
     }
 
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    double2* Ps = reinterpret_cast<double2*>(smem_raw);   // [JROWS][JPITCH] panel chunk
-    double2* G = Ps + JROWS * JPITCH;                     // [JP][JPITCH]
-    double2* W = G + JP * JPITCH;                         // [JP][JPITCH]
-    double2* Gpart = W + JP * JPITCH;                     // [JP][JPITCH] this CTA's partial Gram (read by the cluster)
-    double2* rot = Gpart + JP * JPITCH;                   // [JB] (c, s) + phase
-    double2* rph = rot + JB;                              // [JB] e^{i phi}
+    // shared memory: two panel-chunk buffers [col][row] (filled by TMA bulk copies), G, W, rotation scratch.
+    // The partial Gram Gpart aliases chunk buffer 1 (the buffers are idle between phase 1 and phase 3).
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double2* Pc = reinterpret_cast<double2*>(smem_raw);                  // [2][JP][JRP]
+    double2* G = Pc + 2 * JP * JRP;                                       // [JP][JPITCH]
+    double2* W = G + JP * JPITCH;                                         // [JP][JPITCH]
+    double2* rot = W + JP * JPITCH;                                       // [JB] (c, s)
+    double2* rph = rot + JB;                                              // [JB] e^{i phi}, then [2*JB] ints (p, q)
+    double2* Gpart = Pc + JP * JRP;                                       // alias of chunk buffer 1
     __shared__ int s_any, s_sweep_any, s_rot;
     __shared__ int s_cols[JP];
+    __shared__ __align__(8) unsigned long long s_full[2];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid < JP) s_cols[tid] = panel_col(tid, bi, bj, pr.n);
-    if (tid == 0) { s_any = 0; s_rot = 0; }
-    for (int i = tid; i < JP * JPITCH; i += JTHREADS) { G[i] = make_double2(0, 0); W[i] = make_double2(0, 0); Gpart[i] = make_double2(0, 0); }
+    if (tid == 0) {
+        s_any = 0; s_rot = 0;
+        mbar_init(&s_full[0], 1);
+        mbar_init(&s_full[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = tid; i < JP * JPITCH; i += JTHREADS) { G[i] = make_double2(0, 0); W[i] = make_double2(0, 0); }
+    for (int i = tid; i < 2 * JP * JRP; i += JTHREADS) Pc[i] = make_double2(0, 0);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // zeros visible to the async (TMA) proxy
     __syncthreads();
 
-    // ---------------- phase 1: G = P^H P (each warp takes rows warp*8.. of every chunk) -----------
+    // Chunk pipeline: thread 0 issues one cp.async.bulk per panel column (JROWS rows = 1 KB, contiguous in the
+    // column-major matrix) into buffer `it & 1` with pitch `rp`, completion on an mbarrier; chunk it+1 is in
+    // flight while the DMMAs of chunk it run.  Padding columns are never written (stay zero); a partial last
+    // chunk re-zeroes its buffer first.
+    unsigned issued = 0, waited = 0;  // running chunk counters (parity of the two mbarriers)
+    auto issue = [&](const double2* base, int ld, int r0, int nrows, int rp) {
+        const int buf = issued & 1;
+        const int rows = min(JROWS, nrows - r0);
+        if (rows < JROWS) {  // uniform branch: partial chunk, clear stale rows
+            for (int i = tid; i < JP * JRP; i += JTHREADS) Pc[buf * JP * JRP + i] = make_double2(0, 0);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncthreads();
+        }
+        if (tid == 0) {
+            int ncol = 0;
+            for (int c = 0; c < JP; ++c) ncol += s_cols[c] >= 0;
+            mbar_expect_tx(&s_full[buf], (unsigned)(ncol * rows * 16));
+            for (int c = 0; c < JP; ++c)
+                if (s_cols[c] >= 0)
+                    bulk_g2s(Pc + (size_t)buf * JP * JRP + c * rp, base + (size_t)s_cols[c] * ld + r0, (unsigned)(rows * 16), &s_full[buf]);
+        }
+        ++issued;
+    };
+    auto wait_chunk = [&]() -> const double2* {
+        const int buf = waited & 1;
+        mbar_wait(&s_full[buf], (waited >> 1) & 1);
+        ++waited;
+        return Pc + (size_t)buf * JP * JRP;
+    };
+    const int cstep = CL * JROWS;  // this CTA takes chunks crank, crank + CL, ...
+
+    // ---------------- phase 1: G = P^H P (warp w takes k-rows [8w, 8w+8) of every chunk) -----------
     double gr[4][4][2], gi[4][4][2];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) gr[i][j][0] = gr[i][j][1] = gi[i][j][0] = gi[i][j][1] = 0.0;
-    // chunk staging is software-pipelined: the global loads of chunk i+1 are issued into
-    // registers before the DMMAs of chunk i and parked in shared memory afterwards
-    double2 pre[JP * JROWS / JTHREADS];
-    auto fetch = [&](const double2* base, int ld, int r0, int nrows) {
-        const int r = tid & (JROWS - 1);
-#pragma unroll
-        for (int i = 0; i < JP * JROWS / JTHREADS; ++i) {
-            const int col = s_cols[tid / JROWS + i * (JTHREADS / JROWS)];
-            pre[i] = (col >= 0 && r0 + r < nrows) ? base[(size_t)col * ld + r0 + r] : make_double2(0, 0);
-        }
-    };
-    auto stash = [&]() {
-        const int r = tid & (JROWS - 1);
-#pragma unroll
-        for (int i = 0; i < JP * JROWS / JTHREADS; ++i) Ps[r * JPITCH + tid / JROWS + i * (JTHREADS / JROWS)] = pre[i];
-    };
-    const int cstep = CL * JROWS;  // this CTA takes chunks crank, crank + CL, ...
-    if (crank * JROWS < pr.m) fetch(pr.A, pr.m, crank * JROWS, pr.m);
+    constexpr int RP1 = JROWS + 4;  // pitch = 4 mod 8 (16-B units): conflict-free LDS.128 for the Gram fragments
+    if (crank * JROWS < pr.m) issue(pr.A, pr.m, crank * JROWS, pr.m, RP1);
     for (int r0 = crank * JROWS; r0 < pr.m; r0 += cstep) {
-        stash();
-        __syncthreads();
-        if (r0 + cstep < pr.m) fetch(pr.A, pr.m, r0 + cstep, pr.m);
-        // warp w owns k-rows [8w, 8w+8) of the chunk: two k4 steps
+        if (r0 + cstep < pr.m) issue(pr.A, pr.m, r0 + cstep, pr.m, RP1);
+        const double2* Ps = wait_chunk();
 #pragma unroll
         for (int k4 = 0; k4 < 2; ++k4) {
             const int kr = warp * 8 + k4 * 4 + (lane & 3);
             double2 f[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) f[i] = Ps[kr * JPITCH + i * 8 + (lane >> 2)];
-            // G[i][j] += conj(P[k][i]) * P[k][j]:  re = ar*br + ai*bi ; im = ar*bi - ai*br
+            for (int i = 0; i < 4; ++i) f[i] = Ps[(i * 8 + (lane >> 2)) * RP1 + kr];
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -161,9 +204,11 @@ jacobi_round_kernel(const SvdProblem* __restrict__ probs, int round, double tol,
                     dmma(gi[i][j][0], gi[i][j][1], -f[i].y, f[j].x);
                 }
         }
-        __syncthreads();
+        __syncthreads();  // buffer free for the chunk after next
     }
-    // cross-warp reduction into G (shared atomics on doubles; 8 warps)
+    // cross-warp reduction into Gpart (aliases chunk buffer 1: all chunk reads are complete)
+    for (int i = tid; i < JP * JPITCH; i += JTHREADS) Gpart[i] = make_double2(0, 0);
+    __syncthreads();
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -186,7 +231,7 @@ jacobi_round_kernel(const SvdProblem* __restrict__ probs, int round, double tol,
         }
         G[e] = acc;
     }
-    cluster.sync();  // remote reads done before anyone may leave
+    cluster.sync();  // remote reads done before anyone may leave or re-use the buffer
     // mirror the strictly-lower block triangle, set W = I
     for (int e = tid; e < JP * JP; e += JTHREADS) {
         const int r = e / JP, c = e % JP;
@@ -304,22 +349,23 @@ jacobi_round_kernel(const SvdProblem* __restrict__ probs, int round, double tol,
 
     // ---------------- phase 3: P <- P W for the A panel and the V panel ---------------------------------
     // warp w owns rows [8w, 8w+8) of each 64-row chunk: C(8 x 32) = P(8 x 32) W(32 x 32)
+    constexpr int RP3 = JROWS + 2;  // pitch = 2 mod 8: conflict-free A-fragment loads for the update
+    for (int i = tid; i < 2 * JP * JRP; i += JTHREADS) Pc[i] = make_double2(0, 0);  // Gpart lived here; padding must read 0
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
     for (int which = 0; which < (pr.V ? 2 : 1); ++which) {
         double2* base = which ? pr.V : pr.A;
         const int nrows = which ? pr.n : pr.m;
-        __syncthreads();
-        if (crank * JROWS < nrows) fetch(base, nrows, crank * JROWS, nrows);
+        if (crank * JROWS < nrows) issue(base, nrows, crank * JROWS, nrows, RP3);
         for (int r0 = crank * JROWS; r0 < nrows; r0 += cstep) {
-            __syncthreads();
-            stash();
-            __syncthreads();
-            if (r0 + cstep < nrows) fetch(base, nrows, r0 + cstep, nrows);
+            if (r0 + cstep < nrows) issue(base, nrows, r0 + cstep, nrows, RP3);
+            const double2* Ps = wait_chunk();
             double cr[4][2], ci[4][2];
 #pragma unroll
             for (int j = 0; j < 4; ++j) cr[j][0] = cr[j][1] = ci[j][0] = ci[j][1] = 0.0;
 #pragma unroll
             for (int k4 = 0; k4 < JP / 4; ++k4) {
-                const double2 a = Ps[(warp * 8 + (lane >> 2)) * JPITCH + k4 * 4 + (lane & 3)];
+                const double2 a = Ps[(k4 * 4 + (lane & 3)) * RP3 + warp * 8 + (lane >> 2)];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const double2 b = W[(k4 * 4 + (lane & 3)) * JPITCH + j * 8 + (lane >> 2)];
@@ -339,6 +385,7 @@ jacobi_round_kernel(const SvdProblem* __restrict__ probs, int round, double tol,
                         if (col >= 0) base[(size_t)col * nrows + row] = make_double2(cr[j][q], ci[j][q]);
                     }
             }
+            __syncthreads();  // buffer free for the chunk after next
         }
     }
 }
@@ -595,7 +642,7 @@ int svd_batched_device(int batch, const SvdJob* jobs, double er, int64_t maxdim,
     set_identity_kernel<<<dim3(std::min(148 * 4, (maxn * maxn + 255) / 256), batch), 256, 0, st>>>(dp);
     fro_norm_kernel<<<dim3(std::min(148, (maxn * maxm + 255) / 256), batch), 256, 0, st>>>(dp, dfro);
     count_launch(2);
-    const size_t smem = (size_t)(JROWS * JPITCH + 3 * JP * JPITCH + 2 * JB) * 16 + JB * 8 + 64;
+    const size_t smem = (size_t)(2 * JP * JRP + 2 * JP * JPITCH + 2 * JB) * 16 + JB * 8 + 64;
     static bool attr = false;
     if (!attr) { CUDA_TRY(cudaFuncSetAttribute(jacobi_round_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
     int max_nb = (maxn + JB - 1) / JB;

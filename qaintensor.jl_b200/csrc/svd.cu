@@ -158,13 +158,13 @@ jacobi_round_kernel(const SvdProblem* __restrict__ probs, int round, double tol,
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncthreads();
         }
-        if (tid == 0) {
-            int ncol = 0;
-            for (int c = 0; c < JP; ++c) ncol += s_cols[c] >= 0;
-            mbar_expect_tx(&s_full[buf], (unsigned)(ncol * rows * 16));
-            for (int c = 0; c < JP; ++c)
-                if (s_cols[c] >= 0)
-                    bulk_g2s(Pc + (size_t)buf * JP * JRP + c * rp, base + (size_t)s_cols[c] * ld + r0, (unsigned)(rows * 16), &s_full[buf]);
+        if (warp == 0) {  // lane c issues the bulk copy of panel column c: 32 copies in flight at once
+            const int col = s_cols[lane];
+            const unsigned ncol = __popc(__ballot_sync(0xffffffffu, col >= 0));
+            if (lane == 0) mbar_expect_tx(&s_full[buf], ncol * (unsigned)(rows * 16));
+            __syncwarp();
+            if (col >= 0)
+                bulk_g2s(Pc + (size_t)buf * JP * JRP + lane * rp, base + (size_t)col * ld + r0, (unsigned)(rows * 16), &s_full[buf]);
         }
         ++issued;
     };

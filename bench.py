@@ -406,10 +406,8 @@ def main():
         base = ((i * world + rank) * sps) % max(plan.nslices - sps + 1, 1)
         plan.execute_device(out.data_ptr(), base, base + sps)
         if world > 1:
-            if args.precision == "c128":
-                _lib.check(_lib.lib.qtn_nccl_allreduce_sum_f64(out.data_ptr(), 2 * plan.out_numel))
-            else:
-                dist.all_reduce(out)
+            fn = _lib.lib.qtn_nccl_allreduce_sum_f64 if args.precision == "c128" else _lib.lib.qtn_nccl_allreduce_sum_f32
+            _lib.check(fn(out.data_ptr(), 2 * plan.out_numel))
 
     def sync_all():
         torch.cuda.synchronize()

@@ -132,6 +132,7 @@ int qtn_contract(int32_t nt, const void* const* host_data, const int32_t* ranks,
 int qtn_nccl_unique_id(void* id_out /* 128 bytes */);
 int qtn_nccl_init(int32_t rank, int32_t nranks, const void* id /* 128 bytes */);
 int qtn_nccl_allreduce_sum_f64(void* dev_buf, int64_t count);
+int qtn_nccl_allreduce_sum_f32(void* dev_buf, int64_t count); /* ComplexF32 mode */
 int qtn_contract_sliced(qtn_plan* plan, const void* const* host_data, int32_t rank,
                         int32_t nranks, void* host_out);
 /* Same over the slice window [first_slice, first_slice + nslices) only (partial sums,

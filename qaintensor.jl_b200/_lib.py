@@ -63,6 +63,7 @@ _SIGS = {
     "qtn_nccl_unique_id": [vp],
     "qtn_nccl_init": [i32, i32, vp],
     "qtn_nccl_allreduce_sum_f64": [vp, i64],
+    "qtn_nccl_allreduce_sum_f32": [vp, i64],
     "qtn_contract_sliced": [vp, P(vp), i32, i32, vp],
     "qtn_contract_sliced_range": [vp, P(vp), i64, i64, i32, i32, vp],
     "qtn_permutedims": [vp, i32, P(i64), P(i32), i32, vp],

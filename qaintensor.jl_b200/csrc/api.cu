@@ -209,6 +209,7 @@ static int nccl_allreduce(void* dev_buf, int64_t count, int nccl_dtype) {
     return QTN_OK;
 }
 int qtn_nccl_allreduce_sum_f64(void* dev_buf, int64_t count) { return nccl_allreduce(dev_buf, count, /*ncclFloat64*/ 8); }
+int qtn_nccl_allreduce_sum_f32(void* dev_buf, int64_t count) { return nccl_allreduce(dev_buf, count, /*ncclFloat32*/ 7); }
 
 static int exec_host(Plan* p, const void* const* host_data, int64_t s0, int64_t s1, void* host_out, bool allreduce) {
     int rc = QTN_OK;

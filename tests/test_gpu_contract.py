@@ -232,3 +232,23 @@ def test_complex_3m_option_matches(gpu):  # opt-in 3-multiplication complex GEMM
         env = dict(os.environ, QTN_COMPLEX_3M=flag)
         outs.append(complex(eval(subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, check=True).stdout.strip().splitlines()[-1])))
     assert abs(outs[0] - outs[1]) < 1e-10 * abs(outs[0])
+
+
+def test_random_general_networks_numeric(gpu):  # mixed extents, open legs, self-contractions, slicing
+    from test_host_planner import _random_general_network
+    q = gpu
+    rng = np.random.default_rng(23)
+    for trial in range(25):
+        net = _random_general_network(q, rng, int(rng.integers(2, 9)), int(rng.integers(1, 12)), int(rng.integers(0, 4)))
+        want = oc.contract(to_oracle(net))
+        got = q.contract(net)
+        assert got.shape == np.shape(want) and rel_err(got, want) < TOL
+        il = q.contract_rep(net)
+        arrays = [t.data for t in net.tensors]
+        shapes = [a.shape for a in arrays]
+        plan = q.ContractionPlan(shapes, il)
+        S = q.choose_slices(shapes, il, None, max(int(np.log2(max(plan.max_elems, 2))) - 2, 1), 2)
+        if S:
+            sp = q.ContractionPlan(shapes, il, None, S)
+            assert rel_err(sp.execute(arrays), want) < TOL
+            assert rel_err(q.ContractionPlan(shapes, il, None, S, precision="c64").execute(arrays), want) < 1e-4

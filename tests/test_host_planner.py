@@ -130,3 +130,57 @@ def test_plan_rejects_malformed_networks(q):
         q.ContractionPlan([(2, 3), (2,)], [[-1, 1], [1]])
     with pytest.raises(q.QtnError, match="not a contracted label"):
         q.ContractionPlan([(2, 2), (2,)], [[-1, 1], [1]], None, [7])
+
+
+def _random_general_network(q, rng, nt, ncon, nopen):
+    """Random network with mixed extents (2..4), open legs and an occasional self-contraction."""
+    legs = [[] for _ in range(nt)]          # per tensor: list of extents
+    cons = []
+    for _ in range(ncon):
+        d = int(rng.integers(2, 5))
+        if rng.random() < 0.1:
+            a = b = int(rng.integers(1, nt + 1))
+        else:
+            a, b = (int(x) for x in rng.choice(np.arange(1, nt + 1), size=2, replace=False))
+        legs[a - 1].append(d)
+        la = len(legs[a - 1])
+        legs[b - 1].append(d)
+        cons.append(q.Summation([(a, la), (b, len(legs[b - 1]))]))
+    opn = []
+    for _ in range(nopen):
+        t = int(rng.integers(1, nt + 1))
+        legs[t - 1].append(int(rng.integers(2, 4)))
+        opn.append((t, len(legs[t - 1])))
+    for t in range(nt):
+        if not legs[t]:
+            legs[t].append(2)
+            opn.append((t + 1, 1))
+    ts = [q.Tensor(rng.standard_normal(tuple(l)) + 1j * rng.standard_normal(tuple(l))) for l in legs]
+    return q.GeneralTensorNetwork(ts, cons, opn)
+
+
+def test_random_general_networks_plan_parity(q):
+    """Planner vs oracle tree on random networks: step count, (M,N,K) multiset, cost, output shape, slice set."""
+    rng = np.random.default_rng(11)
+    for trial in range(40):
+        nt = int(rng.integers(2, 9))
+        net = _random_general_network(q, rng, nt, int(rng.integers(1, 12)), int(rng.integers(0, 4)))
+        il = q.contract_rep(net)
+        arrays = [t.data for t in net.tensors]
+        shapes = [a.shape for a in arrays]
+        plan = q.ContractionPlan(shapes, il)
+        nodes, steps = oplan.contraction_tree(il)
+        dims = oplan.label_dims(arrays, il)
+        f, b, mx, mnk = oplan.tree_cost(nodes, steps, dims)
+        gemm = [(max(m, n), min(m, n), k) for m, n, k, fl in plan.steps() if ((fl >> 1) & 7) == 0]
+        assert sorted(gemm) == sorted((max(m, n), min(m, n), k) for m, n, k in mnk)
+        assert (plan.flops_per_slice, plan.bytes_per_slice) == (f, b)
+        want_shape = tuple(dims[l] for l in sorted((l for lab in il for l in lab if l < 0), reverse=True))
+        assert plan.out_dims == want_shape
+        lim = max(int(np.log2(max(mx, 2))) - 2, 1)
+        S = q.choose_slices(shapes, il, None, lim, 2)
+        assert S == oplan.choose_slice_labels(nodes, steps, dims, lim, 2)
+        if S:
+            sp = q.ContractionPlan(shapes, il, None, S)
+            f2, b2, mx2, _ = oplan.tree_cost(nodes, steps, dims, S)
+            assert (sp.flops_per_slice, sp.nslices) == (f2, int(np.prod([dims[l] for l in S])))

@@ -148,7 +148,7 @@ int launch_cgemm(GemmArgs& g, int variant, int split_k, cudaStream_t st) {
         count_launch(1);
         return QTN_OK;
     }
-    const int BM = 64, BN = 64, BK = 16;
+    const int BM = 128, BN = 64, BK = 8;
     int64_t tm = (g.M + BM - 1) / BM, tn = (g.N + BN - 1) / BN;
     if (tm * tn > 2147483647LL) return fail(QTN_EINVAL, "GEMM grid too large");
     g.tiles_m = (int)tm;

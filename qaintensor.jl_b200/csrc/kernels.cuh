@@ -298,7 +298,8 @@ __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc, bool
 }
 
 __global__ void __launch_bounds__(256) cgemm_gather_kernel(const __grid_constant__ GemmArgs g) {
-    constexpr int BM = 64, BN = 64, BK = 16, NT = 256, PA = BM + 2, PB = BN + 2, STAGES = 2;
+    // CTA tile 128 x 64, thread tile 8 x 4 complex (rows tx + 16 i, columns ty * 4 + j), BK = 8, 3 stages
+    constexpr int BM = 128, BN = 64, BK = 8, NT = 256, PA = BM + 2, PB = BN + 2, STAGES = 3, TM = 8, TN = 4;
     __shared__ __align__(16) float2 sA[STAGES][BK][PA];
     __shared__ __align__(16) float2 sB[STAGES][BK][PB];
     __shared__ i64 sRow[BM], sCol[BN];
@@ -316,72 +317,75 @@ __global__ void __launch_bounds__(256) cgemm_gather_kernel(const __grid_constant
     for (int i = tid; i < BM; i += NT) sRow[i] = (m0 + i < g.M) ? tab_off(g.a_row, m0 + i) : -1;
     for (int i = tid; i < BN; i += NT) sCol[i] = (n0 + i < g.N) ? tab_off(g.b_col, n0 + i) : -1;
     __syncthreads();
-    const int lk = tid >> 4, lr = tid & 15;
+    const int lk = tid >> 5, lr = tid & 31;  // 32 threads per k-row of a stage
     auto load_stage = [&](int stage, i64 k0) {
         const i64 k = k0 + lk;
         const bool kv = k < ke;
         const i64 ka = kv ? tab_off(g.a_k, k) : 0, kbo = kv ? tab_off(g.b_k, k) : 0;
 #pragma unroll
-        for (int i = 0; i < BM / 16; ++i) {
-            const int m = lr + 16 * i;
+        for (int i = 0; i < BM / 32; ++i) {
+            const int m = lr + 32 * i;
             const i64 ro = sRow[m];
             const bool v = kv && ro >= 0;
             cp_async8(&sA[stage][lk][m], v ? (A + ro + ka) : A, v);
         }
 #pragma unroll
-        for (int i = 0; i < BN / 16; ++i) {
-            const int n = lr + 16 * i;
+        for (int i = 0; i < BN / 32; ++i) {
+            const int n = lr + 32 * i;
             const i64 co = sCol[n];
             const bool v = kv && co >= 0;
             cp_async8(&sB[stage][lk][n], v ? (B + co + kbo) : B, v);
         }
     };
-    float cr[4][4], ci[4][4];
+    float cr[TM][TN], ci[TM][TN];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < TM; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) cr[i][j] = ci[i][j] = 0.f;
+        for (int j = 0; j < TN; ++j) cr[i][j] = ci[i][j] = 0.f;
+    const float sa = g.conj_a ? -1.f : 1.f, sb = g.conj_b ? -1.f : 1.f;
     const int nk = (int)((ke - kb + BK - 1) / BK);
-    if (nk > 0) load_stage(0, kb);
-    cp_async_commit();
-    for (int it = 0; it < nk; ++it) {
-        if (it + 1 < nk) load_stage((it + 1) & 1, kb + (i64)(it + 1) * BK);
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; ++s) {
+        if (s < nk) load_stage(s, kb + (i64)s * BK);
         cp_async_commit();
-        cp_async_wait<1>();
+    }
+    for (int it = 0; it < nk; ++it) {
+        cp_async_wait<STAGES - 2>();
         __syncthreads();
-        const int st = it & 1;
+        {
+            const int nx = it + STAGES - 1;
+            if (nx < nk) load_stage(nx % STAGES, kb + (i64)nx * BK);
+            cp_async_commit();
+        }
+        const int st = it % STAGES;
 #pragma unroll
         for (int k = 0; k < BK; ++k) {
-            // rows tx + 16 i (coalesced 128-B row runs in the epilogue), columns ty * 4 + j (broadcast reads)
-            float2 a[4], b[4];
+            float2 a[TM], b[TN];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) a[i] = sA[st][k][tx + 16 * i];
+            for (int i = 0; i < TM; ++i) { a[i] = sA[st][k][tx + 16 * i]; a[i].y *= sa; }
             const float4 b01 = *reinterpret_cast<const float4*>(&sB[st][k][ty * 4]);
             const float4 b23 = *reinterpret_cast<const float4*>(&sB[st][k][ty * 4 + 2]);
-            b[0] = make_float2(b01.x, b01.y); b[1] = make_float2(b01.z, b01.w); b[2] = make_float2(b23.x, b23.y); b[3] = make_float2(b23.z, b23.w);
+            b[0] = make_float2(b01.x, b01.y * sb); b[1] = make_float2(b01.z, b01.w * sb);
+            b[2] = make_float2(b23.x, b23.y * sb); b[3] = make_float2(b23.z, b23.w * sb);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float ax = a[i].x, ay = g.conj_a ? -a[i].y : a[i].y;
+            for (int i = 0; i < TM; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float bx = b[j].x, by = g.conj_b ? -b[j].y : b[j].y;
-                    cr[i][j] = fmaf(ax, bx, cr[i][j]);
-                    cr[i][j] = fmaf(-ay, by, cr[i][j]);
-                    ci[i][j] = fmaf(ax, by, ci[i][j]);
-                    ci[i][j] = fmaf(ay, bx, ci[i][j]);
+                for (int j = 0; j < TN; ++j) {
+                    cr[i][j] = fmaf(a[i].x, b[j].x, cr[i][j]);
+                    cr[i][j] = fmaf(-a[i].y, b[j].y, cr[i][j]);
+                    ci[i][j] = fmaf(a[i].x, b[j].y, ci[i][j]);
+                    ci[i][j] = fmaf(a[i].y, b[j].x, ci[i][j]);
                 }
-            }
         }
-        __syncthreads();
     }
     cp_async_wait<0>();
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < TN; ++j) {
         const i64 c = n0 + ty * 4 + j;
         if (c >= g.N) continue;
         const i64 co = g.c_dense ? c * g.M : tab_off(g.c_col, c);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < TM; ++i) {
             const i64 r = m0 + tx + 16 * i;
             if (r >= g.M) continue;
             const i64 ro = g.c_dense ? r : tab_off(g.c_row, r);

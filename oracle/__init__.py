@@ -22,9 +22,12 @@ Rules ("Oracle"):
   with fixed seeds, and against independent dense linear algebra (DFT matrix,
   ``kron`` state vectors, ``numpy.linalg.svd``).  Numeric amplitude /
   singular-value vectors do not exist in the reference (its tests are unseeded
-  and compare paths with ``≈``), so for those quantities parity is
-  "pinned by relation", and the exact contraction *order* for a given network
-  is pinned only by the hand-traced vector of SURVEY.md Appendix B.
+  and compare paths with ``≈``), and the reference cannot be executed here, so
+  for those quantities the status is **parity unpinned** against the reference
+  itself: they are pinned only by relation (dense ``U*psi``, DFT, LAPACK) and
+  by the oracle-generated fixtures of ``tests/golden/``.  The exact contraction
+  *order* for a given network is pinned by the literal subroutine known-answers
+  plus the hand-traced vector of SURVEY.md Appendix B.
 
 Index conventions: every public oracle function speaks the reference's
 conventions -- 1-based tensor / leg / wire numbers, column-major reshapes

@@ -198,6 +198,11 @@ int qtn_mps_apply_layer(qtn_mps* mps, int32_t ngates, const int32_t* sites,
                         double* disc_out /* ngates */);
 /* <a|b> by transfer-matrix contraction; result (re, im).                           */
 int qtn_mps_overlap(const qtn_mps* a, const qtn_mps* b, double out[2]);
+/* Replaces `MPS(psi::Vector{ComplexF64})` (src/mps.jl:55-89): the whole left-to-right chain of
+ * thin SVDs (no truncation) runs on the device.  psi has 2^nsites entries (site 1 = fastest bit).
+ * host_sites[i] receives site i: first (2, b1), middle (b_{i-1}, 2, b_i), last (b_{n-1}, 2), column-major;
+ * bonds_out[i] (nsites-1 entries) = b_{i+1}.  Buffers must hold min(2^i, 2^(n-i)) bonds.          */
+int qtn_mps_from_vector(const void* host_psi, int32_t nsites, void* const* host_sites, int64_t* bonds_out);
 /* EXTENSION (SURVEY 8a iii/iv): site-tensor MPO with the layout of src/mpo.jl:66,
  * W_i = (bond_in, out, in, bond_out) = (dl[i], 2, 2, dr[i]), dl[0] = dr[n-1] = 1.
  * qtn_mps_apply_mpo: |psi> <- compress(MPO |psi>): site-wise apply (bonds multiply), a

@@ -80,6 +80,7 @@ _SIGS = {
     "qtn_mps_apply_gate2": [vp, i32, vp, f64, i64, P(f64)],
     "qtn_mps_apply_layer": [vp, i32, P(i32), vp, f64, i64, P(f64)],
     "qtn_mps_overlap": [vp, vp, P(f64)],
+    "qtn_mps_from_vector": [vp, i32, P(vp), P(i64)],
     "qtn_mps_apply_mpo": [vp, P(vp), P(i64), P(i64), f64, i64, P(f64)],
     "qtn_mps_expect_mpo": [vp, P(vp), P(i64), P(i64), P(f64)],
 }

@@ -363,6 +363,40 @@ int qtn_mps_overlap(const qtn_mps* a, const qtn_mps* b, double out[2]) {
     return QTN_OK;
 }
 
+// ---------------- MPS(psi) on the device (src/mps.jl:55-89) ----------------------------------------------
+int qtn_mps_from_vector(const void* host_psi, int32_t nsites, void* const* host_sites, int64_t* bonds_out) {
+    if (!host_psi || !host_sites || !bonds_out) return fail(QTN_EINVAL, "qtn_mps_from_vector: null argument");
+    if (nsites < 2 || nsites > 30) return fail(QTN_EINVAL, "qtn_mps_from_vector: nsites must be in 2..30");
+    int rc = device_ready();
+    if (rc) return rc;
+    cudaStream_t st = stream();
+    const int64_t n = (int64_t)1 << nsites;
+    DevBuf rest, U, S, Vh, tmp;
+    if ((rc = rest.alloc(n * 16)) || (rc = tmp.alloc(n * 16))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(rest.p, host_psi, n * 16, cudaMemcpyHostToDevice, st));
+    int64_t lbond = 1, cols = n;
+    for (int bit = 1; bit < nsites; ++bit) {
+        // rest is (lbond*2) x (cols/2): U -> site `bit`, diag(S) V' -> next rest      (src/mps.jl:62-76)
+        const int64_t m = lbond * 2;
+        cols /= 2;
+        const int64_t r = std::min(m, cols);
+        DevBuf u, s, v;
+        if ((rc = u.alloc(m * r * 16)) || (rc = s.alloc(r * 8)) || (rc = v.alloc(r * cols * 16))) return rc;
+        SvdJob job{(double2*)rest.p, m, cols, (double2*)u.p, (double*)s.p, (double2*)v.p};
+        int64_t k = 0;
+        if ((rc = svd_batched_device(1, &job, -1.0, 0, &k, nullptr, nullptr))) return rc;
+        CUDA_TRY(cudaMemcpyAsync(host_sites[bit - 1], u.p, (size_t)m * r * 16, cudaMemcpyDeviceToHost, st));
+        if ((rc = scale_copy((double2*)v.p, r, (double2*)tmp.p, r, r, cols, (double*)s.p, 0))) return rc;
+        CUDA_TRY(cudaMemcpyAsync(rest.p, tmp.p, (size_t)r * cols * 16, cudaMemcpyDeviceToDevice, st));
+        CUDA_TRY(cudaStreamSynchronize(st));  // u/s/v are freed at the end of the iteration
+        bonds_out[bit - 1] = r;
+        lbond = r;
+    }
+    CUDA_TRY(cudaMemcpyAsync(host_sites[nsites - 1], rest.p, (size_t)lbond * 2 * 16, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return QTN_OK;
+}
+
 // ---------------- MPO x MPS (EXTENSION iii / iv) ------------------------------------------------------
 static int check_mpo(const qtn_mps* m, const void* const* sites, const int64_t* dl, const int64_t* dr) {
     if (!m || !sites || !dl || !dr) return fail(QTN_EINVAL, "qtn_mps mpo: null argument");

@@ -51,6 +51,8 @@ def _from_vector(psi):  # src/mps.jl:55-89: sequential thin SVD, no truncation
     if not is_power_two(psi.size):
         raise ValueError("Input state must have length 2^N")
     M = psi.size.bit_length() - 1
+    if M >= 2:
+        return _from_vector_device(psi, M)
     tensors, contractions, openidx = [], [], [(1, 1)]
     U, S, Vh = svd(np.reshape(psi, (2, -1), order="F"))
     tensors.append(Tensor(U))
@@ -66,6 +68,27 @@ def _from_vector(psi):  # src/mps.jl:55-89: sequential thin SVD, no truncation
     tensors.append(Tensor(rest))
     contractions.append(Summation([(M - 1, lastleg), (M, 1)]))
     openidx.append((M, 2))
+    return tensors, contractions, openidx
+
+
+def _from_vector_device(psi, M):
+    """The whole SVD chain of ``MPS(psi)`` in one library call (``qtn_mps_from_vector``)."""
+    import ctypes as C
+    from . import _lib
+    _lib.require_device()
+    bonds_cap = [min(2 ** i, 2 ** (M - i)) for i in range(1, M)]
+    shapes = [(2, bonds_cap[0])] + [(bonds_cap[i - 1], 2, bonds_cap[i]) for i in range(1, M - 1)] + [(bonds_cap[-1], 2)]
+    bufs = [np.zeros(int(np.prod(s)), dtype=np.complex128) for s in shapes]
+    ptrs = (C.c_void_p * M)(*[b.ctypes.data for b in bufs])
+    bonds = (C.c_int64 * max(M - 1, 1))()
+    _lib.check(_lib.lib.qtn_mps_from_vector(_lib.as_c128(psi).ctypes.data_as(C.c_void_p), M, ptrs, bonds))
+    b = [int(bonds[i]) for i in range(M - 1)]
+    tensors = []
+    for i in range(M):
+        shp = (2, b[0]) if i == 0 else ((b[-1], 2) if i == M - 1 else (b[i - 1], 2, b[i]))
+        tensors.append(Tensor(np.reshape(bufs[i][:int(np.prod(shp))], shp, order="F")))
+    contractions = [Summation([(1, 2), (2, 1)])] + [Summation([(i, 3), (i + 1, 1)]) for i in range(2, M)]
+    openidx = [(1, 1)] + [(i, 2) for i in range(2, M + 1)]
     return tensors, contractions, openidx
 
 

@@ -447,11 +447,20 @@ int qtn_mps_apply_mpo(qtn_mps* m, const void* const* host_mpo_sites, const int64
     for (int i = 0; i + 1 < n; ++i) {
         const int64_t mm = lb[i] * 2, nn = rb[i], r = std::min(mm, nn);
         SvdJob job{(double2*)fat[i].p, mm, nn, (double2*)U.p, (double*)S.p, (double2*)Vh.p};
+        const bool u_only = mm >= nn;  // carry = diag(S) V' = U^H M exactly: V is never accumulated
+        if (u_only) {
+            job.need_v = false;
+            CUDA_TRY(cudaMemcpyAsync(T.p, fat[i].p, (size_t)mm * nn * 16, cudaMemcpyDeviceToDevice, st));  // the Jacobi overwrites M
+        }
         int64_t k = 0;
         if ((rc = svd_batched_device(1, &job, -1.0, 0, &k, nullptr, nullptr))) return rc;
         // site i <- U (mm x r); C = diag(S) Vh (r x nn); site i+1 <- C * site_{i+1} (nn x 2 rb[i+1])
         if ((rc = scale_copy((double2*)U.p, mm, (double2*)fat[i].p, mm, mm, r, nullptr, 1))) return rc;
-        if ((rc = scale_copy((double2*)Vh.p, r, (double2*)C.p, r, r, nn, (double*)S.p, 0))) return rc;
+        if (u_only) {
+            if ((rc = qtn_zgemm_device('C', 'N', r, nn, mm, U.p, mm, T.p, mm, C.p, r))) return rc;
+        } else {
+            if ((rc = scale_copy((double2*)Vh.p, r, (double2*)C.p, r, r, nn, (double*)S.p, 0))) return rc;
+        }
         const int64_t ncols = 2 * rb[i + 1];
         if ((rc = qtn_zgemm_device('N', 'N', r, ncols, nn, C.p, r, fat[i + 1].p, nn, T.p, r))) return rc;
         CUDA_TRY(cudaMemcpyAsync(fat[i + 1].p, T.p, (size_t)r * ncols * 16, cudaMemcpyDeviceToDevice, st));

@@ -408,8 +408,24 @@ def main():
     il = q.contract_rep(net)
     arrays = [t.data for t in net.tensors]
     shapes = [a.shape for a in arrays]
-    S = q.choose_slices(shapes, il, None, args.max_log2, 1) if args.workload == "cfg3" else []
-    plan = q.ContractionPlan(shapes, il, None, S, precision=args.precision)
+    # slicing level: the largest one (<= --max-log2) whose arena fits the free HBM of this GPU
+    level = args.max_log2
+    while True:
+        S = q.choose_slices(shapes, il, None, level, 1) if args.workload == "cfg3" else []
+        plan = q.ContractionPlan(shapes, il, None, S, precision=args.precision)
+        free_b, _ = torch.cuda.mem_get_info()
+        if args.workload != "cfg3" or level <= 24 or plan.arena_bytes * (0.5 if args.precision == "c64" else 1.0) + (4 << 30) < free_b:
+            break
+        plan.close()
+        level -= 1
+    if world > 1:  # every rank must run the same slicing
+        lv = torch.tensor([level], device="cuda")
+        dist.all_reduce(lv, op=dist.ReduceOp.MIN)
+        if int(lv.item()) != level:
+            level = int(lv.item())
+            plan.close()
+            S = q.choose_slices(shapes, il, None, level, 1)
+            plan = q.ContractionPlan(shapes, il, None, S, precision=args.precision)
     sps = args.slices_per_step if plan.nslices > 1 else 1
     plan.upload(arrays)
     out = torch.zeros(2 * plan.out_numel, dtype=torch.float64 if args.precision == "c128" else torch.float32, device="cuda")

@@ -214,8 +214,14 @@ def test_cfg3_full_size_parity_chain(gpu):  # BASELINE config 3 at full size (se
     sub = sum(complex(p28.execute(None, sid31 + n31 * t, sid31 + n31 * t + 1)) for t in range(n28 // n31))
     p28.close()
     p31 = q.ContractionPlan(shapes, il, None, S[31])
-    got31 = complex(p31.execute(arrays, sid31, sid31 + 1))
-    p31.close()
+    try:
+        got31 = complex(p31.execute(arrays, sid31, sid31 + 1))
+    except q.QtnError as e:  # the 109 GB arena needs an otherwise idle B200
+        if e.code != -4:
+            raise
+        pytest.skip("not enough free HBM for the 2^31-level arena: %s" % e)
+    finally:
+        p31.close()
     assert abs(got31 - sub) < TOL * abs(sub)
 
 

@@ -9,12 +9,13 @@ import __graft_entry__ as graft  # noqa: E402
 q = graft.load_package()
 wl = sys.argv[1] if len(sys.argv) > 1 else "cfg3"
 max_log2 = int(sys.argv[2]) if len(sys.argv) > 2 else 28
+precision = sys.argv[3] if len(sys.argv) > 3 else "c128"
 net = (q.circuits.cfg3_network() if wl == "cfg3" else q.circuits.cfg2_network())[0]
 q.optimize_contraction_order(net)
 il = q.contract_rep(net)
 arrays = [t.data for t in net.tensors]
 S = q.choose_slices([a.shape for a in arrays], il, None, max_log2, 1) if wl == "cfg3" else []
-plan = q.ContractionPlan([a.shape for a in arrays], il, None, S)
+plan = q.ContractionPlan([a.shape for a in arrays], il, None, S, precision=precision)
 plan.upload(arrays)
 plan.time_steps(0)
 ms = plan.time_steps(1 if plan.nslices > 1 else 0)

@@ -13,17 +13,6 @@ namespace qtn {
 cudaStream_t stream();
 void count_launch(int64_t n);
 int permutedims_device(const void* in, int rank, const int64_t* dims, const int32_t* perm, void* out);
-struct SvdJob {
-    double2* A;
-    int64_t m0, n0;
-    double2* U;
-    double* S;
-    double2* Vh;
-    bool need_v = true;
-};
-int svd_batched_device(int batch, const SvdJob* jobs, double er, int64_t maxdim, int64_t* k_out, double* disc_out,
-                       int* sweeps_out);
-
 #define CUDA_TRY(expr)                                                                          \
     do {                                                                                        \
         cudaError_t _e = (expr);                                                                \

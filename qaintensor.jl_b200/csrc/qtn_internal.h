@@ -102,6 +102,20 @@ int materialize_tables(Plan* p);
 OffTable make_table(std::vector<int64_t>& tables, const std::vector<int64_t>& extents,
                     const std::vector<int64_t>& strides, int64_t max_lo);
 
+// ---- svd.cu --------------------------------------------------------------------
+// One SVD problem of a batch (device pointers; double2 = ComplexF64 as void* to keep this header CUDA-free).
+struct SvdJob {
+    void* A;       // m0 x n0, column-major, overwritten
+    int64_t m0, n0;
+    void* U;       // m0 x min(m0, n0)
+    double* S;     // min(m0, n0)
+    void* Vh;      // min(m0, n0) x n0 (ignored when !need_v)
+    bool need_v = true;  // false: sigma and U only (m0 >= n0); callers form S*Vh = U^H A themselves
+};
+// Runs the batch on the library stream and synchronises it; k_out / disc_out are host arrays.
+int svd_batched_device(int batch, const SvdJob* jobs, double er, int64_t maxdim, int64_t* k_out, double* disc_out,
+                       int* sweeps_out);
+
 // ---- exec.cu -------------------------------------------------------------------
 int device_ready();  // QTN_OK or QTN_ENODEVICE (with message)
 int plan_device_init(Plan* p);

@@ -544,15 +544,6 @@ static int work_reserve(size_t bytes, size_t hbytes) {
     return QTN_OK;
 }
 
-struct SvdJob {
-    double2* A;  // m0 x n0 device, overwritten
-    int64_t m0, n0;
-    double2* U;  // m0 x r
-    double* S;   // r
-    double2* Vh; // r x n0 (ignored when !need_v)
-    bool need_v = true;  // false: sigma and U only (m0 >= n0); callers form S*Vh = U^H A themselves
-};
-
 // Runs the batch; k_out / disc_out are host arrays (batch).  Synchronises the stream.
 int svd_batched_device(int batch, const SvdJob* jobs, double er, int64_t maxdim, int64_t* k_out, double* disc_out,
                        int* sweeps_out) {
@@ -604,7 +595,7 @@ int svd_batched_device(int batch, const SvdJob* jobs, double er, int64_t maxdim,
     for (int b = 0; b < batch; ++b) {
         const int64_t m0 = jobs[b].m0, n0 = jobs[b].n0;
         const int m = (int)(tr[b] ? n0 : m0), n = (int)(tr[b] ? m0 : n0);
-        hp[b].A = tr[b] ? (double2*)(base + offAt[b]) : jobs[b].A;
+        hp[b].A = tr[b] ? (double2*)(base + offAt[b]) : (double2*)jobs[b].A;
         hp[b].V = (jobs[b].need_v || tr[b]) ? (double2*)(base + offV[b]) : nullptr;
         hp[b].m = m;
         hp[b].n = n;
@@ -616,7 +607,7 @@ int svd_batched_device(int batch, const SvdJob* jobs, double er, int64_t maxdim,
         // last_mod = 1, last_ok = 0: every pair starts "modified after its last check"
         CUDA_TRY(cudaMemsetAsync(hp[b].last_ok, 0, (size_t)nbk * nbk * 4, st));
         set_int_kernel<<<(nbk + 255) / 256, 256, 0, st>>>(hp[b].last_mod, nbk, 1);
-        hf[b].U = jobs[b].U; hf[b].S = jobs[b].S; hf[b].Vh = jobs[b].Vh;
+        hf[b].U = (double2*)jobs[b].U; hf[b].S = jobs[b].S; hf[b].Vh = (double2*)jobs[b].Vh;
         hf[b].k = (int64_t*)dptr(hk + b);
         hf[b].disc = (double*)dptr(hdisc + b);
         hf[b].transposed = tr[b];
@@ -636,7 +627,7 @@ int svd_batched_device(int batch, const SvdJob* jobs, double er, int64_t maxdim,
     for (int b = 0; b < batch; ++b)
         if (tr[b]) {
             dim3 g((unsigned)((jobs[b].m0 + 31) / 32), (unsigned)((jobs[b].n0 + 31) / 32));
-            conj_transpose_kernel<<<g, dim3(32, 8), 0, st>>>(jobs[b].A, hp[b].A, (int)jobs[b].m0, (int)jobs[b].n0);
+            conj_transpose_kernel<<<g, dim3(32, 8), 0, st>>>((const double2*)jobs[b].A, hp[b].A, (int)jobs[b].m0, (int)jobs[b].n0);
             count_launch(1);
         }
     set_identity_kernel<<<dim3(std::min(148 * 4, (maxn * maxn + 255) / 256), batch), 256, 0, st>>>(dp);

@@ -200,9 +200,23 @@ def permutedims(a, perm):
     return out
 
 
-def contract(net, optimize=False, precision="c128"):
+def contract(net, optimize=False, precision="c128", max_log2_elems=None, min_slices=1, rank=0, nranks=1):
     """``contract(net::TensorNetwork, optimize::Bool=false)`` (src/contract.jl:242-264).
-    ``precision`` is an EXTENSION keyword with the reference-preserving default ComplexF64."""
+
+    EXTENSION keywords with reference-preserving defaults: ``precision`` ("c128" | "c64");
+    ``max_log2_elems`` slices the contraction until no tensor exceeds 2^k elements (deterministic greedy
+    rule) and, with ``nranks > 1`` (after ``qtn_nccl_init``), gives every rank a contiguous block of the
+    slices and sums the partial results with one NCCL allreduce."""
+    if max_log2_elems is not None and len(net.tensors) > 1 and not optimize:
+        il = contract_rep(net)
+        arrays = [t.data for t in net.tensors]
+        shapes = [a.shape for a in arrays]
+        S = choose_slices(shapes, il, None, max_log2_elems, min_slices)
+        plan = ContractionPlan(shapes, il, None, S, precision=precision)
+        try:
+            return plan.contract_sliced(arrays, rank, nranks)
+        finally:
+            plan.close()
     if len(net.tensors) == 1:
         out = permutedims(net.tensors[0].data, [l for (_, l) in net.openidx])
         return out.astype(np.complex64) if _lib.dtype_code(precision) == _lib.QTN_C64 else out

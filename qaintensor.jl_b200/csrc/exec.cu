@@ -484,7 +484,7 @@ int plan_execute(Plan* p, int64_t s0, int64_t s1, void* dev_out) {
         d->capture_events.clear();
         launch_count(1);
         count_launch(keep);
-        if (rc) return rc;
+        if (rc) { if (e == cudaSuccess) cudaGraphDestroy(graph); return rc; }
         if (e != cudaSuccess) return fail(QTN_ECUDA, "graph capture failed: %s", cudaGetErrorString(e));
         e = cudaGraphInstantiate(&d->graph, graph, 0);
         cudaGraphDestroy(graph);

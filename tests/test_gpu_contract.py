@@ -258,3 +258,12 @@ def test_random_general_networks_numeric(gpu):  # mixed extents, open legs, self
             sp = q.ContractionPlan(shapes, il, None, S)
             assert rel_err(sp.execute(arrays), want) < TOL
             assert rel_err(q.ContractionPlan(shapes, il, None, S, precision="c64").execute(arrays), want) < 1e-4
+
+
+def test_contract_sliced_keyword(gpu):  # EXTENSION keyword on the reference's `contract`
+    q = gpu
+    net, _, _ = q.circuits.cfg2_network(14, 10, seed=2)
+    q.optimize_contraction_order(net)
+    want = complex(oc.contract(to_oracle(net)))
+    assert abs(complex(q.contract(net, max_log2_elems=6, min_slices=8)) - want) < TOL * abs(want)
+    assert abs(complex(q.contract(net, max_log2_elems=6, precision="c64")) - want) < 1e-4 * abs(want)

@@ -52,7 +52,8 @@ def tensor_circuit(psi, cgc, is_decompose=False):
                     psi.contractions.append(Summation([(nt - 1, c), (nt, 1)]))
                 psi.openidx[w - 1] = (nt, 1 if i == 1 else 2)
             continue
-        psi.tensors.append(Tensor(np.reshape(cg.matrix, (2,) * (2 * M), order="F")))
+        # column-major storage: the C ABI then takes the buffer as is (no per-call conversion copy)
+        psi.tensors.append(Tensor(np.asfortranarray(np.reshape(cg.matrix, (2,) * (2 * M), order="F"))))
         nt = len(psi.tensors)
         for i, w in enumerate(cg.iwire, 1):
             psi.contractions.append(Summation([psi.openidx[w - 1], (nt, i)]))

@@ -40,6 +40,8 @@ def parse():
                     help="slice until the largest tensor has <= 2^k elements (31: 2048 slices, 1.05x flop overhead, 109 GB arena)")
     ap.add_argument("--cpu-max-log2", type=int, default=26, help="slicing level of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--open-wires", type=int, default=0,
+                    help="cfg2 only: leave the first K output wires open -> 2^K amplitudes per contraction (SURVEY 8f item 2)")
     ap.add_argument("--precision", default="c128", choices=["c128", "c64"], help="c64 = optional ComplexF32 mode (cfg2/cfg3)")
     return ap.parse_args()
 
@@ -402,8 +404,22 @@ def main():
         net, _, _ = q.circuits.cfg3_network()
         name = "cfg3: 36-qubit 6x6 RQC, 16 cycles, single amplitude, reference treewidth order, sliced"
     else:
-        net, _, _ = q.circuits.cfg2_network()
+        net, gates2, bits2 = q.circuits.cfg2_network()
         name = "cfg2: 24-qubit brickwork depth 20, single amplitude, reference treewidth order"
+        if args.open_wires > 0:
+            import warnings
+            k = args.open_wires
+            full = q.circuits.amplitude_network(24, gates2, None)
+            keep = [full.openidx[w] for w in range(k)]
+            for w in range(k, 24):
+                v = np.zeros(2, dtype=np.complex128)
+                v[int(bits2[w])] = 1.0
+                full.tensors.append(q.Tensor(v))
+                full.contractions.append(q.Summation([full.openidx[w], (len(full.tensors), 1)]))
+            full.openidx = keep
+            net = full
+            name = "cfg2 batched: 24-qubit brickwork depth 20, 2^%d amplitudes per contraction (first %d wires open)" % (k, k)
+            warnings.simplefilter("ignore")
     q.optimize_contraction_order(net)
     il = q.contract_rep(net)
     arrays = [t.data for t in net.tensors]
@@ -460,7 +476,7 @@ def main():
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = float(ms.item())
     clocks = sampler.stop() if sampler else None
-    units = args.steps * world * sps / plan.nslices  # amplitudes completed
+    units = args.steps * world * sps / plan.nslices * plan.out_numel  # amplitudes completed
     value = units / (ms * 1e-3)
 
     # ---- end-to-end through the public host-buffer API (H2D + D2H inside the timed region) ----

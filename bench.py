@@ -34,7 +34,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg3", choices=["cfg3", "cfg2", "cfg4", "cfg5"])
     ap.add_argument("--chi", type=int, default=512, help="cfg4: max bond dimension")
-    ap.add_argument("--sites", type=int, default=50, help="cfg4: number of MPS sites")
+    ap.add_argument("--sites", type=int, default=None, help="number of MPS sites (default: cfg4 50, cfg5 40)")
     ap.add_argument("--slices-per-step", type=int, default=1)
     ap.add_argument("--max-log2", type=int, default=31,
                     help="slice until the largest tensor has <= 2^k elements (31: 2048 slices, 1.05x flop overhead, 109 GB arena)")
@@ -43,7 +43,10 @@ def parse():
     ap.add_argument("--open-wires", type=int, default=0,
                     help="cfg2 only: leave the first K output wires open -> 2^K amplitudes per contraction (SURVEY 8f item 2)")
     ap.add_argument("--precision", default="c128", choices=["c128", "c64"], help="c64 = optional ComplexF32 mode (cfg2/cfg3)")
-    return ap.parse_args()
+    args = ap.parse_args()
+    if args.sites is None:
+        args.sites = 40 if args.workload == "cfg5" else 50   # BASELINE.json configs 4 and 5
+    return args
 
 
 def peaks():

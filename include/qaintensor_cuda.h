@@ -206,13 +206,19 @@ int qtn_mps_from_vector(const void* host_psi, int32_t nsites, void* const* host_
 /* EXTENSION (SURVEY 8a iii/iv): site-tensor MPO with the layout of src/mpo.jl:66,
  * W_i = (bond_in, out, in, bond_out) = (dl[i], 2, 2, dr[i]), dl[0] = dr[n-1] = 1.
  * qtn_mps_apply_mpo: |psi> <- compress(MPO |psi>): site-wise apply (bonds multiply), a
- * left-to-right SVD sweep that orthogonalises, a right-to-left SVD sweep that truncates with
- * (er, maxdim).  disc_out[n-1] (may be NULL) = discarded 2-norm per bond of the second sweep.
+ * left-to-right gauge sweep that orthogonalises (CholeskyQR2 on the GEMM kernel, verified on the
+ * device; U-only Jacobi SVD when the site matrix is too ill-conditioned for it), a right-to-left
+ * SVD sweep that truncates with (er, maxdim).  disc_out[n-1] (may be NULL) = discarded 2-norm per bond of the second sweep.
  * qtn_mps_expect_mpo: <psi| MPO |psi> by left-environment contraction, result (re, im).  */
 int qtn_mps_apply_mpo(qtn_mps* mps, const void* const* host_mpo_sites, const int64_t* dl,
                       const int64_t* dr, double er, int64_t maxdim, double* disc_out);
 int qtn_mps_expect_mpo(const qtn_mps* mps, const void* const* host_mpo_sites, const int64_t* dl,
                        const int64_t* dr, double out[2]);
+/* EXTENSION: the gauge step of qtn_mps_apply_mpo on its own.  host_q (m x n, column-major) receives an
+ * orthonormal basis of the columns of host_a (m >= n >= 1; where the reference would keep U of
+ * `svd`, cf. src/mps.jl:63).  method_out (may be NULL): 1 = blocked CholeskyQR2, 2 = Jacobi SVD
+ * fallback (n < 128, a failed orthogonality check, or QTN_ORTH=jacobi in the environment).          */
+int qtn_orth_columns(const void* host_a, int64_t m, int64_t n, void* host_q, int32_t* method_out);
 
 #ifdef __cplusplus
 }

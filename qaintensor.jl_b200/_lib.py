@@ -83,6 +83,7 @@ _SIGS = {
     "qtn_mps_from_vector": [vp, i32, P(vp), P(i64)],
     "qtn_mps_apply_mpo": [vp, P(vp), P(i64), P(i64), f64, i64, P(f64)],
     "qtn_mps_expect_mpo": [vp, P(vp), P(i64), P(i64), P(f64)],
+    "qtn_orth_columns": [vp, i64, i64, vp, P(i32)],
 }
 for _name, _args in _SIGS.items():
     _f = getattr(lib, _name)

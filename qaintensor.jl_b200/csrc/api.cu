@@ -272,13 +272,19 @@ int qtn_permutedims(const void* host_in, int32_t rank, const int64_t* dims, cons
 }
 
 // ---- dense ZGEMM ---------------------------------------------------------------------
-int qtn_zgemm_device(char opa, char opb, int64_t m, int64_t n, int64_t k, const void* dev_a, int64_t lda,
-                     const void* dev_b, int64_t ldb, void* dev_c, int64_t ldc) {
-    int rc = device_ready();
-    if (rc) return rc;
+}  // extern "C"
+
+namespace qtn {
+// C (+)= op(A) op(B) on the library stream with the contraction GEMM kernel in linear-stride mode.
+int zgemm_dense(char opa, char opb, int64_t m, int64_t n, int64_t k, const void* dev_a, int64_t lda, const void* dev_b,
+                int64_t ldb, void* dev_c, int64_t ldc, bool accumulate) {
     auto ok = [](char c) { return c == 'N' || c == 'T' || c == 'C'; };
-    if (!ok(opa) || !ok(opb)) return fail(QTN_EINVAL, "qtn_zgemm_device: op must be N, T or C");
+    if (!ok(opa) || !ok(opb)) return fail(QTN_EINVAL, "zgemm: op must be N, T or C");
     if (m <= 0 || n <= 0) return QTN_OK;
+    if (k <= 0) {
+        if (!accumulate) CUDA_TRY(cudaMemset2DAsync(dev_c, (size_t)ldc * 16, 0, (size_t)m * 16, (size_t)n, stream()));
+        return QTN_OK;
+    }
     GemmArgs g;
     memset(&g, 0, sizeof(g));
     g.A = dev_a;
@@ -295,9 +301,17 @@ int qtn_zgemm_device(char opa, char opb, int64_t m, int64_t n, int64_t k, const 
     g.conj_a = opa == 'C';
     g.conj_b = opb == 'C';
     g.M = m; g.N = n; g.K = k;
-    g.mode = 0;
-    if (k <= 0) { CUDA_TRY(cudaMemset2DAsync(dev_c, (size_t)ldc * 16, 0, (size_t)m * 16, (size_t)n, stream())); return QTN_OK; }
+    g.mode = accumulate ? 1 : 0;
     return launch_gemm(g, n <= 16 ? 1 : 0, 1, stream());
+}
+}  // namespace qtn
+
+extern "C" {
+int qtn_zgemm_device(char opa, char opb, int64_t m, int64_t n, int64_t k, const void* dev_a, int64_t lda,
+                     const void* dev_b, int64_t ldb, void* dev_c, int64_t ldc) {
+    int rc = device_ready();
+    if (rc) return rc;
+    return zgemm_dense(opa, opb, m, n, k, dev_a, lda, dev_b, ldb, dev_c, ldc, false);
 }
 
 }  // extern "C"

@@ -115,6 +115,31 @@ struct DevBuf {
     ~DevBuf() { if (p) cudaFree(p); }
 };
 
+
+// M (mm x nn, mm >= nn, device) <- an orthonormal basis Q of its columns; keep <- the original M;
+// carry (nn x nn) <- Q^H M, so that Q * carry = M.  A gauge sweep needs no singular values: CholeskyQR2 (GEMM
+// work) when the matrix is large enough to pay, the U-only Jacobi SVD when its checks fail or QTN_ORTH=jacobi
+// is set (A/B runs).  u_scratch: mm x nn elements, s_scratch: nn doubles.  *method: 1 CholeskyQR2, 2 Jacobi.
+static int orth_columns(void* M, void* keep, void* carry, int64_t mm, int64_t nn, void* u_scratch, double* s_scratch, int* method) {
+    cudaStream_t st = stream();
+    int rc;
+    CUDA_TRY(cudaMemcpyAsync(keep, M, (size_t)mm * nn * 16, cudaMemcpyDeviceToDevice, st));
+    const char* env = getenv("QTN_ORTH");
+    bool done = false;
+    if (nn >= 128 && !(env && strcmp(env, "jacobi") == 0)) {
+        if ((rc = orth_cholqr2(M, keep, carry, mm, nn, &done))) return rc;
+        if (!done) CUDA_TRY(cudaMemcpyAsync(M, keep, (size_t)mm * nn * 16, cudaMemcpyDeviceToDevice, st));
+    }
+    if (method) *method = done ? 1 : 2;
+    if (done) return QTN_OK;
+    SvdJob job{M, mm, nn, u_scratch, s_scratch, nullptr};
+    job.need_v = false;
+    int64_t k = 0;
+    if ((rc = svd_batched_device(1, &job, -1.0, 0, &k, nullptr, nullptr))) return rc;
+    if ((rc = scale_copy((const double2*)u_scratch, mm, (double2*)M, mm, mm, nn, nullptr, 1))) return rc;
+    return zgemm_dense('C', 'N', nn, nn, mm, M, mm, keep, mm, carry, nn, false);
+}
+
 }  // namespace qtn
 
 using namespace qtn;
@@ -435,21 +460,17 @@ int qtn_mps_apply_mpo(qtn_mps* m, const void* const* host_mpo_sites, const int64
         return rc;
     for (int i = 0; i + 1 < n; ++i) {
         const int64_t mm = lb[i] * 2, nn = rb[i], r = std::min(mm, nn);
-        SvdJob job{(double2*)fat[i].p, mm, nn, (double2*)U.p, (double*)S.p, (double2*)Vh.p};
         const bool u_only = mm >= nn;  // carry = diag(S) V' = U^H M exactly: V is never accumulated
         if (u_only) {
-            job.need_v = false;
-            CUDA_TRY(cudaMemcpyAsync(T.p, fat[i].p, (size_t)mm * nn * 16, cudaMemcpyDeviceToDevice, st));  // the Jacobi overwrites M
-        }
-        int64_t k = 0;
-        if ((rc = svd_batched_device(1, &job, -1.0, 0, &k, nullptr, nullptr))) return rc;
-        // site i <- U (mm x r); C = diag(S) Vh (r x nn); site i+1 <- C * site_{i+1} (nn x 2 rb[i+1])
-        if ((rc = scale_copy((double2*)U.p, mm, (double2*)fat[i].p, mm, mm, r, nullptr, 1))) return rc;
-        if (u_only) {
-            if ((rc = qtn_zgemm_device('C', 'N', r, nn, mm, U.p, mm, T.p, mm, C.p, r))) return rc;
+            if ((rc = orth_columns(fat[i].p, T.p, C.p, mm, nn, U.p, (double*)S.p, nullptr))) return rc;
         } else {
-            if ((rc = scale_copy((double2*)Vh.p, r, (double2*)C.p, r, r, nn, (double*)S.p, 0))) return rc;
+            SvdJob job{(double2*)fat[i].p, mm, nn, (double2*)U.p, (double*)S.p, (double2*)Vh.p};
+            int64_t k = 0;
+            if ((rc = svd_batched_device(1, &job, -1.0, 0, &k, nullptr, nullptr))) return rc;
+            if ((rc = scale_copy((double2*)U.p, mm, (double2*)fat[i].p, mm, mm, r, nullptr, 1))) return rc;  // site i <- U
         }
+        // C = carry (r x nn): Q^H M, or diag(S) Vh after the full SVD; site i+1 <- C * site_{i+1} (nn x 2 rb[i+1])
+        if (!u_only && (rc = scale_copy((double2*)Vh.p, r, (double2*)C.p, r, r, nn, (double*)S.p, 0))) return rc;
         const int64_t ncols = 2 * rb[i + 1];
         if ((rc = qtn_zgemm_device('N', 'N', r, ncols, nn, C.p, r, fat[i + 1].p, nn, T.p, r))) return rc;
         CUDA_TRY(cudaMemcpyAsync(fat[i + 1].p, T.p, (size_t)r * ncols * 16, cudaMemcpyDeviceToDevice, st));
@@ -480,6 +501,27 @@ int qtn_mps_apply_mpo(qtn_mps* m, const void* const* host_mpo_sites, const int64
     m->lb[0] = lb[0];
     m->rb[0] = rb[0];
     CUDA_TRY(cudaStreamSynchronize(st));
+    return QTN_OK;
+}
+
+// EXTENSION: orthonormal basis of the columns of a host matrix (m >= n); the gauge step of qtn_mps_apply_mpo.
+int qtn_orth_columns(const void* host_a, int64_t m, int64_t n, void* host_q, int32_t* method_out) {
+    if (!host_a || !host_q) return fail(QTN_EINVAL, "qtn_orth_columns: null argument");
+    if (n < 1 || m < n) return fail(QTN_EINVAL, "qtn_orth_columns: needs m >= n >= 1 (got %lld x %lld)", (long long)m, (long long)n);
+    int rc = device_ready();
+    if (rc) return rc;
+    DevBuf M, keep, U, S, carry;
+    const size_t bytes = (size_t)m * n * 16;
+    if ((rc = M.alloc(bytes)) || (rc = keep.alloc(bytes)) || (rc = U.alloc(bytes)) || (rc = S.alloc((size_t)n * 8)) ||
+        (rc = carry.alloc((size_t)n * n * 16)))
+        return rc;
+    cudaStream_t st = stream();
+    CUDA_TRY(cudaMemcpyAsync(M.p, host_a, bytes, cudaMemcpyHostToDevice, st));
+    int method = 0;
+    if ((rc = orth_columns(M.p, keep.p, carry.p, m, n, U.p, (double*)S.p, &method))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(host_q, M.p, bytes, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (method_out) *method_out = method;
     return QTN_OK;
 }
 

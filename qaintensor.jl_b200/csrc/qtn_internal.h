@@ -116,6 +116,15 @@ struct SvdJob {
 int svd_batched_device(int batch, const SvdJob* jobs, double er, int64_t maxdim, int64_t* k_out, double* disc_out,
                        int* sweeps_out);
 
+// ---- api.cu / orth.cu ----------------------------------------------------------
+// C (+)= op(A) op(B), dense column-major ComplexF64 device matrices, on the library stream.
+int zgemm_dense(char opa, char opb, int64_t m, int64_t n, int64_t k, const void* dev_a, int64_t lda, const void* dev_b,
+                int64_t ldb, void* dev_c, int64_t ldc, bool accumulate);
+// Orthonormalises the columns of the m x n (m >= n) device matrix M (ld = m) in place by blocked CholeskyQR2;
+// dev_keep holds an untouched copy of M, dev_c (n x n) receives Q^H M.  *ok = false (M and C are then garbage)
+// when M is too ill-conditioned for it: callers fall back to the Jacobi SVD.  Synchronises the library stream.
+int orth_cholqr2(void* dev_m, const void* dev_keep, void* dev_c, int64_t m, int64_t n, bool* ok);
+
 // ---- exec.cu -------------------------------------------------------------------
 int device_ready();  // QTN_OK or QTN_ENODEVICE (with message)
 int plan_device_init(Plan* p);

@@ -476,8 +476,12 @@ __global__ void sort_truncate_kernel(const SvdProblem* probs, double* const* sig
     }
 }
 
-// U[:, rank[j]] = a_j / sigma_j ; Vh[rank[j], :] = conj(V[:, j])   (roles swapped if transposed)
-__global__ void scatter_factors_kernel(const SvdProblem* probs, double* const* sig, int* const* rank, const FinishArgs* fin) {
+// U[:, rank[j]] = a_j / sigma_j ; Vh[rank[j], :] = conj(V[:, j])   (roles swapped if transposed).
+// U-only jobs (no V): callers form S*Vh = U^H A, so a deflated column (norm below the rotation threshold, never
+// orthogonalised against the others: pure rounding noise of a rank-deficient A) must not survive as a unit
+// vector -- it is written as zero, like an exactly zero column.
+__global__ void scatter_factors_kernel(const SvdProblem* probs, double* const* sig, int* const* rank, const FinishArgs* fin,
+                                       const double* __restrict__ fro2) {
     const SvdProblem pr = probs[blockIdx.y];
     const FinishArgs f = fin[blockIdx.y];
     const int n = pr.n, m = pr.m;
@@ -489,7 +493,8 @@ __global__ void scatter_factors_kernel(const SvdProblem* probs, double* const* s
         if (r < m) {
             const double sj = s[j];
             double2 v = pr.A[(size_t)j * m + r];
-            if (sj > 0) { v.x /= sj; v.y /= sj; } else { v = make_double2(0, 0); }
+            const bool dead = !pr.V && sj * sj <= 4e-30 * fro2[blockIdx.y];
+            if (sj > 0 && !dead) { v.x /= sj; v.y /= sj; } else { v = make_double2(0, 0); }
             if (!f.transposed) f.U[(size_t)dst * m + r] = v;              // U is m x n
             else f.Vh[(size_t)r * n + dst] = make_double2(v.x, -v.y);     // Vh (n x m0=m) row dst = conj(column)
         } else {
@@ -694,7 +699,7 @@ int svd_batched_device(int batch, const SvdJob* jobs, double er, int64_t maxdim,
     }
     column_norms_kernel<<<dim3(std::min(148 * 2, (maxn + 7) / 8), batch), 256, 0, st>>>(dp, dsig);
     sort_truncate_kernel<<<batch, 256, 0, st>>>(dp, dsig, drank, df, er, (long long)maxdim);
-    scatter_factors_kernel<<<dim3(148 * 2, batch), 256, 0, st>>>(dp, dsig, drank, df);
+    scatter_factors_kernel<<<dim3(148 * 2, batch), 256, 0, st>>>(dp, dsig, drank, df, (const double*)dfro);
     count_launch(3);
     CUDA_TRY(cudaMemcpyAsync(hk, dptr(hk), (size_t)batch * 16, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));

@@ -51,3 +51,18 @@ def contract_svd(T1, T2, indx, er=0.0):
                                b.ctypes.data_as(C.c_void_p), b.ndim, arr_i64(b.shape), i2, float(er),
                                out.ctypes.data_as(C.c_void_p)))
     return Tensor(out)
+
+
+def orth_columns(A):
+    """EXTENSION: orthonormal basis Q of the columns of a tall matrix (the gauge step of the MPO x MPS
+    compression, where the reference would keep ``U`` of ``svd``).  Returns (Q, method) with method
+    1 = blocked CholeskyQR2, 2 = Jacobi SVD fallback."""
+    _lib.require_device()
+    A = as_c128(A)
+    if A.ndim != 2 or A.shape[0] < A.shape[1] or A.shape[1] < 1:
+        raise ValueError("orth_columns expects an m x n matrix with m >= n >= 1")
+    m, n = A.shape
+    Q = np.zeros((m, n), dtype=np.complex128, order="F")
+    method = C.c_int32(0)
+    check(lib.qtn_orth_columns(A.ctypes.data_as(C.c_void_p), m, n, Q.ctypes.data_as(C.c_void_p), C.byref(method)))
+    return Q, int(method.value)

@@ -18,6 +18,12 @@ from oracle import svd as osvd
 pytestmark = pytest.mark.gpu
 
 
+def sys_svd(q):
+    """The ``svd`` submodule (the package attribute of that name is the function)."""
+    import sys
+    return sys.modules[q.__name__ + ".svd"]
+
+
 def crand(rng, *s):
     return rng.standard_normal(s) + 1j * rng.standard_normal(s)
 
@@ -320,3 +326,104 @@ def test_mpo_apply_compress_truncated_vs_oracle(gpu):  # fidelity 1e-9, bonds an
     assert abs(abs(osim.overlap(got, ref)) ** 2 / (ng * nr) - 1) < 1e-9 and abs(ng / nr - 1) < 1e-9
     e_gpu, e_ref = mps.expect_mpo(mpo), osim.expect_mpo(ref, mpo)
     assert abs(e_gpu - e_ref) < 1e-9 * abs(e_ref)
+
+
+@pytest.mark.parametrize("shape", [(300, 200), (700, 333), (1024, 512), (128, 128)])
+def test_orth_columns_cholqr2(gpu, shape):  # EXTENSION: gauge step of the MPO x MPS compression
+    q = gpu
+    m, n = shape
+    A = crand(np.random.default_rng(m + n), m, n)
+    Q, method = sys_svd(q).orth_columns(A)
+    assert method == 1
+    assert np.abs(Q.conj().T @ Q - np.eye(n)).max() < 1e-12
+    assert np.abs(Q @ (Q.conj().T @ A) - A).max() < 1e-12 * np.abs(A).max() * n
+
+
+def test_orth_columns_fallbacks(gpu):
+    q = gpu
+    rng = np.random.default_rng(5)
+    m, n = 400, 160
+    U = np.linalg.qr(crand(rng, m, n))[0]
+    V = np.linalg.qr(crand(rng, n, n))[0]
+    ill = (U * np.logspace(0, -13, n)) @ V.conj().T          # cond 1e13: CholeskyQR2 must refuse
+    Q, method = sys_svd(q).orth_columns(ill)
+    assert method == 2
+    assert np.abs(Q @ (Q.conj().T @ ill) - ill).max() < 1e-12
+    deficient = crand(rng, m, 40) @ crand(rng, 40, n)        # rank 40 < n
+    Q, method = sys_svd(q).orth_columns(deficient)
+    assert method == 2
+    assert np.abs(Q @ (Q.conj().T @ deficient) - deficient).max() < 1e-11 * np.abs(deficient).max()
+    small = crand(rng, 90, 60)                               # below the block size that pays
+    Q, method = sys_svd(q).orth_columns(small)
+    assert method == 2 and np.abs(Q.conj().T @ Q - np.eye(60)).max() < 1e-12
+    moderately_ill = (U * np.logspace(0, -6, n)) @ V.conj().T  # cond 1e6: still inside CholeskyQR2's range
+    Q, method = sys_svd(q).orth_columns(moderately_ill)
+    assert method == 1 and np.abs(Q.conj().T @ Q - np.eye(n)).max() < 1e-12
+
+
+def test_mpo_apply_compress_wide_bonds_vs_oracle(gpu):  # fat bonds >= 128: the CholeskyQR2 gauge sweep runs
+    q = gpu
+    rng = np.random.default_rng(21)
+    n, chi = 14, 48
+    bonds = [min(2 ** min(i, n - i), chi) for i in range(n + 1)]
+    sites = random_open_mps(rng, bonds)
+    mpo = q.tfi_mpo(n, 1.0, 0.8)
+    ref = [s.copy() for s in sites]
+    d_ref = osim.apply_mpo_compress(ref, mpo, 1e-10, chi)
+    mps = q.DeviceMPS(sites, chi)
+    d_gpu = mps.apply_mpo(mpo, er=1e-10, maxdim=chi)
+    got = mps.download()
+    assert [g.shape for g in got] == [r.shape for r in ref]
+    assert np.abs(np.array(d_gpu) - np.array(d_ref)).max() < 1e-9 * max(1.0, max(d_ref))
+    ng, nr = osim.overlap(got, got).real, osim.overlap(ref, ref).real
+    assert abs(abs(osim.overlap(got, ref)) ** 2 / (ng * nr) - 1) < 1e-9 and abs(ng / nr - 1) < 1e-9
+    e_gpu, e_ref = mps.expect_mpo(mpo), osim.expect_mpo(ref, mpo)
+    assert abs(e_gpu - e_ref) < 1e-9 * abs(e_ref)
+
+
+def inflate_bonds(rng, sites, pad):
+    """Same state on bonds of size ``pad``: site_i -> W_{i-1}^H site_i W_i with random isometries W (b x pad).
+    Every site matrix becomes dense and rank-deficient."""
+    n = len(sites)
+    out, Wl = [], np.ones((1, 1))
+    for i, s in enumerate(sites):
+        r = s.shape[2]
+        Wr = np.ones((1, 1)) if i == n - 1 else np.linalg.qr(crand(rng, pad, r))[0].conj().T   # r x pad, W W^H = I
+        out.append(np.einsum("al,lpr,rb->apb", Wl.conj().T, s, Wr))
+        Wl = Wr
+    return out
+
+
+def test_mpo_apply_compress_rank_deficient_sites(gpu):  # every gauge-sweep matrix is rank-deficient (U-only SVD path)
+    q = gpu
+    rng = np.random.default_rng(33)
+    n, b, pad = 10, 6, 16
+    bonds = [min(2 ** min(i, n - i), b) for i in range(n + 1)]
+    sites = random_open_mps(rng, bonds)
+    fat = inflate_bonds(rng, sites, pad)
+    assert rel_err(osim.to_vector(fat), osim.to_vector(sites)) < 1e-13
+    mpo = q.tfi_mpo(n, 1.0, 0.6)
+    ref = [s.copy() for s in sites]
+    osim.apply_mpo_compress(ref, mpo, 1e-12, None)
+    want = osim.to_vector(ref)
+    mps = q.DeviceMPS(fat, 3 * pad)
+    mps.apply_mpo(mpo, er=1e-12, maxdim=0)
+    got = osim.to_vector(mps.download())
+    assert rel_err(got, want) < 1e-9
+
+
+def test_device_mps_layer_rank_deficient_sites(gpu):  # U-only gate SVDs on rank-deficient theta, er = 0 keeps noise columns
+    q = gpu
+    rng = np.random.default_rng(34)
+    n, b, pad = 8, 4, 12
+    bonds = [min(2 ** min(i, n - i), b) for i in range(n + 1)]
+    sites = random_open_mps(rng, bonds)
+    fat = inflate_bonds(rng, sites, pad)
+    ref = [s.copy() for s in sites]
+    mps = q.DeviceMPS(fat, 2 * pad)
+    for layer in range(2):
+        where = list(range(1 + layer % 2, n, 2))
+        gates = [np.linalg.qr(crand(rng, 4, 4))[0] for _ in where]
+        osim.apply_layer(ref, where, gates, 0.0, None)
+        mps.apply_layer(where, gates, er=0.0, maxdim=0)
+    assert rel_err(osim.to_vector(mps.download()), osim.to_vector(ref)) < 1e-10

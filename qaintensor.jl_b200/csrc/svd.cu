@@ -416,6 +416,10 @@ __global__ void set_identity_kernel(const SvdProblem* probs) {
         pr.V[e] = make_double2((e % pr.n) == (e / pr.n) ? 1.0 : 0.0, 0.0);
 }
 
+// Columns with ||a_j||^2 <= kDeadFactor * ||A||_F^2 were deflated by the rotation kernel (threshold 1e-30, with
+// slack for the recomputed norm).
+constexpr double kDeadFactor = 4e-30;
+
 // sigma_j = ||a_j||  (one warp per column)
 __global__ void column_norms_kernel(const SvdProblem* probs, double* const* sig) {
     const SvdProblem pr = probs[blockIdx.y];
@@ -441,8 +445,11 @@ struct FinishArgs {
 };
 
 // rank[j] = position of sigma_j in descending order (stable); S sorted; truncation rule (K6).
+// dead[b] = number of columns at or below the deflation threshold (never orthogonalised: their direction is
+// rounding noise); they sort last and are replaced by an orthonormal completion afterwards.
 __global__ void sort_truncate_kernel(const SvdProblem* probs, double* const* sig, int* const* rank,
-                                     const FinishArgs* fin, double er, long long maxdim) {
+                                     const FinishArgs* fin, double er, long long maxdim, const double* __restrict__ fro2,
+                                     int* __restrict__ dead) {
     const SvdProblem pr = probs[blockIdx.x];
     const FinishArgs f = fin[blockIdx.x];
     const double* s = sig[blockIdx.x];
@@ -473,13 +480,18 @@ __global__ void sort_truncate_kernel(const SvdProblem* probs, double* const* sig
         for (int j = n - 1; j >= (int)k; --j) d += f.S[j] * f.S[j];
         *f.k = k;
         if (f.disc) *f.disc = sqrt(d);
+        int nd = 0;
+        const double thr = kDeadFactor * fro2[blockIdx.x];
+        for (int j = n - 1; j >= 0 && f.S[j] * f.S[j] <= thr; --j) ++nd;
+        dead[blockIdx.x] = nd;
     }
 }
 
 // U[:, rank[j]] = a_j / sigma_j ; Vh[rank[j], :] = conj(V[:, j])   (roles swapped if transposed).
-// U-only jobs (no V): callers form S*Vh = U^H A, so a deflated column (norm below the rotation threshold, never
-// orthogonalised against the others: pure rounding noise of a rank-deficient A) must not survive as a unit
-// vector -- it is written as zero, like an exactly zero column.
+// A deflated column (norm below the rotation threshold, never orthogonalised against the others: pure rounding
+// noise of a rank-deficient A) must not survive as a unit vector -- callers that form S*Vh = U^H A would pick up
+// a direction that is not orthogonal to the rest.  It is written as zero here and replaced by an orthonormal
+// completion (complete_null_vectors) afterwards, so the factor is an isometry like LAPACK's.
 __global__ void scatter_factors_kernel(const SvdProblem* probs, double* const* sig, int* const* rank, const FinishArgs* fin,
                                        const double* __restrict__ fro2) {
     const SvdProblem pr = probs[blockIdx.y];
@@ -493,7 +505,7 @@ __global__ void scatter_factors_kernel(const SvdProblem* probs, double* const* s
         if (r < m) {
             const double sj = s[j];
             double2 v = pr.A[(size_t)j * m + r];
-            const bool dead = !pr.V && sj * sj <= 4e-30 * fro2[blockIdx.y];
+            const bool dead = sj * sj <= kDeadFactor * fro2[blockIdx.y];
             if (sj > 0 && !dead) { v.x /= sj; v.y /= sj; } else { v = make_double2(0, 0); }
             if (!f.transposed) f.U[(size_t)dst * m + r] = v;              // U is m x n
             else f.Vh[(size_t)r * n + dst] = make_double2(v.x, -v.y);     // Vh (n x m0=m) row dst = conj(column)
@@ -520,6 +532,80 @@ __global__ void conj_transpose_kernel(const double2* __restrict__ A, double2* __
         const int r = by + threadIdx.x, c = bx + j;  // B[r, c] = conj(A[c, r])
         if (r < n && c < m) { const double2 v = t[threadIdx.x][j]; B[(size_t)c * n + r] = make_double2(v.x, -v.y); }
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// orthonormal completion of the null vectors of a rank-deficient problem
+// ---------------------------------------------------------------------------------------------
+// D[i] = pseudo-random in [-1, 1)^2 (splitmix64 of the index: reproducible, no state)
+__global__ void fill_random_kernel(double2* __restrict__ D, int64_t n) {
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+        unsigned long long z = (unsigned long long)e * 0x9E3779B97F4A7C15ull + 0xD1B54A32D192ED03ull;
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        z ^= z >> 31;
+        const double a = (double)(z >> 32) * (1.0 / 2147483648.0) - 1.0, b = (double)(z & 0xffffffffull) * (1.0 / 2147483648.0) - 1.0;
+        D[e] = make_double2(a, b);
+    }
+}
+__global__ void negate_kernel(double2* __restrict__ P, int64_t n) {
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+        const double2 v = P[e];
+        P[e] = make_double2(-v.x, -v.y);
+    }
+}
+// Vh[row0 + j, c] = conj(D[c, j])  (D: len x d column-major; Vh: leading dimension ld)
+__global__ void store_conj_rows_kernel(const double2* __restrict__ D, int64_t len, int64_t d, double2* __restrict__ Vh, int64_t ld, int64_t row0) {
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < len * d; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t c = e % len, j = e / len;
+        const double2 v = D[e];
+        Vh[c * ld + row0 + j] = make_double2(v.x, -v.y);
+    }
+}
+
+// The factor built from the normalised Jacobi columns (U, or the rows of Vh when the Jacobi ran on A^H) has `dead`
+// zeroed vectors in its last positions.  Replace them: random block, projected twice against the good vectors
+// (GEMMs), orthonormalised by CholeskyQR2.  Any orthonormal completion is a valid SVD factor (LAPACK's is as
+// arbitrary); the singular values of those positions stay at their (noise-level) computed values.
+static int complete_null_vectors(const SvdJob& job, bool transposed, int dead) {
+    cudaStream_t st = stream();
+    const int64_t r = std::min(job.m0, job.n0), len = transposed ? job.n0 : job.m0, g = r - dead, d = dead;
+    struct Buf {
+        void* p = nullptr;
+        ~Buf() { if (p) cudaFree(p); }
+    } D, keep, P, C;
+    if (cudaMalloc(&D.p, (size_t)len * d * 16) != cudaSuccess || cudaMalloc(&keep.p, (size_t)len * d * 16) != cudaSuccess ||
+        cudaMalloc(&P.p, (size_t)std::max<int64_t>(g, 1) * d * 16) != cudaSuccess || cudaMalloc(&C.p, (size_t)d * d * 16) != cudaSuccess)
+        return fail(QTN_ENOMEM, "svd: null-space completion workspace");
+    auto grid = [](int64_t n) { return (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, 148 * 8)); };
+    fill_random_kernel<<<grid(len * d), 256, 0, st>>>((double2*)D.p, len * d);
+    count_launch(1);
+    int rc;
+    for (int pass = 0; pass < 2 && g > 0; ++pass) {
+        if (!transposed) {  // good vectors: columns of U (len x g, ld len)
+            if ((rc = zgemm_dense('C', 'N', g, d, len, job.U, len, D.p, len, P.p, g, false))) return rc;
+            negate_kernel<<<grid(g * d), 256, 0, st>>>((double2*)P.p, g * d);
+            if ((rc = zgemm_dense('N', 'N', len, d, g, job.U, len, P.p, g, D.p, len, true))) return rc;
+        } else {            // good vectors: conj of the rows of Vh (g x len, ld r)
+            if ((rc = zgemm_dense('N', 'N', g, d, len, job.Vh, r, D.p, len, P.p, g, false))) return rc;
+            negate_kernel<<<grid(g * d), 256, 0, st>>>((double2*)P.p, g * d);
+            if ((rc = zgemm_dense('C', 'N', len, d, g, job.Vh, r, P.p, g, D.p, len, true))) return rc;
+        }
+        count_launch(1);
+    }
+    CUDA_TRY(cudaMemcpyAsync(keep.p, D.p, (size_t)len * d * 16, cudaMemcpyDeviceToDevice, st));
+    bool ok = false;
+    if ((rc = orth_cholqr2(D.p, keep.p, C.p, len, d, &ok))) return rc;
+    if (!ok) return fail(QTN_ECUDA, "svd: orthonormal completion of %d null vectors failed", dead);
+    if (!transposed) {
+        CUDA_TRY(cudaMemcpyAsync((double2*)job.U + (size_t)g * len, D.p, (size_t)len * d * 16, cudaMemcpyDeviceToDevice, st));
+    } else {
+        store_conj_rows_kernel<<<grid(len * d), 256, 0, st>>>((const double2*)D.p, len, d, (double2*)job.Vh, r, g);
+        count_launch(1);
+    }
+    CUDA_TRY(cudaStreamSynchronize(st));
+    CUDA_TRY(cudaGetLastError());
+    return QTN_OK;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -579,7 +665,7 @@ int svd_batched_device(int batch, const SvdJob* jobs, double er, int64_t maxdim,
         maxm = std::max<int>(maxm, (int)m);
     }
     size_t tab = dev_bytes;
-    size_t tab_bytes = (size_t)batch * (sizeof(SvdProblem) + sizeof(FinishArgs) + 2 * sizeof(void*) + 8 + 8 + 8 + 4) + 1024;
+    size_t tab_bytes = (size_t)batch * (sizeof(SvdProblem) + sizeof(FinishArgs) + 2 * sizeof(void*) + 8 + 8 + 8 + 4 + 4) + 1024;
     dev_bytes += (tab_bytes + 255) / 256 * 256;
     int rc = work_reserve(dev_bytes, tab_bytes);
     if (rc) return rc;
@@ -595,6 +681,7 @@ int svd_batched_device(int batch, const SvdJob* jobs, double er, int64_t maxdim,
     double* hdisc = (double*)(hk + batch);
     double* hfro = hdisc + batch;
     int* hrot = (int*)(hfro + batch);
+    int* hdead = hrot + batch;
     char* dtab = base + tab;
     auto dptr = [&](void* hostp) { return dtab + ((char*)hostp - h); };
     for (int b = 0; b < batch; ++b) {
@@ -620,6 +707,7 @@ int svd_batched_device(int batch, const SvdJob* jobs, double er, int64_t maxdim,
         hsig[b] = (double*)(base + offSig[b]);
         hrank[b] = (int*)(base + offRank[b]);
         hrot[b] = 0;
+        hdead[b] = 0;
         hfro[b] = 0.0;
     }
     CUDA_TRY(cudaMemcpyAsync(dtab, h, tab_bytes - 1024, cudaMemcpyHostToDevice, st));
@@ -698,16 +786,22 @@ int svd_batched_device(int batch, const SvdJob* jobs, double er, int64_t maxdim,
         cudaFree(dstat);
     }
     column_norms_kernel<<<dim3(std::min(148 * 2, (maxn + 7) / 8), batch), 256, 0, st>>>(dp, dsig);
-    sort_truncate_kernel<<<batch, 256, 0, st>>>(dp, dsig, drank, df, er, (long long)maxdim);
+    sort_truncate_kernel<<<batch, 256, 0, st>>>(dp, dsig, drank, df, er, (long long)maxdim, (const double*)dfro, (int*)dptr(hdead));
     scatter_factors_kernel<<<dim3(148 * 2, batch), 256, 0, st>>>(dp, dsig, drank, df, (const double*)dfro);
     count_launch(3);
     CUDA_TRY(cudaMemcpyAsync(hk, dptr(hk), (size_t)batch * 16, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(hdead, dptr(hdead), (size_t)batch * 4, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     CUDA_TRY(cudaGetLastError());
     for (int b = 0; b < batch; ++b) {
         if (k_out) k_out[b] = hk[b];
         if (disc_out) disc_out[b] = hdisc[b];
     }
+    // rank-deficient inputs (rare path): the zeroed null vectors become an orthonormal completion.  The pinned
+    // table image is not touched by the GEMMs below, but copy what is needed first: orth_cholqr2 may not reuse it.
+    std::vector<int> dead(hdead, hdead + batch);
+    for (int b = 0; b < batch; ++b)
+        if (dead[b] > 0 && (rc = complete_null_vectors(jobs[b], tr[b] != 0, dead[b]))) return rc;
     if (sweeps_out) *sweeps_out = sweeps;
     if (sweeps >= kMaxSweeps) return fail(QTN_ECUDA, "Jacobi SVD did not converge in %d sweeps", kMaxSweeps);
     return QTN_OK;

@@ -40,9 +40,9 @@ def check_svd(q, A, er=-1.0, maxdim=0, stol=1e-10):
     assert k == kref
     rec = (U * S) @ Vh
     assert np.abs(rec - A).max() <= 1e-12 * scale * max(A.shape)
-    r = int(np.sum(Sref > 1e-12 * scale))
-    assert np.abs(U[:, :r].conj().T @ U[:, :r] - np.eye(r)).max() < 1e-11
-    assert np.abs(Vh[:r] @ Vh[:r].conj().T - np.eye(r)).max() < 1e-11
+    r = len(Sref)   # both factors are isometries even when A is rank-deficient (null vectors completed, like LAPACK)
+    assert np.abs(U.conj().T @ U - np.eye(r)).max() < 1e-11
+    assert np.abs(Vh @ Vh.conj().T - np.eye(r)).max() < 1e-11
     return U, S, Vh, k
 
 

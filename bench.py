@@ -42,6 +42,11 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--open-wires", type=int, default=0,
                     help="cfg2 only: leave the first K output wires open -> 2^K amplitudes per contraction (SURVEY 8f item 2)")
+    ap.add_argument("--order", default="reference", choices=["reference", "search"],
+                    help="reference = optimize_contraction_order! (treewidth heuristic, the default and the named config); "
+                         "search = EXTENSION qtn_order_search (randomised greedy + annealing), reported separately")
+    ap.add_argument("--search-trials", type=int, default=512)
+    ap.add_argument("--dump-steps", default=None, help="write the per-step (M, N, K, ms) table of one slice to this file")
     ap.add_argument("--precision", default="c128", choices=["c128", "c64"], help="c64 = optional ComplexF32 mode (cfg2/cfg3)")
     args = ap.parse_args()
     if args.sites is None:
@@ -423,15 +428,27 @@ def main():
             net = full
             name = "cfg2 batched: 24-qubit brickwork depth 20, 2^%d amplitudes per contraction (first %d wires open)" % (k, k)
             warnings.simplefilter("ignore")
-    q.optimize_contraction_order(net)
-    il = q.contract_rep(net)
     arrays = [t.data for t in net.tensors]
     shapes = [a.shape for a in arrays]
+    search_info = None
+    if args.order == "reference":
+        q.optimize_contraction_order(net)
+    else:
+        name = name.replace("reference treewidth order", "EXTENSION searched order (qtn_order_search, %d trials)" % args.search_trials)
+    il = q.contract_rep(net)
+
+    def make_plan(level):
+        order = None
+        if args.order == "search":  # the search is slicing-aware, so it is repeated per memory target
+            nonlocal search_info
+            order, search_info = q.search_order(shapes, il, args.search_trials, 0, level if args.workload == "cfg3" else -1)
+        S_ = q.choose_slices(shapes, il, order, level, 1) if args.workload == "cfg3" else []
+        return S_, q.ContractionPlan(shapes, il, order, S_, precision=args.precision)
+
     # slicing level: the largest one (<= --max-log2) whose arena fits the free HBM of this GPU
     level = args.max_log2
     while True:
-        S = q.choose_slices(shapes, il, None, level, 1) if args.workload == "cfg3" else []
-        plan = q.ContractionPlan(shapes, il, None, S, precision=args.precision)
+        S, plan = make_plan(level)
         free_b, _ = torch.cuda.mem_get_info()
         if args.workload != "cfg3" or level <= 24 or plan.arena_bytes * (0.5 if args.precision == "c64" else 1.0) + (4 << 30) < free_b:
             break
@@ -443,8 +460,7 @@ def main():
         if int(lv.item()) != level:
             level = int(lv.item())
             plan.close()
-            S = q.choose_slices(shapes, il, None, level, 1)
-            plan = q.ContractionPlan(shapes, il, None, S, precision=args.precision)
+            S, plan = make_plan(level)
     sps = args.slices_per_step if plan.nslices > 1 else 1
     plan.upload(arrays)
     out = torch.zeros(2 * plan.out_numel, dtype=torch.float64 if args.precision == "c128" else torch.float32, device="cuda")
@@ -501,6 +517,12 @@ def main():
         # ---- roofline of the dominant kernel: per-step CUDA-event durations of one slice ----
         step_ms = plan.time_steps(0)
         steps = plan.steps()
+        if args.dump_steps:
+            with open(args.dump_steps, "w") as f:
+                f.write("# step M N K invariant ms GFLOP/s GB/s(algorithmic)\n")
+                for i, ((M_, N_, K_, fl_), t_) in enumerate(zip(steps, step_ms)):
+                    f.write("%d %d %d %d %d %.4f %.1f %.1f\n" % (i, M_, N_, K_, fl_ & 1, t_, 8.0 * M_ * N_ * K_ / max(t_, 1e-6) / 1e6,
+                                                                16.0 * (M_ * K_ + K_ * N_ + M_ * N_) / max(t_, 1e-6) / 1e6))
         dom = max(range(len(steps)), key=lambda i: step_ms[i])
         M, N, K, _ = steps[dom]
         dom_flops = 8.0 * M * N * K
@@ -553,7 +575,8 @@ def main():
                                  if plan.arena_bytes > 2e8 else "working set fits L2 (latency-bound workload); no flush",
                            "value_definition": "(slices processed / slices per amplitude) / time; a full amplitude is "
                                                "%d slices" % plan.nslices,
-                           "parallelism": "slice-parallel x%d, one 16-byte ncclAllReduce per step" % world},
+                           "parallelism": "slice-parallel x%d, one 16-byte ncclAllReduce per step" % world,
+                           "order": args.order, "order_search": search_info},
                 "slices_per_s": args.steps * world * sps / (ms * 1e-3),
                 "clocks": clocks, "e2e": {"value": e2e_val, "unit": "amplitudes/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu}

@@ -99,6 +99,20 @@ int qtn_choose_slices(int32_t nt, const int32_t* ranks, const int64_t* const* di
                       const int32_t* const* labels, const int32_t* order, int32_t norder,
                       int32_t max_log2_elems, int64_t min_slices, int32_t* labels_out,
                       int32_t* nlabels_out);
+/* EXTENSION (no reference counterpart; the reference's treewidth
+ * order of src/network2graph.jl:473-479 stays the default): randomised greedy
+ * search for a cheaper pairwise order.  Runs ntrials greedy constructions
+ * (deterministic for a given seed), ranks them by flops with a penalty for
+ * tensors above 2^max_log2_elems elements (max_log2_elems < 0: no memory target),
+ * re-costs the best few exactly with the planner's walk + qtn_choose_slices rule
+ * and returns the cheapest as a complete label sequence for `order` of
+ * qtn_plan_create / qtn_contract (capacity of order_out = #contracted labels).
+ * cost_out (optional): [0] total flops over all slices, [1] flops per slice,
+ * [2] number of slices, [3] log2 of the largest tensor per slice.  Host-only.    */
+int qtn_order_search(int32_t nt, const int32_t* ranks, const int64_t* const* dims,
+                     const int32_t* const* labels, int32_t ntrials, uint64_t seed,
+                     int32_t max_log2_elems, int32_t* order_out, int32_t* norder_out,
+                     double cost_out[4]);
 /* Plan facts (host-only): info[0]=#pairwise steps, [1]=#slices, [2]=output rank,
  * [3]=#output elements, [4]=max tensor elements (per slice), [5]=#slice-invariant
  * steps, [6]=arena bytes, [7]=#kernel launches per slice.

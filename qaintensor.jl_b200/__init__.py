@@ -6,7 +6,7 @@ from ._lib import QtnError, launch_count  # noqa: F401
 from .tensor_network import (GeneralTensorNetwork, Summation, Tensor, TensorNetwork,  # noqa: F401
                              is_power_two, shift_pair, shift_summation)
 from .contract import (ContractionPlan, choose_slices, contract, contract_order, contract_rep,  # noqa: F401
-                       ncon, permutedims)
+                       ncon, permutedims, search_order)
 from .network2graph import (contraction_order, line_graph, network_graph,  # noqa: F401
                             optimize_contraction_order, tree_decomposition_width)
 from .svd import contract_svd, svd, svd_trunc  # noqa: F401

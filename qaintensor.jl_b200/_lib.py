@@ -52,6 +52,7 @@ _SIGS = {
     "qtn_plan_create": [i32, P(i32), P(P(i64)), P(P(i32)), P(i32), i32, P(i32), i32, i32, P(vp)],
     "qtn_plan_destroy": [vp],
     "qtn_choose_slices": [i32, P(i32), P(P(i64)), P(P(i32)), P(i32), i32, i32, i64, P(i32), P(i32)],
+    "qtn_order_search": [i32, P(i32), P(P(i64)), P(P(i32)), i32, C.c_uint64, i32, P(i32), P(i32), P(f64)],
     "qtn_plan_info": [vp, P(i64), P(f64)],
     "qtn_plan_out_dims": [vp, P(i64)],
     "qtn_plan_steps": [vp, P(i64), P(i32)],

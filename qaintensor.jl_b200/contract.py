@@ -163,6 +163,22 @@ def choose_slices(shapes, labels, order=None, max_log2_elems=28, min_slices=1):
     return [int(out[i]) for i in range(n.value)]
 
 
+def search_order(shapes, labels, ntrials=256, seed=0, max_log2_elems=-1):
+    """Randomised greedy order search (EXTENSION; ``qtn_order_search``).  Returns
+    ``(order, info)``: a complete label sequence for ``order=`` and the exact planner cost of it
+    (total flops over all slices, flops per slice, slices, log2 of the largest tensor)."""
+    args = NetworkArgs(shapes, labels)
+    ncap = max(sum(len(l) for l in labels), 1)
+    out = (C.c_int32 * ncap)()
+    n = C.c_int32(0)
+    cost = (C.c_double * 4)()
+    check(lib.qtn_order_search(args.nt, args.ranks, args.dims, args.labels, int(ntrials), int(seed), int(max_log2_elems),
+                               out, C.byref(n), cost))
+    info = {"total_flops": float(cost[0]), "flops_per_slice": float(cost[1]), "nslices": float(cost[2]),
+            "log2_max_elems": float(cost[3])}
+    return [int(out[i]) for i in range(n.value)], info
+
+
 def ncon(arrays, indexlist, order=None, precision="c128"):
     """``TensorOperations.ncon(tensors, indexlist; order)`` on the GPU (one-shot).
     ``precision="c64"`` selects the optional ComplexF32 mode (EXTENSION vii)."""

@@ -89,6 +89,12 @@ int qtn_choose_slices(int32_t nt, const int32_t* ranks, const int64_t* const* di
     if (!ranks || !dims || !labels || !labels_out || !nlabels_out) return fail(QTN_EINVAL, "qtn_choose_slices: null argument");
     return choose_slices(nt, ranks, dims, labels, order, norder, max_log2_elems, min_slices, labels_out, nlabels_out);
 }
+int qtn_order_search(int32_t nt, const int32_t* ranks, const int64_t* const* dims, const int32_t* const* labels,
+                     int32_t ntrials, uint64_t seed, int32_t max_log2_elems, int32_t* order_out, int32_t* norder_out,
+                     double cost_out[4]) {
+    if (!ranks || !dims || !labels || !order_out || !norder_out) return fail(QTN_EINVAL, "qtn_order_search: null argument");
+    return order_search(nt, ranks, dims, labels, ntrials, seed, max_log2_elems, order_out, norder_out, cost_out);
+}
 int qtn_plan_info(const qtn_plan* plan, int64_t info[8], double cost[2]) {
     if (!plan) return fail(QTN_EINVAL, "null plan");
     const Plan& p = *plan->p;

@@ -121,7 +121,21 @@ int launch_gemm(GemmArgs& g, int variant, int split_k, cudaStream_t st) {
         count_launch(1);
         return QTN_OK;
     }
-    if (variant == 1) return launch_gemm_t<128, 8, 32, 8, 16, 3>(g, split_k, st);
+    // Tall-skinny steps with a short contraction (M >= 4096, N <= 32, K <= 64: "apply a small operator to a big
+    // tensor", what a searched, state-vector-like order consists of) are HBM-bound: the tile covers all N columns so A
+    // is read exactly once, and stages are kept small so that 3-6 CTAs per SM keep ~96 KB of loads in flight.
+    // Measured on cfg 3 with the searched order (2^31 elements per step, B200): N = K = 16 steps 2.2 -> 4.5 TB/s.
+    // QTN_SKINNY=0 restores the generic tiles for A/B runs.
+    static int skinny = -1;
+    if (skinny < 0) { const char* e = getenv("QTN_SKINNY"); skinny = e ? atoi(e) : 1; }
+    const bool sk = skinny && g.M >= 4096 && g.K <= 64;
+    if (variant == 1) {
+        if (sk && g.N <= 8) return g.K <= 8 ? launch_gemm_t<128, 8, 32, 8, 8, 2, 5>(g, split_k, st)
+                                            : launch_gemm_t<128, 8, 32, 8, 8, 3, 4>(g, split_k, st);
+        if (sk) return launch_gemm_t<128, 16, 32, 16, 8, 3, 3>(g, split_k, st);
+        return launch_gemm_t<128, 8, 32, 8, 16, 3>(g, split_k, st);
+    }
+    if (sk && g.N <= 32) return launch_gemm_t<128, 32, 32, 32, 8, 3, 2>(g, split_k, st);
     // Measured on the dominant cfg-3 step (M=65536, N=2048, K=4096), TFLOP/s of the 37.1 DMMA ceiling:
     //   64x64 BK=16 3 stages 31.3 | 128x64 / 64x128 (8 warps, 1 CTA/SM) 25.2 | 64x32 (3 CTAs/SM) 32.6
     //   64x64 BK=8 3/4/6 stages 35.2 / 35.2 / 35.0 | 64x64 BK=4 8 stages 32.9
@@ -302,6 +316,8 @@ static int run_step(Plan* p, DevPlan* d, const Step& s, void* dev_out, cudaStrea
         g.c_dense = s.c_dense ? 1 : 0;
         if (!s.c_dense) { g.c_row = tab_arg(d, s.c_row); g.c_col = tab_arg(d, s.c_col); }
         g.M = s.M; g.N = s.N; g.K = s.K;
+        g.a_kmajor = s.a_kmajor ? 1 : 0;
+        g.b_kmajor = s.b_kmajor ? 1 : 0;
         g.use_3m = (s.M >= 512 && s.N >= 512 && s.K >= 64) ? 1 : 0;  // large contraction GEMMs only
         int variant = s.variant, split = s.split_k;
         bool atomic = (variant == 2) || split > 1;

@@ -48,6 +48,7 @@ struct GemmArgs {
     int mode;  // 0 store, 1 add (single writer), 2 atomic add
     int conj_a, conj_b;  // conjugate the operand on the way into the tensor pipe
     int use_3m;          // contraction plans may use the 3-multiplication complex product (see zgemm_gather_kernel)
+    int a_kmajor, b_kmajor;  // operand's contiguous direction is k: consecutive threads of a stage load take consecutive k
 };
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool valid) {
@@ -147,28 +148,37 @@ zgemm_gather_kernel(const __grid_constant__ GemmArgs g) {
     for (int i = tid; i < BN; i += NT) sCol[i] = (n0 + i < g.N) ? tab_off(g.b_col, n0 + i) : -1;
     __syncthreads();
 
-    const int lk = tid / TPK, lr = tid % TPK;
+    // Stage loads: TPK threads share one k-row.  Consecutive threads walk the rows (columns) of the operand
+    // unless its contiguous direction is k (kmajor), where they walk k so that a warp's requests coalesce.
+    const int lka = g.a_kmajor ? tid % BK : tid / TPK, lra = g.a_kmajor ? tid / BK : tid % TPK;
+    const int lkb = g.b_kmajor ? tid % BK : tid / TPK, lrb = g.b_kmajor ? tid / BK : tid % TPK;
     auto load_stage = [&](int stage, i64 k0) {
-        const i64 k = k0 + lk;
-        const bool kv = k < ke;
-        const i64 ka = kv ? tab_off(g.a_k, k) : 0;
-        const i64 kbo = kv ? tab_off(g.b_k, k) : 0;
-        double2* da = sA + (stage * BK + lk) * PA;
-        double2* db = sB + (stage * BK + lk) * PB;
+        {
+            const i64 k = k0 + lka;
+            const bool kv = k < ke;
+            const i64 ka = kv ? tab_off(g.a_k, k) : 0;
+            double2* da = sA + (stage * BK + lka) * PA;
 #pragma unroll
-        for (int i = 0; i < A_PER; ++i) {
-            const int m = lr + i * TPK;
-            const i64 ro = sRow[m];
-            const bool v = kv && ro >= 0;
-            cp_async16(da + m, v ? (A + ro + ka) : A, v);
+            for (int i = 0; i < A_PER; ++i) {
+                const int m = lra + i * TPK;
+                const i64 ro = sRow[m];
+                const bool v = kv && ro >= 0;
+                cp_async16(da + m, v ? (A + ro + ka) : A, v);
+            }
         }
+        {
+            const i64 k = k0 + lkb;
+            const bool kv = k < ke;
+            const i64 kbo = kv ? tab_off(g.b_k, k) : 0;
+            double2* db = sB + (stage * BK + lkb) * PB;
 #pragma unroll
-        for (int i = 0; i < B_PER; ++i) {
-            const int n = lr + i * TPK;
-            if (n < BN) {
-                const i64 co = sCol[n];
-                const bool v = kv && co >= 0;
-                cp_async16(db + n, v ? (B + co + kbo) : B, v);
+            for (int i = 0; i < B_PER; ++i) {
+                const int n = lrb + i * TPK;
+                if (n < BN) {
+                    const i64 co = sCol[n];
+                    const bool v = kv && co >= 0;
+                    cp_async16(db + n, v ? (B + co + kbo) : B, v);
+                }
             }
         }
     };

@@ -9,7 +9,10 @@
 // additive offset tables (row offset + k offset), and whose result is written in
 // the layout the next step / the caller wants.
 #include <algorithm>
+#include <climits>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <map>
 #include <memory>
 #include <set>
@@ -230,26 +233,30 @@ struct Arena {
 
 }  // namespace
 
-int choose_slices(int nt, const int32_t* ranks, const int64_t* const* dims, const int32_t* const* labels,
-                  const int32_t* order, int norder, int max_log2, int64_t min_slices, int32_t* labels_out,
-                  int32_t* nlabels_out) {
-    Parsed P;
-    int rc = parse(nt, ranks, dims, labels, order, norder, P);
-    if (rc) return rc;
-    if (max_log2 < 0 || max_log2 > 62) return fail(QTN_EINVAL, "qtn_choose_slices: max_log2_elems out of range");
-    SymTree T = sym_tree(P);
-    std::vector<int> sliced;
+namespace {
+
+// The greedy slice rule on a parsed network; returns total flops over all slices (exact) and the labels.
+struct SliceChoice {
+    std::vector<int> labels;
+    unsigned __int128 nslices = 1;
+    Cost per_slice;
+};
+
+SliceChoice choose_slices_sym(const Parsed& P, const SymTree& T, int max_log2, int64_t min_slices) {
+    SliceChoice R;
     std::set<int> sl;
     const int64_t limit = (int64_t)1 << max_log2;
-    auto nslices = [&](const std::set<int>& s) { unsigned __int128 n = 1; for (int l : s) n *= (unsigned __int128)P.ldim[l]; return n; };
-    auto size = [&](const std::vector<int>& labs) { int64_t s = 1; for (int l : labs) if (!sl.count(l)) s *= P.ldim[l]; return s; };
+    auto nslices = [&](const std::set<int>& s) { unsigned __int128 n = 1; for (int l : s) n *= (unsigned __int128)P.ldim.at(l); return n; };
+    auto size = [&](const std::vector<int>& labs) { int64_t s = 1; for (int l : labs) if (!sl.count(l)) s *= P.ldim.at(l); return s; };
     while (true) {
         Cost c = sym_cost(T, P.nt, P.ldim, sl);
-        if (c.mx <= limit && nslices(sl) >= (unsigned __int128)std::max<int64_t>(min_slices, 1)) break;
+        R.per_slice = c;
+        R.nslices = nslices(sl);
+        if (c.mx <= limit && R.nslices >= (unsigned __int128)std::max<int64_t>(min_slices, 1)) break;
         std::set<int> cand;
         for (auto& labs : T.nodes)
             if (size(labs) == c.mx)
-                for (int l : labs) if (l > 0 && !sl.count(l) && P.ldim[l] > 1) cand.insert(l);
+                for (int l : labs) if (l > 0 && !sl.count(l) && P.ldim.at(l) > 1) cand.insert(l);
         if (cand.empty()) break;
         bool have = false;
         unsigned __int128 bf = 0; int64_t bm = 0; int bl = 0;
@@ -260,11 +267,415 @@ int choose_slices(int nt, const int32_t* ranks, const int64_t* const* dims, cons
             unsigned __int128 f = c2.flops_exact * nslices(s2);
             if (!have || f < bf || (f == bf && (c2.mx < bm || (c2.mx == bm && l < bl)))) { have = true; bf = f; bm = c2.mx; bl = l; }
         }
-        sliced.push_back(bl);
+        R.labels.push_back(bl);
         sl.insert(bl);
     }
-    for (size_t i = 0; i < sliced.size(); ++i) labels_out[i] = sliced[i];
-    *nlabels_out = (int)sliced.size();
+    return R;
+}
+
+}  // namespace
+
+int choose_slices(int nt, const int32_t* ranks, const int64_t* const* dims, const int32_t* const* labels,
+                  const int32_t* order, int norder, int max_log2, int64_t min_slices, int32_t* labels_out,
+                  int32_t* nlabels_out) {
+    Parsed P;
+    int rc = parse(nt, ranks, dims, labels, order, norder, P);
+    if (rc) return rc;
+    if (max_log2 < 0 || max_log2 > 62) return fail(QTN_EINVAL, "qtn_choose_slices: max_log2_elems out of range");
+    SymTree T = sym_tree(P);
+    SliceChoice R = choose_slices_sym(P, T, max_log2, min_slices);
+    for (size_t i = 0; i < R.labels.size(); ++i) labels_out[i] = R.labels[i];
+    *nlabels_out = (int)R.labels.size();
+    return QTN_OK;
+}
+
+// ---- EXTENSION (no reference counterpart) -------------------------------------
+// Randomised greedy search for a cheaper pairwise order than the reference's treewidth order.
+// The reference order stays the default everywhere; this is what `optimize_contraction_order!`
+// would be replaced by on request.  One trial: repeatedly merge the connected pair minimising
+//   sign(c) log2(|c| + 1) - T * Gumbel,   c = size(out) - alpha * (size(a) + size(b)),
+// (alpha, T drawn per trial; trial 0 is the noise-free alpha = 1 greedy).  Trials are ranked by
+// log2(flops) + 0.5 * max(0, log2(max tensor) - max_log2); the best four trees are then refined by
+// simulated annealing on tree rotations (AnnealTree below; slicing-aware when a memory target is
+// given), and all finalists are re-costed exactly through the planner's own walk and the
+// deterministic slice rule; the cheapest (flops + 5.7 flop/B * bytes, summed over slices) wins.
+// Deterministic for a given (network, ntrials, seed); single-threaded.
+namespace {
+
+// FP64 tensor ceiling / HBM bandwidth of a B200 (37.1 TFLOP/s / 6.5 TB/s): flops one byte of traffic is worth.
+constexpr double kBalanceFlopPerByte = 5.7;
+
+struct SplitMix {
+    uint64_t s;
+    uint64_t next() {
+        uint64_t z = (s += 0x9E3779B97F4A7C15ull);
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        return z ^ (z >> 31);
+    }
+    double uni() { return ((next() >> 11) + 0.5) * (1.0 / 9007199254740992.0); }  // (0, 1)
+};
+
+struct Trial {
+    std::vector<int> seq;   // one contracted label per merge, in merge order
+    std::vector<std::array<int, 2>> merges;  // node ids (inputs 0..nt-1, the m-th merge creates nt + m)
+    double log2_flops = 0;  // of the un-sliced tree
+    double log2_mx = 0;
+    double obj = 0;
+};
+
+struct SearchNet {
+    std::vector<int> orig;                 // label index -> label
+    std::vector<double> lw;                // log2 extent
+    std::vector<std::vector<int>> nodes0;  // per input: sorted label indices (traced labels removed)
+};
+
+double lsize(const SearchNet& N, const std::vector<int>& labs) {
+    double s = 0;
+    for (int l : labs) s += N.lw[l];
+    return s;
+}
+
+Trial greedy_trial(const SearchNet& N, double alpha, double temp, SplitMix& rng) {
+    struct Cand { double key; int a, b; };
+    auto cmp = [](const Cand& x, const Cand& y) { return x.key > y.key || (x.key == y.key && (x.a > y.a || (x.a == y.a && x.b > y.b))); };
+    std::vector<std::vector<int>> nodes = N.nodes0;
+    std::vector<double> ls(nodes.size());
+    std::vector<char> alive(nodes.size(), 1);
+    std::vector<std::array<int, 2>> holder(N.orig.size(), std::array<int, 2>{-1, -1});
+    for (size_t i = 0; i < nodes.size(); ++i) {
+        ls[i] = lsize(N, nodes[i]);
+        for (int l : nodes[i]) (holder[l][0] < 0 ? holder[l][0] : holder[l][1]) = (int)i;
+    }
+    std::vector<Cand> heap;
+    auto push = [&](int a, int b) {
+        // symmetric difference size
+        const auto &la = nodes[a], &lb = nodes[b];
+        double lo = 0;
+        size_t i = 0, j = 0;
+        while (i < la.size() || j < lb.size()) {
+            if (j == lb.size() || (i < la.size() && la[i] < lb[j])) lo += N.lw[la[i++]];
+            else if (i == la.size() || lb[j] < la[i]) lo += N.lw[lb[j++]];
+            else { ++i; ++j; }
+        }
+        double c = std::exp2(lo) - alpha * (std::exp2(ls[a]) + std::exp2(ls[b]));
+        double key = c >= 0 ? std::log2(c + 1.0) : -std::log2(1.0 - c);
+        if (temp > 0) key -= temp * -std::log(-std::log(rng.uni()));
+        heap.push_back({key, std::min(a, b), std::max(a, b)});
+        std::push_heap(heap.begin(), heap.end(), cmp);
+    };
+    {
+        std::set<std::pair<int, int>> seen;
+        for (size_t l = 0; l < holder.size(); ++l) {
+            int a = holder[l][0], b = holder[l][1];
+            if (N.orig[l] < 0 || a < 0 || b < 0 || a == b) continue;
+            if (seen.insert({std::min(a, b), std::max(a, b)}).second) push(a, b);
+        }
+    }
+    Trial R;
+    double flops = 0, mx = 0;
+    for (double x : ls) mx = std::max(mx, x);
+    while (!heap.empty()) {
+        std::pop_heap(heap.begin(), heap.end(), cmp);
+        Cand c = heap.back();
+        heap.pop_back();
+        if (!alive[c.a] || !alive[c.b]) continue;
+        const auto &la = nodes[c.a], &lb = nodes[c.b];
+        std::vector<int> out;
+        double lk = 0;
+        int first_shared = -1;
+        size_t i = 0, j = 0;
+        while (i < la.size() || j < lb.size()) {
+            if (j == lb.size() || (i < la.size() && la[i] < lb[j])) out.push_back(la[i++]);
+            else if (i == la.size() || lb[j] < la[i]) out.push_back(lb[j++]);
+            else { lk += N.lw[la[i]]; if (first_shared < 0) first_shared = la[i]; ++i; ++j; }
+        }
+        if (first_shared < 0) continue;  // cannot happen: candidates share a label
+        R.seq.push_back(N.orig[first_shared]);
+        R.merges.push_back({c.a, c.b});
+        flops += std::exp2(ls[c.a] + ls[c.b] - lk);
+        alive[c.a] = alive[c.b] = 0;
+        int o = (int)nodes.size();
+        nodes.push_back(out);
+        ls.push_back(lsize(N, out));
+        alive.push_back(1);
+        mx = std::max(mx, ls[o]);
+        std::vector<int> nb;
+        for (int l : nodes[o]) {
+            auto& h = holder[l];
+            for (int q = 0; q < 2; ++q) if (h[q] == c.a || h[q] == c.b) h[q] = o;
+            if (N.orig[l] < 0) continue;
+            int other = h[0] == o ? h[1] : h[0];
+            if (other >= 0 && other != o && std::find(nb.begin(), nb.end(), other) == nb.end()) nb.push_back(other);
+        }
+        for (int d : nb) push(o, d);
+    }
+    R.log2_flops = std::log2(std::max(flops, 1.0)) + 3.0;
+    R.log2_mx = mx;
+    return R;
+}
+
+// Binary contraction tree over label bitsets, refined by simulated annealing on tree rotations:
+// at a node p = (a.b).c the alternatives (a.c).b and (b.c).a change one intermediate only, so a
+// move is costed locally.  Step cost model: MNK + kByteWeight * (MK + KN + MN), i.e. flops plus
+// operand traffic at the machine balance (FP64 tensor ceiling / HBM bandwidth ~ 5.7 flop per byte
+// -> 16 B * 5.7 / 8 flop ~ 11 per complex element).  Sliced labels have weight zero; with a
+// memory target, moves creating a tensor above it are rejected.
+struct AnnealTree {
+    const SearchNet* N = nullptr;
+    int nleaf = 0, W = 0, root = -1;
+    std::vector<int> parent, kid[2];
+    std::vector<uint64_t> bits;     // node-major, W words
+    std::vector<double> lw;         // label weight with sliced labels zeroed
+    std::vector<double> sz;         // log2 size of each node under lw
+    static constexpr double kByteWeight = kBalanceFlopPerByte * 16.0 / 8.0;  // per complex element, in units of 8 flop
+
+    uint64_t* b(int n) { return &bits[(size_t)n * W]; }
+    const uint64_t* b(int n) const { return &bits[(size_t)n * W]; }
+    double wsum(const uint64_t* x) const {
+        double s = 0;
+        for (int w = 0; w < W; ++w) for (uint64_t v = x[w]; v; v &= v - 1) s += lw[w * 64 + __builtin_ctzll(v)];
+        return s;
+    }
+    double wsum_and(const uint64_t* x, const uint64_t* y) const {
+        double s = 0;
+        for (int w = 0; w < W; ++w) for (uint64_t v = x[w] & y[w]; v; v &= v - 1) s += lw[w * 64 + __builtin_ctzll(v)];
+        return s;
+    }
+    bool share(const uint64_t* x, const uint64_t* y) const {
+        for (int w = 0; w < W; ++w) if (x[w] & y[w] & contr[w]) return true;
+        return false;
+    }
+    std::vector<uint64_t> contr;  // contracted (positive) labels
+    double step_cost(int x, int y, double so) const {
+        double k = wsum_and(b(x), b(y));
+        return std::exp2(sz[x] + sz[y] - k) + kByteWeight * (std::exp2(sz[x]) + std::exp2(sz[y]) + std::exp2(so));
+    }
+    double node_cost(int p) const { return step_cost(kid[0][p], kid[1][p], sz[p]); }
+    double total_cost() const {
+        double c = 0;
+        for (int n = nleaf; n < (int)parent.size(); ++n) c += node_cost(n);
+        return c;
+    }
+    double max_size() const {
+        double m = 0;
+        for (double x : sz) m = std::max(m, x);
+        return m;
+    }
+    void resize_all() { for (int n = 0; n < (int)parent.size(); ++n) sz[n] = wsum(b(n)); }
+
+    // Builds the tree from a greedy merge sequence (must connect everything).
+    bool init(const SearchNet& net, const std::vector<std::array<int, 2>>& merges) {
+        N = &net;
+        nleaf = (int)net.nodes0.size();
+        if ((int)merges.size() != nleaf - 1) return false;
+        int L = (int)net.orig.size();
+        W = (L + 63) / 64;
+        int nn = 2 * nleaf - 1;
+        parent.assign(nn, -1);
+        kid[0].assign(nn, -1);
+        kid[1].assign(nn, -1);
+        bits.assign((size_t)nn * W, 0);
+        contr.assign(W, 0);
+        lw = net.lw;
+        lw.resize((size_t)W * 64, 0.0);
+        for (int l = 0; l < L; ++l) if (net.orig[l] > 0) contr[l / 64] |= 1ull << (l % 64);
+        for (int i = 0; i < nleaf; ++i) for (int l : net.nodes0[i]) b(i)[l / 64] |= 1ull << (l % 64);
+        for (int m = 0; m < nleaf - 1; ++m) {
+            int o = nleaf + m, x = merges[m][0], y = merges[m][1];
+            kid[0][o] = x; kid[1][o] = y;
+            parent[x] = parent[y] = o;
+            for (int w = 0; w < W; ++w) b(o)[w] = b(x)[w] ^ b(y)[w];
+        }
+        root = nn - 1;
+        sz.assign(nn, 0.0);
+        resize_all();
+        return true;
+    }
+
+    // One Metropolis sweep of `moves` random rotations at temperature T; cap < 0: no size cap.
+    void anneal(int64_t moves, double T, double cap, SplitMix& rng) {
+        int nint = nleaf - 1;
+        std::vector<uint64_t> nb(W);
+        for (int64_t it = 0; it < moves; ++it) {
+            uint64_t r = rng.next();
+            int p = nleaf + (int)(r % (uint64_t)nint);
+            int s = (int)((r >> 32) & 1), t = (int)((r >> 33) & 1);
+            int l = kid[s][p], c = kid[1 - s][p];
+            if (l < nleaf) continue;
+            int x = kid[t][l], y = kid[1 - t][l];  // new: l = (x.c), p = (l.y)
+            if (!share(b(x), b(c))) continue;
+            for (int w = 0; w < W; ++w) nb[w] = b(x)[w] ^ b(c)[w];
+            double ns = wsum(nb.data());
+            if (cap >= 0 && ns > cap + 1e-9 && ns > sz[l]) continue;
+            double old_cost = node_cost(l) + node_cost(p);
+            double kxc = wsum_and(b(x), b(c));
+            double kly = wsum_and(nb.data(), b(y));
+            double new_cost = std::exp2(sz[x] + sz[c] - kxc) + kByteWeight * (std::exp2(sz[x]) + std::exp2(sz[c]) + std::exp2(ns)) +
+                              std::exp2(ns + sz[y] - kly) + kByteWeight * (std::exp2(ns) + std::exp2(sz[y]) + std::exp2(sz[p]));
+            double dE = std::log2(new_cost) - std::log2(old_cost);
+            if (dE > 0 && (T <= 0 || rng.uni() >= std::exp2(-dE / T))) continue;
+            kid[0][l] = x; kid[1][l] = c;
+            parent[c] = l;
+            kid[s][p] = l; kid[1 - s][p] = y;
+            parent[y] = p;
+            std::copy(nb.begin(), nb.end(), b(l));
+            sz[l] = ns;
+        }
+    }
+
+    // Adds sliced labels by the planner's rule (label on a largest tensor minimising the total cost) until
+    // every tensor fits 2^cap; then drops sliced labels that are no longer needed.
+    void fit_slices(double cap, std::vector<int>& sliced) {
+        for (;;) {
+            double mx = max_size();
+            if (mx <= cap + 1e-9) break;
+            std::vector<uint64_t> cand(W, 0);
+            for (int n = 0; n < (int)parent.size(); ++n)
+                if (sz[n] >= mx - 1e-9) for (int w = 0; w < W; ++w) cand[w] |= b(n)[w] & contr[w];
+            int best = -1;
+            double bc = 0, bm = 0;
+            for (int w = 0; w < W; ++w)
+                for (uint64_t v = cand[w]; v; v &= v - 1) {
+                    int l = w * 64 + __builtin_ctzll(v);
+                    if (lw[l] <= 0) continue;
+                    double keep = lw[l];
+                    lw[l] = 0;
+                    resize_all();
+                    double c = total_cost() * std::exp2(keep), m = max_size();
+                    if (best < 0 || c < bc || (c == bc && m < bm)) { best = l; bc = c; bm = m; }
+                    lw[l] = keep;
+                }
+            if (best < 0) { resize_all(); break; }
+            lw[best] = 0;
+            sliced.push_back(best);
+            resize_all();
+        }
+    }
+    void drop_unneeded_slices(double cap, std::vector<int>& sliced) {
+        for (size_t i = sliced.size(); i-- > 0;) {
+            int l = sliced[i];
+            lw[l] = N->lw[l];
+            resize_all();
+            if (max_size() <= cap + 1e-9) sliced.erase(sliced.begin() + i);
+            else lw[l] = 0;
+        }
+        resize_all();
+    }
+
+    // Label sequence of the tree (children before parents, costlier subtree first).
+    std::vector<int> sequence() const {
+        std::vector<int> seq, stack{root};
+        std::vector<int> post;
+        while (!stack.empty()) {
+            int n = stack.back();
+            stack.pop_back();
+            if (n < nleaf) continue;
+            post.push_back(n);
+            stack.push_back(kid[0][n]);
+            stack.push_back(kid[1][n]);
+        }
+        for (size_t i = post.size(); i-- > 0;) {
+            int n = post[i];
+            const uint64_t *x = b(kid[0][n]), *y = b(kid[1][n]);
+            for (int w = 0; w < W; ++w) {
+                uint64_t v = x[w] & y[w] & contr[w];
+                if (v) { seq.push_back(N->orig[w * 64 + __builtin_ctzll(v)]); break; }
+            }
+        }
+        return seq;
+    }
+};
+
+}  // namespace
+
+int order_search(int nt, const int32_t* ranks, const int64_t* const* dims, const int32_t* const* labels,
+                 int ntrials, uint64_t seed, int max_log2, int32_t* order_out, int32_t* norder_out, double* cost_out) {
+    Parsed P;
+    int rc = parse(nt, ranks, dims, labels, nullptr, 0, P);
+    if (rc) return rc;
+    if (ntrials < 1) return fail(QTN_EINVAL, "qtn_order_search: ntrials must be >= 1");
+    if (max_log2 > 62) return fail(QTN_EINVAL, "qtn_order_search: max_log2_elems out of range");
+    SearchNet N;
+    std::map<int, int> index;
+    for (auto& kv : P.ldim) {
+        index[kv.first] = (int)N.orig.size();
+        N.orig.push_back(kv.first);
+        N.lw.push_back(std::log2((double)kv.second));
+    }
+    for (auto& lab : P.labels) {
+        std::vector<int> l;
+        for (int x : lab) if (std::count(lab.begin(), lab.end(), x) == 1) l.push_back(index[x]);
+        std::sort(l.begin(), l.end());
+        N.nodes0.push_back(l);
+    }
+    SplitMix rng{seed ^ 0x51ED270B35A1F2C7ull};
+    const size_t keep = 8;
+    std::vector<Trial> best;
+    for (int t = 0; t < ntrials; ++t) {
+        double alpha = 1.0, temp = 0.0;
+        if (t > 0) {
+            alpha = 2.0 * rng.uni();
+            temp = std::exp2(-7.0 + 8.0 * rng.uni());  // 2^-7 .. 2
+        }
+        Trial R = greedy_trial(N, alpha, temp, rng);
+        R.obj = R.log2_flops + (max_log2 >= 0 ? 0.5 * std::max(0.0, R.log2_mx - (double)max_log2) : 0.0);
+        size_t pos = 0;
+        while (pos < best.size() && best[pos].obj <= R.obj) ++pos;
+        if (pos < keep) {
+            best.insert(best.begin() + pos, std::move(R));
+            if (best.size() > keep) best.pop_back();
+        }
+    }
+    // refinement of the best trees by annealing (connected networks only)
+    std::vector<std::vector<int>> cands;
+    for (auto& t : best) cands.push_back(t.seq);
+    const int n_anneal = 4, n_steps = 64;          // trees refined, temperature steps per phase
+    const double mv = 0.125, t_hi = 0.5, t_lo = 0.01;  // moves per step = mv * ntrials * (nt - 1); log2-cost temperatures
+    const double cap = max_log2 >= 0 ? (double)max_log2 : -1.0;
+    for (size_t i = 0; i < best.size() && (int)i < n_anneal; ++i) {
+        AnnealTree A;
+        if (nt < 3 || !A.init(N, best[i].merges)) continue;
+        int64_t moves = std::max<int64_t>(64, (int64_t)(mv * ntrials * (nt - 1)));
+        std::vector<int> sliced;
+        for (int st = 0; st < n_steps; ++st) A.anneal(moves, t_hi * std::pow(t_lo / t_hi, (double)st / (n_steps - 1)), -1.0, rng);
+        A.anneal(4 * moves, 0.0, -1.0, rng);
+        if (cap >= 0) {
+            for (int round = 0; round < 3; ++round) {
+                A.fit_slices(cap, sliced);
+                for (int st = 0; st < n_steps; ++st)
+                    A.anneal(moves, 0.5 * t_hi * std::pow(t_lo / t_hi, (double)st / (n_steps - 1)), cap, rng);
+                A.anneal(4 * moves, 0.0, cap, rng);
+                A.drop_unneeded_slices(cap, sliced);
+            }
+        }
+        cands.push_back(A.sequence());
+    }
+    // exact re-costing of the finalists through the planner's walk + slice rule
+    bool have = false;
+    double bt = 0;
+    SliceChoice bc;
+    std::vector<int> border;
+    for (size_t i = 0; i < cands.size(); ++i) {
+        Parsed Q = P;
+        Q.order = cands[i];
+        std::set<int> seen(Q.order.begin(), Q.order.end());
+        for (auto& kv : P.ldim) if (kv.first > 0 && !seen.count(kv.first)) Q.order.push_back(kv.first);
+        SymTree T = sym_tree(Q);
+        SliceChoice c = max_log2 >= 0 ? choose_slices_sym(Q, T, max_log2, 1) : SliceChoice();
+        if (max_log2 < 0) c.per_slice = sym_cost(T, Q.nt, Q.ldim, {});
+        // ranked by flops + machine balance * bytes (the annealer's step model, summed exactly by the planner)
+        double tot = ((double)c.per_slice.flops + kBalanceFlopPerByte * c.per_slice.bytes) * (double)c.nslices;
+        if (!have || tot < bt) { have = true; bt = tot; bc = c; border = Q.order; }
+    }
+    for (size_t i = 0; i < border.size(); ++i) order_out[i] = border[i];
+    *norder_out = (int)border.size();
+    if (cost_out) {
+        cost_out[0] = bc.per_slice.flops * (double)bc.nslices;
+        cost_out[1] = bc.per_slice.flops;
+        cost_out[2] = (double)bc.nslices;
+        cost_out[3] = std::log2((double)bc.per_slice.mx);
+    }
     return QTN_OK;
 }
 
@@ -417,15 +828,24 @@ int build_plan(int nt, const int32_t* ranks, const int64_t* const* dims, const i
         sel(pl.nodes[a], node_strides[a], fa, e, st);
         s.M = prod(e);
         s.a_row = spec_table(e, st);
+        auto min_stride = [](const std::vector<int64_t>& ex, const std::vector<int64_t>& sx) {
+            int64_t m = INT64_MAX;
+            for (size_t q = 0; q < ex.size(); ++q) if (ex[q] > 1) m = std::min(m, sx[q]);
+            return m;
+        };
+        const int64_t a_row_min = min_stride(e, st);
         std::vector<int64_t> me = e;
         sel(pl.nodes[a], node_strides[a], sh, e, st);
         s.K = prod(e);
         s.a_k = spec_table(e, st);
+        s.a_kmajor = min_stride(e, st) < a_row_min;
         sel(pl.nodes[b], node_strides[b], sh, e, st);
         s.b_k = spec_table(e, st);
+        const int64_t b_k_min = min_stride(e, st);
         sel(pl.nodes[b], node_strides[b], fb, e, st);
         s.N = prod(e);
         s.b_col = spec_table(e, st);
+        s.b_kmajor = b_k_min < min_stride(e, st);
         s.n_mlabels = (int)fa.size();
         {
             std::vector<int> f;
@@ -572,6 +992,21 @@ int build_plan(int nt, const int32_t* ranks, const int64_t* const* dims, const i
         if (!s.invariant) pl.launches_per_slice += 1;
     }
     for (int i = 0; i < nt; ++i) pl.max_elems = std::max(pl.max_elems, pl.nodes[i].numel);
+    if (getenv("QTN_PLAN_DEBUG")) {  // operand layouts of the big steps (diagnostics)
+        auto show = [&](const char* nm, const OffTable& t) {
+            const TableSpec& sp = pl.table_specs[t.spec];
+            fprintf(stderr, "   %s:", nm);
+            for (size_t q = 0; q < sp.extents.size(); ++q) fprintf(stderr, " %lldx%lld", (long long)sp.extents[q], (long long)sp.strides[q]);
+            fprintf(stderr, "\n");
+        };
+        for (size_t i = 0; i < pl.steps.size(); ++i) {
+            const Step& s = pl.steps[i];
+            if (s.kind != STEP_GEMM || s.invariant || (double)s.M * s.N * s.K < 1e9) continue;
+            fprintf(stderr, "step %zu M=%lld N=%lld K=%lld variant %d split %d akm %d bkm %d\n", i, (long long)s.M, (long long)s.N,
+                    (long long)s.K, s.variant, s.split_k, (int)s.a_kmajor, (int)s.b_kmajor);
+            show("a_row", s.a_row); show("a_k", s.a_k); show("b_k", s.b_k); show("b_col", s.b_col);
+        }
+    }
     *out = plan.release();
     return QTN_OK;
 }

@@ -58,6 +58,8 @@ struct Step {
     bool final_step = false;      // writes (accumulates into) the caller's output
     OffTable a_row, a_k, b_k, b_col, c_row, c_col;
     bool c_dense = false;         // c offset = m + M * n
+    bool a_kmajor = false;        // the lowest-stride mode of A is a contracted one (k runs are contiguous, rows are not)
+    bool b_kmajor = false;        // same for B
     int split_k = 1;
     int variant = 0;              // kernel tile configuration
     // permute / trace
@@ -96,6 +98,9 @@ int build_plan(int nt, const int32_t* ranks, const int64_t* const* dims, const i
 int choose_slices(int nt, const int32_t* ranks, const int64_t* const* dims, const int32_t* const* labels,
                   const int32_t* order, int norder, int max_log2, int64_t min_slices, int32_t* labels_out,
                   int32_t* nlabels_out);
+// EXTENSION: randomised greedy order search (see plan.cpp).  order_out: capacity = #contracted labels.
+int order_search(int nt, const int32_t* ranks, const int64_t* const* dims, const int32_t* const* labels,
+                 int ntrials, uint64_t seed, int max_log2, int32_t* order_out, int32_t* norder_out, double* cost_out);
 // Fills Plan::tables from Plan::table_specs (called once, before the first upload).
 int materialize_tables(Plan* p);
 // Builds the table buffer entries for a mode group; returns the descriptor.

@@ -102,8 +102,20 @@ def contraction_order(net):
     return out
 
 
-def optimize_contraction_order(net):
-    """``optimize_contraction_order!(net)`` (src/network2graph.jl:473-479)."""
+def optimize_contraction_order(net, method="treewidth", ntrials=256, seed=0, max_log2_elems=-1):
+    """``optimize_contraction_order!(net)`` (src/network2graph.jl:473-479).
+
+    EXTENSION: ``method="search"`` replaces the reference's treewidth heuristic by the
+    randomised-greedy + annealing search of ``qtn_order_search`` (same contract: ``net.contractions`` is
+    permuted in place so that the default ascending-label walk of ``contract`` follows the found tree;
+    open indices are handled).  The default stays the reference's order."""
+    if method == "search":
+        from .contract import contract_rep, search_order
+        order, _ = search_order([t.data.shape for t in net.tensors], contract_rep(net), ntrials, seed, max_log2_elems)
+        net.contractions = [net.contractions[k - 1] for k in order]
+        return None
+    if method != "treewidth":
+        raise ValueError("method must be 'treewidth' (reference) or 'search' (extension)")
     if len(net.openidx) != 0:
         warnings.warn("For TensorNetworks with open indices the treewidth algorithm is unlikely to optimize performance")
         warnings.warn("All open indices are disregarded")

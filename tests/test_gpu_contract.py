@@ -267,3 +267,39 @@ def test_contract_sliced_keyword(gpu):  # EXTENSION keyword on the reference's `
     want = complex(oc.contract(to_oracle(net)))
     assert abs(complex(q.contract(net, max_log2_elems=6, min_slices=8)) - want) < TOL * abs(want)
     assert abs(complex(q.contract(net, max_log2_elems=6, precision="c64")) - want) < 1e-4 * abs(want)
+
+
+def test_searched_order_value_invariance(gpu):  # EXTENSION: qtn_order_search, same bar as the reference order
+    q = gpu
+    # (1) closed brickwork amplitude, order passed explicitly and through the optimize_contraction_order! mirror
+    net, _, _ = q.circuits.cfg2_network(16, 12, seed=11)
+    want = complex(oc.contract(to_oracle(net)))
+    il = q.contract_rep(net)
+    arrays = [t.data for t in net.tensors]
+    shapes = [a.shape for a in arrays]
+    order, info = q.search_order(shapes, il, 64, 3, -1)
+    plan = q.ContractionPlan(shapes, il, order)
+    assert plan.flops_per_slice == info["total_flops"]
+    assert abs(complex(plan.execute(arrays)) - want) < TOL * abs(want)
+    n2 = net.copy()
+    q.optimize_contraction_order(n2, method="search", ntrials=64, seed=3)
+    assert abs(complex(q.contract(n2)) - want) < TOL * abs(want)
+    # (2) 2-D RQC, slicing-aware search: state-vector-like tree (huge M, small N and K), sliced
+    net, _, _ = q.circuits.cfg3_network(4, 4, 8, seed=21)
+    want = complex(oc.contract(to_oracle(net)))
+    il = q.contract_rep(net)
+    arrays = [t.data for t in net.tensors]
+    shapes = [a.shape for a in arrays]
+    order, info = q.search_order(shapes, il, 64, 0, 7)
+    S = q.choose_slices(shapes, il, order, 7, 1)
+    sp = q.ContractionPlan(shapes, il, order, S)
+    assert sp.nslices == info["nslices"] and sp.max_elems <= 2 ** 7 and sp.nslices > 1
+    assert abs(complex(sp.execute(arrays)) - want) < TOL * abs(want)
+    assert abs(complex(q.ContractionPlan(shapes, il, order, S, precision="c64").execute(arrays)) - want) < 1e-4 * abs(want)
+    # (3) open legs: 2^10 amplitudes in one contraction
+    rng = np.random.default_rng(9)
+    net = q.circuits.amplitude_network(10, q.circuits.brickwork_gates(10, 6, rng), None)
+    want = oc.contract(to_oracle(net))
+    n2 = net.copy()
+    q.optimize_contraction_order(n2, method="search", ntrials=32)
+    assert rel_err(q.contract(n2), want) < TOL

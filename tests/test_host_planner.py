@@ -184,3 +184,78 @@ def test_random_general_networks_plan_parity(q):
             sp = q.ContractionPlan(shapes, il, None, S)
             f2, b2, mx2, _ = oplan.tree_cost(nodes, steps, dims, S)
             assert (sp.flops_per_slice, sp.nslices) == (f2, int(np.prod([dims[l] for l in S])))
+
+
+# ---- EXTENSION: qtn_order_search ---------------------------------------------------
+def _plan_total(q, shapes, il, order, max_log2):
+    S = q.choose_slices(shapes, il, order, max_log2, 1) if max_log2 >= 0 else []
+    plan = q.ContractionPlan(shapes, il, order, S)
+    tot = plan.flops_per_slice * plan.nslices
+    info = (tot, plan.flops_per_slice, plan.nslices, plan.max_elems)
+    plan.close()
+    return info
+
+
+def test_order_search_is_valid_deterministic_and_exactly_costed(q):
+    net, _, _ = q.circuits.cfg2_network(12, 8, seed=3)
+    il = q.contract_rep(net)
+    shapes = [t.data.shape for t in net.tensors]
+    o1, i1 = q.search_order(shapes, il, 64, 7, -1)
+    o2, i2 = q.search_order(shapes, il, 64, 7, -1)
+    assert o1 == o2 and i1 == i2                                   # deterministic for (network, ntrials, seed)
+    assert sorted(o1) == list(range(1, len(net.contractions) + 1))  # a complete sequence of the contracted labels
+    tot, fps, nsl, mx = _plan_total(q, shapes, il, o1, -1)
+    assert i1["total_flops"] == tot and i1["flops_per_slice"] == fps and i1["nslices"] == nsl == 1
+    assert 2.0 ** i1["log2_max_elems"] == mx                       # the reported cost IS the planner's cost of that order
+    o3, _ = q.search_order(shapes, il, 64, 8, -1)
+    assert sorted(o3) == sorted(o1)
+
+
+def test_order_search_beats_reference_order_on_cfg3_and_cfg2(q):
+    # cfg 3 (6x6, 16 cycles): reference treewidth order 3.2e17 flop at the 2^31 slicing; the search must find < 1e15
+    net, _, _ = q.circuits.cfg3_network()
+    il = q.contract_rep(net)
+    shapes = [t.data.shape for t in net.tensors]
+    order, info = q.search_order(shapes, il, 128, 0, 31)
+    tot, _, nsl, mx = _plan_total(q, shapes, il, order, 31)
+    assert tot == info["total_flops"] and nsl == info["nslices"] and mx <= 2 ** 31
+    ref = net.copy()
+    q.optimize_contraction_order(ref)
+    ref_tot = _plan_total(q, shapes, q.contract_rep(ref), None, 31)[0]
+    assert ref_tot > 3e17 and tot < 1e15
+    net2, _, _ = q.circuits.cfg2_network()
+    il2 = q.contract_rep(net2)
+    shapes2 = [t.data.shape for t in net2.tensors]
+    _, info2 = q.search_order(shapes2, il2, 256, 0, -1)
+    ref2 = net2.copy()
+    q.optimize_contraction_order(ref2)
+    assert info2["total_flops"] < _plan_total(q, shapes2, q.contract_rep(ref2), None, -1)[0]
+
+
+def test_order_search_general_networks_and_mirror(q):
+    rng = np.random.default_rng(11)
+    r = lambda *sh: rng.standard_normal(sh) + 1j * rng.standard_normal(sh)  # noqa: E731
+    disconnected = q.GeneralTensorNetwork(
+        [q.Tensor(r(2, 3)), q.Tensor(r(3, 2)), q.Tensor(r(4, 2)), q.Tensor(r(2, 4)), q.Tensor(r(2, 2))],
+        [q.Summation([(1, 1), (2, 2)]), q.Summation([(1, 2), (2, 1)]), q.Summation([(3, 1), (4, 2)]),
+         q.Summation([(3, 2), (4, 1)]), q.Summation([(5, 1), (5, 2)])], [])
+    nets = [random_TN(q, Nn, Ne, rng) for (Nn, Ne) in [(2, 1), (3, 6), (6, 12), (10, 30), (20, 60)]]
+    nets = [n for n in nets if all(t.data.shape != (1,) for t in n.tensors)] + [disconnected]
+    assert len(nets) >= 4
+    for net in nets:
+        Ne = len(net.contractions)
+        il = q.contract_rep(net)
+        shapes = [t.data.shape for t in net.tensors]
+        order, info = q.search_order(shapes, il, 16, 1, -1)
+        assert sorted(order) == list(range(1, Ne + 1))
+        assert info["total_flops"] == _plan_total(q, shapes, il, order, -1)[0]
+        # value invariance under the searched order (test/test_treewidth.jl:326-327 for the reference's order)
+        n2 = net.copy()
+        q.optimize_contraction_order(n2, method="search", ntrials=16, seed=1)
+        assert set(n2.contractions) == set(net.contractions) and n2.tensors == net.tensors
+        assert [net.contractions[k - 1] for k in order] == n2.contractions
+        assert np.allclose(oc.contract(to_oracle(n2)), oc.contract(to_oracle(net)), rtol=1e-12, atol=1e-12)
+    with pytest.raises(ValueError):
+        q.optimize_contraction_order(net, method="nope")
+    with pytest.raises(q.QtnError):
+        q.search_order([(2, 2), (2, 2)], [[1, 2], [2, 1]], 0, 0, -1)  # ntrials < 1

@@ -77,6 +77,48 @@ int qtn_order_exhaustive(int32_t nt, const int32_t* ranks, const int32_t* const*
                          int32_t nlabels, const int64_t* legdims, int32_t* seq_out,
                          int32_t* nseq_out, int64_t* cost_out);
 
+/* ---- network builder (host) ----------------------------------------------------
+ * The symbolic part of the reference, so that a C / C++ / Julia harness can go from
+ * gate matrices to amplitudes through this library alone.  Tensor data
+ * is copied into the handle (ComplexF64, column-major); indices are 1-based.
+ * qtn_net_create   GeneralTensorNetwork(tensors, contractions, openidx)
+ *                  (src/tensor_network.jl:26-33): pairs[k] = (t1, l1, t2, l2),
+ *                  openidx[i] = (tensor, leg).
+ * qtn_net_tensor_circuit  tensor_circuit!(psi, cgc), non-decomposed branch
+ *                  (src/tensor_circuit.jl:44-51): gate g acts on nwires[g] wires
+ *                  (concatenated in `wires`), matrices[g] is 2^M x 2^M column-major.
+ *                  Error strings of the reference's wire checks are kept.
+ * qtn_net_apply_mpo  apply_MPO(psi, mpo::MPO, iwire) (src/mpo.jl:232-252): `op` is an
+ *                  operator network whose 2M open legs follow the MPO convention of
+ *                  src/mpo.jl:88; returns a NEW network (psi, op untouched).
+ * qtn_net_close    EXTENSION: contracts every open leg w with the basis bra <bits[w]|.
+ * qtn_net_optimize_order  optimize_contraction_order!(net) (src/network2graph.jl:473-479):
+ *                  method 0 = reference treewidth heuristic (bit-exact), 1 = EXTENSION
+ *                  qtn_order_search(ntrials, seed, max_log2_elems).
+ * qtn_net_contract contract(net) (src/contract.jl:242-264, default-order branch) on the
+ *                  GPU; max_log2_elems >= 0 slices the contraction (EXTENSION);
+ *                  dtype QTN_C64 rounds the tensors to ComplexF32 (host_out = float pairs).
+ * qtn_net_sizes / qtn_net_structure / qtn_net_tensor read the network back
+ * (sizes = #tensors, #contractions, #open legs; data pointers stay library-owned).   */
+typedef struct qtn_net qtn_net;
+int qtn_net_create(int32_t nt, const void* const* host_data, const int32_t* ranks,
+                   const int64_t* const* dims, int32_t ncontr, const int32_t* pairs,
+                   int32_t nopen, const int32_t* openidx, qtn_net** net_out);
+int qtn_net_destroy(qtn_net* net);
+int qtn_net_sizes(const qtn_net* net, int32_t sizes[3]);
+int qtn_net_structure(const qtn_net* net, int32_t* pairs_out, int32_t* openidx_out);
+int qtn_net_tensor(const qtn_net* net, int32_t i, int32_t* rank_out, int64_t* dims_out,
+                   const void** data_out);
+int qtn_net_tensor_circuit(qtn_net* net, int32_t ngates, const int32_t* nwires,
+                           const int32_t* wires, const void* const* matrices);
+int qtn_net_apply_mpo(const qtn_net* psi, const qtn_net* op, int32_t nw, const int32_t* iwire,
+                      qtn_net** net_out);
+int qtn_net_close(qtn_net* net, const int32_t* bits);
+int qtn_net_optimize_order(qtn_net* net, int32_t method, int32_t ntrials, uint64_t seed,
+                           int32_t max_log2_elems);
+int qtn_net_contract(const qtn_net* net, int32_t dtype, int32_t max_log2_elems, void* host_out,
+                     int32_t* out_rank, int64_t* out_dims /* capacity 64 */);
+
 /* ---- contraction plans -------------------------------------------------------
  * Replaces `TensorOperations.ncon(tensors, indexlist; order)` as called from
  * src/contract.jl:257, 263.  A plan fixes shapes, labels and order; it can be
@@ -119,7 +161,9 @@ int qtn_order_search(int32_t nt, const int32_t* ranks, const int64_t* const* dim
  * cost[0]=sum 8MNK per slice, cost[1]=sum 16(MK+KN+MN) per slice.               */
 int qtn_plan_info(const qtn_plan* plan, int64_t info[8], double cost[2]);
 int qtn_plan_out_dims(const qtn_plan* plan, int64_t* dims_out /* rank entries */);
-/* Per-step shapes: mnk[3*nsteps], flags[nsteps] (bit0 = slice-invariant).        */
+/* Per-step shapes: mnk[3*nsteps], flags[nsteps]: bit0 = slice-invariant,
+ * bits1-3 = kind (0 pairwise GEMM, 1 permute, 2 partial trace), bits4-7 = kernel
+ * tile variant, bits8+ = split-K factor.                                         */
 int qtn_plan_steps(const qtn_plan* plan, int64_t* mnk, int32_t* flags);
 
 /* Copy the nt input tensors host -> device (one staged transfer).               */

@@ -67,6 +67,28 @@ function treewidth_perm(ntensors::Integer, pairs::Vector{NTuple{4,Int}})
     Int.(perm[1:nc]), Int(tw[])
 end
 
+# ---- EXTENSION: searched contraction order (opt-in replacement of optimize_contraction_order!'s heuristic) ----
+# `network` as for `ncon` (positive labels = contractions); returns the label sequence to pass as `order`,
+# equivalently the permutation `perm` with `net.contractions = net.contractions[perm]`.
+function search_order(dims::Vector{Vector{Int64}}, network::Vector{Vector{Int}}; ntrials::Integer=256, seed::Integer=0,
+                      max_log2_elems::Integer=-1)
+    nt = length(dims)
+    ranks = Cint[length(d) for d in dims]
+    labs = [Cint.(l) for l in network]
+    ncap = max(sum(length, network), 1)
+    order = Vector{Cint}(undef, ncap)
+    n = Ref{Cint}(0)
+    cost = zeros(Float64, 4)
+    dptr = Ptr{Int64}[pointer(d) for d in dims]
+    lptr = Ptr{Cint}[pointer(l) for l in labs]
+    GC.@preserve dims labs begin
+        check(ccall((:qtn_order_search, LIB), Cint,
+            (Cint, Ptr{Cint}, Ptr{Ptr{Int64}}, Ptr{Ptr{Cint}}, Cint, UInt64, Cint, Ptr{Cint}, Ref{Cint}, Ptr{Float64}),
+            nt, ranks, dptr, lptr, ntrials, UInt64(seed), max_log2_elems, order, n, cost))
+    end
+    Int.(order[1:n[]]), (total_flops=cost[1], flops_per_slice=cost[2], nslices=cost[3], log2_max_elems=cost[4])
+end
+
 # ---- LinearAlgebra.svd + tail-norm rule (src/svd.jl:26-33) + max-bond cap (extension) ------------------
 function svd_trunc(A::Matrix{ComplexF64}; er::Float64=-1.0, maxdim::Integer=0)
     m, n = size(A)

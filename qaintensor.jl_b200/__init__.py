@@ -15,4 +15,5 @@ from .tensor_circuit import decompose, tensor_circuit  # noqa: F401
 from .mps import (MPS, ClosedMPS, OpenMPS, PeriodicMPS, check_mps, contract_svd_mps, permute, switch)  # noqa: F401
 from .mpo import MPO, apply_MPO, extend_MPO  # noqa: F401
 from .mps_sim import DeviceMPS, brickwork_layer_sites, tfi_mpo  # noqa: F401
+from .native_network import NativeNetwork  # noqa: F401
 from . import circuits, gates  # noqa: F401

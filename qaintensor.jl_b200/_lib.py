@@ -85,6 +85,16 @@ _SIGS = {
     "qtn_mps_apply_mpo": [vp, P(vp), P(i64), P(i64), f64, i64, P(f64)],
     "qtn_mps_expect_mpo": [vp, P(vp), P(i64), P(i64), P(f64)],
     "qtn_orth_columns": [vp, i64, i64, vp, P(i32)],
+    "qtn_net_create": [i32, P(vp), P(i32), P(P(i64)), i32, P(i32), i32, P(i32), P(vp)],
+    "qtn_net_destroy": [vp],
+    "qtn_net_sizes": [vp, P(i32)],
+    "qtn_net_structure": [vp, P(i32), P(i32)],
+    "qtn_net_tensor": [vp, i32, P(i32), P(i64), P(vp)],
+    "qtn_net_tensor_circuit": [vp, i32, P(i32), P(i32), P(vp)],
+    "qtn_net_apply_mpo": [vp, vp, i32, P(i32), P(vp)],
+    "qtn_net_close": [vp, P(i32)],
+    "qtn_net_optimize_order": [vp, i32, i32, C.c_uint64, i32],
+    "qtn_net_contract": [vp, i32, i32, vp, P(i32), P(i64)],
 }
 for _name, _args in _SIGS.items():
     _f = getattr(lib, _name)

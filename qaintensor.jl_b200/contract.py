@@ -78,6 +78,10 @@ class ContractionPlan:
         check(lib.qtn_plan_steps(self._h, mnk, flags))
         return [(int(mnk[3 * i]), int(mnk[3 * i + 1]), int(mnk[3 * i + 2]), int(flags[i])) for i in range(self.nsteps)]
 
+    def n_pairwise(self):
+        """Number of pairwise (GEMM) steps, i.e. without trace steps and operand pre-permutes."""
+        return sum(1 for (_, _, _, f) in self.steps() if (f >> 1) & 7 == 0)
+
     def _marshal(self, arrays):
         """Arrays in the ABI's layout plus their pointer table; repeated calls with the very same
         (already column-major, right-precision) array objects re-use the marshalled table."""

@@ -135,7 +135,7 @@ int launch_gemm(GemmArgs& g, int variant, int split_k, cudaStream_t st) {
         if (sk) return launch_gemm_t<128, 16, 32, 16, 8, 3, 3>(g, split_k, st);
         return launch_gemm_t<128, 8, 32, 8, 16, 3>(g, split_k, st);
     }
-    if (sk && g.N <= 32) return launch_gemm_t<128, 32, 32, 32, 8, 3, 2>(g, split_k, st);
+    if ((sk || (skinny && variant == 3)) && g.N <= 32) return launch_gemm_t<128, 32, 32, 32, 8, 3, 2>(g, split_k, st);
     // Measured on the dominant cfg-3 step (M=65536, N=2048, K=4096), TFLOP/s of the 37.1 DMMA ceiling:
     //   64x64 BK=16 3 stages 31.3 | 128x64 / 64x128 (8 warps, 1 CTA/SM) 25.2 | 64x32 (3 CTAs/SM) 32.6
     //   64x64 BK=8 3/4/6 stages 35.2 / 35.2 / 35.0 | 64x64 BK=4 8 stages 32.9
@@ -340,7 +340,7 @@ static int run_step(Plan* p, DevPlan* d, const Step& s, void* dev_out, cudaStrea
     if (blocks < 1) blocks = 1;
     if (s.kind == STEP_PERMUTE) {
         u.c_row = tab_arg(d, s.c_row);
-        u.mode = 1;
+        u.mode = s.final_step ? 1 : 0;  // the closing permute accumulates over slices; a pre-permute just stores
         if (p->dtype == QTN_C64) permute_gather_kernel<float2><<<blocks, 256, 0, st>>>(u);
         else permute_gather_kernel<double2><<<blocks, 256, 0, st>>>(u);
     } else {

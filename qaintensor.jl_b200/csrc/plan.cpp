@@ -819,12 +819,61 @@ int build_plan(int nt, const int32_t* ranks, const int64_t* const* dims, const i
         sh.clear();
         for (int l : pl.nodes[a].labels)
             if (std::find(pl.nodes[b].labels.begin(), pl.nodes[b].labels.end(), l) != pl.nodes[b].labels.end()) sh.push_back(l);
+        std::vector<int64_t> e, st;
+        // Pre-permute of the smaller operand (the one TTGT transpose that is worth its traffic).  k is enumerated
+        // in A's layout order, so A always has its stride-1 mode first in its row or k group; B need not: when
+        // neither B's first k mode nor its first column mode has stride 1, every 16-byte element of a B tile
+        // comes from a different sector, and B is re-read once per row tile.  If B is small against the step's
+        // traffic it is first rewritten dense as (k in A's order, columns): one gather pass, coalesced writes.
+        {
+            std::vector<int64_t> ek, sk_, ec, sc_;
+            sel(pl.nodes[b], node_strides[b], sh, ek, sk_);
+            sel(pl.nodes[b], node_strides[b], fb, ec, sc_);
+            auto first_stride = [](const std::vector<int64_t>& ex, const std::vector<int64_t>& sx) {
+                for (size_t q = 0; q < ex.size(); ++q) if (ex[q] > 1) return sx[q];
+                return (int64_t)1;
+            };
+            const int64_t Kb = prod(ek), Nb = prod(ec), Ma = vol(fa);
+            const bool scattered = first_stride(ek, sk_) != 1 && first_stride(ec, sc_) != 1;
+            const bool reread = Ma > 128;                                        // more than one row tile
+            const bool cheap = Kb * Nb >= 65536 && 4 * Kb * Nb <= Ma * (Kb + Nb);  // permute traffic << step traffic
+            static int prepermute = -1;
+            if (prepermute < 0) { const char* ev = getenv("QTN_PREPERMUTE"); prepermute = ev ? atoi(ev) : 1; }
+            // QTN_PREPERMUTE: 0 = never, 1 = rule above (default), 2 = whenever B is scattered (exercises the path in tests)
+            if (prepermute && scattered && ((reread && cheap) || prepermute == 2)) {
+                const Node& nb = pl.nodes[b];
+                Step ps;
+                ps.kind = STEP_PERMUTE;
+                ps.a = b;
+                ps.out = (int)pl.nodes.size();
+                ps.M = nb.numel;
+                Node o;
+                o.labels = sh;
+                o.labels.insert(o.labels.end(), fb.begin(), fb.end());
+                std::vector<int64_t> sin;
+                for (int l : o.labels) {
+                    size_t q = std::find(nb.labels.begin(), nb.labels.end(), l) - nb.labels.begin();
+                    o.dims.push_back(nb.dims[q]);
+                    sin.push_back(node_strides[b][q]);
+                }
+                o.numel = nb.numel;
+                o.slice_dep = nb.slice_dep;
+                ps.a_row = spec_table(o.dims, sin);
+                ps.c_row = spec_table(o.dims, dense_strides(o.dims));
+                pl.nodes.push_back(o);
+                node_strides.push_back(dense_strides(o.dims));
+                full.push_back(full[b]);
+                pl.steps.push_back(ps);
+                if (a0 == b) a0 = ps.out;  // keep the alive-list bookkeeping below pointed at live nodes
+                *std::find(alive.begin(), alive.end(), b) = ps.out;
+                b = ps.out;
+            }
+        }
         Step s;
         s.kind = STEP_GEMM;
         s.a = a;
         s.b = b;
         s.out = (int)pl.nodes.size();
-        std::vector<int64_t> e, st;
         sel(pl.nodes[a], node_strides[a], fa, e, st);
         s.M = prod(e);
         s.a_row = spec_table(e, st);
@@ -976,6 +1025,7 @@ int build_plan(int nt, const int32_t* ranks, const int64_t* const* dims, const i
         if (s.kind == STEP_GEMM) {
             int bm = 64, bn = (s.N <= 16) ? 8 : 64;
             s.variant = (s.N <= 16) ? 1 : 0;
+            if (s.N > 16 && s.N <= 32 && s.M >= 1024) { s.variant = 3; bm = 128; bn = 32; }  // 128x32 tile: all columns in one CTA
             int64_t tiles = ((s.M + bm - 1) / bm) * ((s.N + bn - 1) / bn);
             s.split_k = 1;
             if (s.M * s.N <= 16 && s.K >= 2048) {

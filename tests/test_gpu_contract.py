@@ -303,3 +303,15 @@ def test_searched_order_value_invariance(gpu):  # EXTENSION: qtn_o
     n2 = net.copy()
     q.optimize_contraction_order(n2, method="search", ntrials=32)
     assert rel_err(q.contract(n2), want) < TOL
+
+
+def test_operand_prepermute_forced(gpu):  # planner pre-permutes of scattered B operands, forced on for small networks
+    import os
+    import subprocess
+    import sys
+    from conftest import ROOT
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "prepermute_check.py")],
+                         env=dict(os.environ, QTN_PREPERMUTE="2"), capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    last = out.stdout.strip().splitlines()[-1]
+    assert " ok, " in last and int(last.split(" ok, ")[1].split()[0]) > 20, last

@@ -1,0 +1,110 @@
+"""The library's own network builder (csrc/network.cpp, ``qtn_net_*``) against the Python mirror of the
+reference's symbolic code (structure bit-exact) and, on the GPU, against the CPU oracle (amplitudes 1e-10)."""
+import numpy as np
+import pytest
+
+from conftest import random_TN, rel_err, to_oracle
+from oracle import contract as oc
+
+
+def _same(a, b):
+    return (a.contractions == b.contractions and list(a.openidx) == list(b.openidx) and len(a.tensors) == len(b.tensors) and
+            all(x.data.shape == y.data.shape and np.array_equal(x.data, y.data) for x, y in zip(a.tensors, b.tensors)))
+
+
+def _ket_network(q, nq):
+    return q.GeneralTensorNetwork([q.Tensor(np.array([1, 0], dtype=np.complex128)) for _ in range(nq)], [],
+                                  [(i, 1) for i in range(1, nq + 1)])
+
+
+def test_round_trip_and_tensor_circuit_structure(q):
+    rng = np.random.default_rng(2)
+    net = random_TN(q, 10, 20, rng)
+    assert _same(q.NativeNetwork.from_network(net).to_network(), net)
+    for nq, gates in ((12, q.qft_circuit(12)), (24, q.circuits.brickwork_gates(24, 20, rng)),
+                      (36, q.circuits.rqc2d_gates(6, 6, 16, rng))):
+        want = _ket_network(q, nq)
+        q.tensor_circuit(want, gates)
+        nn = q.NativeNetwork.from_network(_ket_network(q, nq))
+        nn.tensor_circuit(gates)
+        assert nn.sizes() == (len(want.tensors), len(want.contractions), nq)
+        assert _same(nn.to_network(), want)
+    # amplitude network of BASELINE config 3, and both orderings, bit-exact with the mirror
+    want, gates, bits = q.circuits.cfg3_network()
+    nn = q.NativeNetwork.from_network(_ket_network(q, 36))
+    nn.tensor_circuit(gates)
+    nn.close_wires(bits)
+    assert _same(nn.to_network(), want)
+    nn.optimize_contraction_order()
+    q.optimize_contraction_order(want)
+    assert _same(nn.to_network(), want)
+    nn.optimize_contraction_order(method="search", ntrials=16, seed=5, max_log2_elems=31)
+    q.optimize_contraction_order(want, method="search", ntrials=16, seed=5, max_log2_elems=31)
+    assert _same(nn.to_network(), want)
+
+
+def test_apply_mpo_structure_and_error_strings(q):
+    from qaintensor_b200 import mpo as pm
+    rng = np.random.default_rng(3)
+    r = lambda *s: rng.standard_normal(s) + 1j * rng.standard_normal(s)  # noqa: E731
+    # a hand-built 3-site operator network in the MPO layout of src/mpo.jl:57-88 (no SVD needed on the host)
+    op = pm.MPO.__new__(pm.MPO)
+    op.tensors = [q.Tensor(r(2, 2, 3)), q.Tensor(r(3, 2, 2, 4)), q.Tensor(r(4, 2, 2))]
+    op.contractions = [q.Summation([(1, 3), (2, 1)]), q.Summation([(2, 4), (3, 1)])]
+    op.openidx = [(3, 2), (2, 2), (1, 1), (3, 3), (2, 3), (1, 2)]
+    psi = _ket_network(q, 5)
+    q.tensor_circuit(psi, q.circuits.brickwork_gates(5, 3, rng))
+    for iwire in ((1, 2, 3), (2, 4, 5), (5, 3, 1)):
+        want = q.apply_MPO(psi, op, iwire)
+        got = q.NativeNetwork.from_network(psi).apply_mpo(q.NativeNetwork.from_network(op), iwire)
+        assert _same(got.to_network(), want)
+    npsi, nop = q.NativeNetwork.from_network(psi), q.NativeNetwork.from_network(op)
+    with pytest.raises(q.QtnError, match="Repeated wires are not valid."):
+        npsi.apply_mpo(nop, (1, 1, 2))
+    with pytest.raises(q.QtnError, match="Wires must be integers between 1 and n"):
+        npsi.apply_mpo(nop, (1, 2, 6))
+    with pytest.raises(q.QtnError, match="2 \\* 2 open legs"):
+        npsi.apply_mpo(nop, (1, 2))
+    g = q.CircuitGate((1, 7), np.eye(4))
+    with pytest.raises(q.QtnError, match="more wires than the network has open legs"):
+        npsi.tensor_circuit([g])
+    with pytest.raises(q.QtnError, match="Repeated wires"):
+        npsi.tensor_circuit([_FakeGate((2, 2), np.eye(4))])  # CircuitGate's own constructor already rejects this
+    bad = q.GeneralTensorNetwork([q.Tensor(r(2, 2))], [], [(1, 1)])
+    with pytest.raises(q.QtnError, match="tensor leg without contraction or open index"):
+        q.NativeNetwork.from_network(bad).optimize_contraction_order(method="search")
+
+
+class _FakeGate:
+    def __init__(self, iwire, matrix):
+        self.iwire, self.matrix = iwire, matrix
+
+
+@pytest.mark.gpu
+def test_native_network_contract_gpu(gpu):
+    q = gpu
+    rng = np.random.default_rng(4)
+    # open legs: full state vector of a 10-qubit brickwork circuit
+    gates = q.circuits.brickwork_gates(10, 6, rng)
+    want_net = q.circuits.amplitude_network(10, gates, None)
+    nn = q.NativeNetwork.from_network(_ket_network(q, 10))
+    nn.tensor_circuit(gates)
+    want = oc.contract(to_oracle(want_net))
+    got = nn.contract()
+    assert got.shape == want.shape and rel_err(got, want) < 1e-10
+    assert rel_err(nn.contract(precision="c64"), want) < 1e-4
+    # closed amplitude, reference order / searched order / sliced
+    net, gates, bits = q.circuits.cfg2_network(16, 12, seed=11)
+    want = complex(oc.contract(to_oracle(net)))
+    nn = q.NativeNetwork.from_network(_ket_network(q, 16))
+    nn.tensor_circuit(gates)
+    nn.close_wires(bits)
+    nn.optimize_contraction_order()
+    assert abs(complex(nn.contract()) - want) < 1e-10 * abs(want)
+    assert abs(complex(nn.contract(max_log2_elems=8)) - want) < 1e-10 * abs(want)
+    nn.optimize_contraction_order(method="search", ntrials=32)
+    assert abs(complex(nn.contract()) - want) < 1e-10 * abs(want)
+    # single tensor: permutedims by the open legs (src/contract.jl:243-245)
+    d = rng.standard_normal((2, 6)) + 1j * rng.standard_normal((2, 6))
+    one = q.NativeNetwork.from_network(q.GeneralTensorNetwork([q.Tensor(d)], [], [(1, 2), (1, 1)]))
+    assert np.array_equal(one.contract(), d.T)

@@ -409,25 +409,28 @@ def main():
 
     # ---- workload ----------------------------------------------------------------------
     if args.workload == "cfg3":
-        net, _, _ = q.circuits.cfg3_network()
+        net, gates2, bits2 = q.circuits.cfg3_network()
+        nq = 36
         name = "cfg3: 36-qubit 6x6 RQC, 16 cycles, single amplitude, reference treewidth order, sliced"
     else:
         net, gates2, bits2 = q.circuits.cfg2_network()
+        nq = 24
         name = "cfg2: 24-qubit brickwork depth 20, single amplitude, reference treewidth order"
-        if args.open_wires > 0:
-            import warnings
-            k = args.open_wires
-            full = q.circuits.amplitude_network(24, gates2, None)
-            keep = [full.openidx[w] for w in range(k)]
-            for w in range(k, 24):
-                v = np.zeros(2, dtype=np.complex128)
-                v[int(bits2[w])] = 1.0
-                full.tensors.append(q.Tensor(v))
-                full.contractions.append(q.Summation([full.openidx[w], (len(full.tensors), 1)]))
-            full.openidx = keep
-            net = full
-            name = "cfg2 batched: 24-qubit brickwork depth 20, 2^%d amplitudes per contraction (first %d wires open)" % (k, k)
-            warnings.simplefilter("ignore")
+    if args.open_wires > 0:  # amplitude batching: the first k output wires stay open -> 2^k amplitudes per contraction
+        import warnings
+        k = args.open_wires
+        full = q.circuits.amplitude_network(nq, gates2, None)
+        keep = [full.openidx[w] for w in range(k)]
+        for w in range(k, nq):
+            v = np.zeros(2, dtype=np.complex128)
+            v[int(bits2[w])] = 1.0
+            full.tensors.append(q.Tensor(v))
+            full.contractions.append(q.Summation([full.openidx[w], (len(full.tensors), 1)]))
+        full.openidx = keep
+        net = full
+        name = name.replace("single amplitude", "2^%d amplitudes per contraction (first %d wires open)" % (k, k)).replace(
+            "cfg%s:" % args.workload[-1], "cfg%s batched:" % args.workload[-1])
+        warnings.simplefilter("ignore")
     arrays = [t.data for t in net.tensors]
     shapes = [a.shape for a in arrays]
     search_info = None
@@ -586,7 +589,7 @@ def main():
                                  if plan.arena_bytes > 2e8 else "working set fits L2 (latency-bound workload); no flush",
                            "value_definition": "(slices processed / slices per amplitude) / time; a full amplitude is "
                                                "%d slices" % plan.nslices,
-                           "parallelism": "slice-parallel x%d, one 16-byte ncclAllReduce per step" % world,
+                           "parallelism": "slice-parallel x%d, one %d-byte ncclAllReduce per step" % (world, 16 * plan.out_numel),
                            "order": args.order, "order_search": search_info},
                 "slices_per_s": args.steps * world * sps / (ms * 1e-3),
                 "clocks": clocks, "e2e": {"value": e2e_val, "unit": "amplitudes/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},

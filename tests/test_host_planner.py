@@ -219,6 +219,13 @@ def test_order_search_beats_reference_order_on_cfg3_and_cfg2(q):
     order, info = q.search_order(shapes, il, 128, 0, 31)
     tot, _, nsl, mx = _plan_total(q, shapes, il, order, 31)
     assert tot == info["total_flops"] and nsl == info["nslices"] and mx <= 2 ** 31
+    # independent check: the oracle's walk, cost model and slice rule applied to the searched label sequence
+    nodes, steps = oplan.contraction_tree(il, order)
+    dims = oplan.label_dims([t.data for t in net.tensors], il)
+    S = oplan.choose_slice_labels(nodes, steps, dims, 31, 1)
+    assert S == q.choose_slices(shapes, il, order, 31, 1)
+    f, _, mx_o, _ = oplan.tree_cost(nodes, steps, dims, S)
+    assert f == info["flops_per_slice"] and 2 ** len(S) == nsl and mx_o == mx
     ref = net.copy()
     q.optimize_contraction_order(ref)
     ref_tot = _plan_total(q, shapes, q.contract_rep(ref), None, 31)[0]

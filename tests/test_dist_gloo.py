@@ -52,6 +52,22 @@ def _worker(rank, world, port, ret):
     dist.all_reduce(cover)
     full = complex(oc.contract(on.Network([on.Tensor(a) for a in arrays], [on.Summation(s.idx) for s in net.contractions], [])))
     ok = bool(torch.all(cover == 1)) and abs(complex(buf[0], buf[1]) - full) < 1e-12 * abs(full)
+    # EXTENSION: the searched order (qtn_order_search) is deterministic, so every rank derives the same tree and
+    # slice set without any exchange, and the slice-parallel sum over that tree gives the same amplitude
+    net2, _, _ = q.circuits.cfg2_network(10, 8, seed=5)
+    il2 = q.contract_rep(net2)
+    order, info = q.search_order(shapes, il2, 32, 3, 5)
+    S2 = q.choose_slices(shapes, il2, order, 5, 1)
+    n2 = 2 ** len(S2)
+    digest2 = torch.tensor([float(sum((i + 1) * l for i, l in enumerate(order))), float(sum(S2)), info["total_flops"]], dtype=torch.float64)
+    lo, hi = digest2.clone(), digest2.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    t0, t1 = n2 * rank // world, n2 * (rank + 1) // world
+    part2 = complex(oplan.contract_sliced(arrays, il2, order, S2, range(t0, t1)))
+    buf2 = torch.tensor([part2.real, part2.imag], dtype=torch.float64)
+    dist.all_reduce(buf2)
+    ok = ok and torch.equal(lo, hi) and n2 > 1 and abs(complex(buf2[0], buf2[1]) - full) < 1e-12 * abs(full)
     ret[rank] = ok
     dist.destroy_process_group()
 

@@ -545,9 +545,16 @@ def main():
         hbm_peak = pk["hbm_gbs"] if pk else 6650.0
         ridge = dmma_peak * 1e12 / (hbm_peak * 1e9)
         tensor_bound = dom_flops / dom_bytes >= ridge
+        # measured DRAM bytes of the dominant launch (ncu --set full, profiles/): reported only for the launch shape /
+        # kernel variant the capture was taken on, else null
         traffic = None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get(args.workload + ("_search" if args.order == "search" else ""))
+            ent = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get(
+                args.workload + ("_search" if args.order == "search" else ""))
+            if ent and ent.get("MNK") == [M, N, K]:
+                traffic = ent["bytes"]
+            elif ent and "factor" in ent and ent.get("variant") == top_variant:
+                traffic = ent["factor"] * dom_bytes
         except Exception:
             pass
         if tensor_bound:

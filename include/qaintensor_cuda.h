@@ -91,6 +91,8 @@ int qtn_order_exhaustive(int32_t nt, const int32_t* ranks, const int32_t* const*
  * qtn_net_apply_mpo  apply_MPO(psi, mpo::MPO, iwire) (src/mpo.jl:232-252): `op` is an
  *                  operator network whose 2M open legs follow the MPO convention of
  *                  src/mpo.jl:88; returns a NEW network (psi, op untouched).
+ * qtn_net_extend_mpo  extend_MPO(mpo::MPO, iwire) (src/mpo.jl:122-157): identity pipes on
+ *                  the wires between iwire[M] and iwire[1] (sorted descending); mutates `mpo`.
  * qtn_net_close    EXTENSION: contracts every open leg w with the basis bra <bits[w]|.
  * qtn_net_optimize_order  optimize_contraction_order!(net) (src/network2graph.jl:473-479):
  *                  method 0 = reference treewidth heuristic (bit-exact), 1 = EXTENSION
@@ -113,6 +115,7 @@ int qtn_net_tensor_circuit(qtn_net* net, int32_t ngates, const int32_t* nwires,
                            const int32_t* wires, const void* const* matrices);
 int qtn_net_apply_mpo(const qtn_net* psi, const qtn_net* op, int32_t nw, const int32_t* iwire,
                       qtn_net** net_out);
+int qtn_net_extend_mpo(qtn_net* mpo, int32_t nw, const int32_t* iwire);
 int qtn_net_close(qtn_net* net, const int32_t* bits);
 int qtn_net_optimize_order(qtn_net* net, int32_t method, int32_t ntrials, uint64_t seed,
                            int32_t max_log2_elems);

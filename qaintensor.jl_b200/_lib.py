@@ -92,6 +92,7 @@ _SIGS = {
     "qtn_net_tensor": [vp, i32, P(i32), P(i64), P(vp)],
     "qtn_net_tensor_circuit": [vp, i32, P(i32), P(i32), P(vp)],
     "qtn_net_apply_mpo": [vp, vp, i32, P(i32), P(vp)],
+    "qtn_net_extend_mpo": [vp, i32, P(i32)],
     "qtn_net_close": [vp, P(i32)],
     "qtn_net_optimize_order": [vp, i32, i32, C.c_uint64, i32],
     "qtn_net_contract": [vp, i32, i32, vp, P(i32), P(i64)],

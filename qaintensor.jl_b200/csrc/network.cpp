@@ -224,6 +224,45 @@ int qtn_net_apply_mpo(const qtn_net* psi, const qtn_net* op, int32_t nw, const i
     return QTN_OK;
 }
 
+// extend_MPO(mpo::MPO, iwire) (src/mpo.jl:122-157): an operator on M qubits (wires sorted descending) becomes one on
+// the N = iwire[1] - iwire[M] + 1 qubits it spans by inserting identity "pipe" tensors delta(a, e) delta(b, c) of shape
+// (bond, 2, 2, bond) on the wires in between.  Mutates `mpo` like the reference; the reference's error strings are kept.
+int qtn_net_extend_mpo(qtn_net* mpo, int32_t nw, const int32_t* iwire) {
+    if (!mpo || !iwire || nw < 1) return fail(QTN_EINVAL, "qtn_net_extend_mpo: bad argument");
+    for (int i = 0; i < nw; ++i)
+        for (int j = 0; j < i; ++j) if (iwire[i] == iwire[j]) return fail(QTN_EINVAL, "Repeated wires are not valid.");
+    for (int i = 1; i < nw; ++i) if (iwire[i] > iwire[i - 1]) return fail(QTN_EINVAL, "Wires not sorted");
+    for (int i = 0; i < nw; ++i) if (iwire[i] < 1) return fail(QTN_EINVAL, "Wires must be positive integers.");
+    const int lo = iwire[nw - 1], hi = iwire[0];
+    const int N = hi - lo + 1, M = nw;
+    if ((int)mpo->tensors.size() != M) return fail(QTN_EINVAL, "MPO length does not match the wires");
+    if (M == N) return fail(QTN_EINVAL, "MPO is already decomposed in N tensors");
+    // qwire reversed = hi, hi-1, ..., lo; pipes = wires in [lo, hi] the operator does not act on, ascending
+    for (int w = lo; w <= hi; ++w) {
+        bool acts = false;
+        for (int i = 0; i < nw; ++i) acts = acts || iwire[i] == w;
+        if (acts) continue;
+        const int ind = hi - w + 1;  // 1-based position of w in the reversed wire list
+        if (ind < 2 || ind - 1 > (int)mpo->tensors.size()) return fail(QTN_EINVAL, "internal: pipe position out of range");
+        const NetTensor& prev = mpo->tensors[ind - 2];
+        if (prev.dims.empty()) return fail(QTN_EINVAL, "MPO tensor %d has no bond leg", ind - 1);
+        const int64_t bond = prev.dims.back();
+        NetTensor t;
+        t.dims = {bond, 2, 2, bond};
+        t.data.assign((size_t)(bond * 4 * bond), cplx(0.0, 0.0));
+        for (int64_t a = 0; a < bond; ++a)
+            for (int64_t b = 0; b < 2; ++b) t.data[(size_t)(a + bond * (b + 2 * (b + 2 * a)))] = cplx(1.0, 0.0);
+        mpo->tensors.insert(mpo->tensors.begin() + (ind - 1), std::move(t));
+    }
+    for (int i = M; i < N; ++i) {
+        mpo->contractions.push_back({{Pair{i, 4}, Pair{i + 1, 1}}});
+        mpo->openidx.insert(mpo->openidx.begin(), Pair{i + 1, 2});
+        if (i + 1 > (int)mpo->openidx.size()) return fail(QTN_EINVAL, "operator network has too few open legs for extend_MPO");
+        mpo->openidx.insert(mpo->openidx.begin() + (i + 1), Pair{i + 1, 3});
+    }
+    return QTN_OK;
+}
+
 // EXTENSION (amplitude networks of BASELINE configs 2 and 3): closes every open leg w with the basis bra <bits[w]|.
 int qtn_net_close(qtn_net* net, const int32_t* bits) {
     if (!net || (!bits && !net->openidx.empty())) return fail(QTN_EINVAL, "qtn_net_close: null argument");

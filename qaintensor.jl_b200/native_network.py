@@ -69,6 +69,10 @@ class NativeNetwork:
         check(lib.qtn_net_apply_mpo(self._h, op._h, len(iwire), arr_i32(list(iwire)), C.byref(h)))
         return NativeNetwork(h)
 
+    def extend_mpo(self, iwire):
+        """``extend_MPO(mpo, iwire)`` (src/mpo.jl:122-157), in place like the reference."""
+        check(lib.qtn_net_extend_mpo(self._h, len(iwire), arr_i32(list(iwire))))
+
     def close_wires(self, bits):
         check(lib.qtn_net_close(self._h, arr_i32([int(b) for b in bits])))
 

@@ -75,6 +75,52 @@ def test_apply_mpo_structure_and_error_strings(q):
         q.NativeNetwork.from_network(bad).optimize_contraction_order(method="search")
 
 
+def test_extend_mpo_structure_and_oracle_cross_check(q):
+    from oracle import mpo as ompo, network as on
+    from qaintensor_b200 import mpo as pm
+    rng = np.random.default_rng(7)
+    r = lambda *s: rng.standard_normal(s) + 1j * rng.standard_normal(s)  # noqa: E731
+
+    def hand_mpo(bonds):
+        """Operator network in the MPO layout of src/mpo.jl:57-88 with the given inner bond dimensions."""
+        M = len(bonds) + 1
+        op = pm.MPO.__new__(pm.MPO)
+        op.tensors = [q.Tensor(r(2, 2, bonds[0]))] + [q.Tensor(r(bonds[i - 1], 2, 2, bonds[i])) for i in range(1, M - 1)] + \
+                     [q.Tensor(r(bonds[-1], 2, 2))]
+        op.contractions = [q.Summation([(i, 3 if i == 1 else 4), (i + 1, 1)]) for i in range(1, M)]
+        op.openidx = [(M - i + 1, 2) for i in range(1, M)] + [(1, 1)] + [(M - i + 1, 3) for i in range(1, M)] + [(1, 2)]
+        return op
+
+    nfail = 0
+    for bonds, iwire in (([3], (4, 1)), ([2, 4], (6, 4, 1)), ([4, 3], (5, 4, 2)), ([2], (3, 1)), ([2, 2], (4, 3, 1)), ([3, 2, 2], (5, 4, 3, 1))):
+        want = hand_mpo(bonds)
+        nn = q.NativeNetwork.from_network(want)
+        ocopy = object.__new__(ompo.MPO)
+        on.Network.__init__(ocopy, [on.Tensor(t.data) for t in want.tensors], [on.Summation(c.idx) for c in want.contractions],
+                            list(want.openidx))
+        try:
+            q.extend_MPO(want, iwire)      # Python mirror (mutates)
+        except IndexError:                 # the reference indexes past the tensor list for this wire pattern (BoundsError there)
+            with pytest.raises(IndexError):
+                ompo.extend_MPO(ocopy, iwire)
+            with pytest.raises(q.QtnError, match="pipe position out of range"):
+                nn.extend_mpo(iwire)
+            nfail += 1
+            continue
+        nn.extend_mpo(iwire)               # C++ builder (mutates)
+        ompo.extend_MPO(ocopy, iwire)      # oracle (mutates)
+        got = nn.to_network()
+        assert _same(got, want)
+        assert [c.idx for c in got.contractions] == [c.idx for c in ocopy.contractions] and list(got.openidx) == list(ocopy.openidx)
+        assert all(np.array_equal(a.data, b.data) for a, b in zip(got.tensors, ocopy.tensors))
+    assert 0 < nfail < 6
+    nn = q.NativeNetwork.from_network(hand_mpo([3]))
+    for iwire, msg in (((2, 1), "MPO is already decomposed in N tensors"), ((1, 4), "Wires not sorted"), ((3, 3), "Repeated wires are not valid."),
+                       ((2, 0), "Wires must be positive integers."), ((5, 3, 1), "MPO length does not match the wires")):
+        with pytest.raises(q.QtnError, match=msg):
+            nn.extend_mpo(iwire)
+
+
 class _FakeGate:
     def __init__(self, iwire, matrix):
         self.iwire, self.matrix = iwire, matrix

@@ -111,15 +111,24 @@ def cpu_threads():
         return os.cpu_count() or 1
 
 
-def oracle_cfg3_sampler(max_log2):
+def oracle_cfg3_sampler(max_log2, order_mode="reference", search_trials=512):
     """CPU arm: the oracle's per-slice tree execution (numpy transpose + OpenBLAS zgemm, all
-    host threads) on ONE slice of the same amplitude; returns (run_one_slice, nslices, flops)."""
+    host threads) on ONE slice of the same amplitude; returns (run_one_slice, nslices, flops).
+    order_mode "search": the same searched label sequence the GPU arm uses (host-only planner call,
+    no device code involved), so that both arms execute the same tree."""
     from oracle import circuits as ocirc, contract as oc, network2graph as o2g, plan as op
     net, _, _ = ocirc.cfg3_network()
-    o2g.optimize_contraction_order(net)
-    il = oc.contract_rep(net)
+    order = None
+    if order_mode == "search":
+        import __graft_entry__ as graft
+        q = graft.load_package()
+        il = oc.contract_rep(net)
+        order, _ = q.search_order([t.data.shape for t in net.tensors], il, search_trials, 0, max_log2)
+    else:
+        o2g.optimize_contraction_order(net)
+        il = oc.contract_rep(net)
     arrays = [t.data for t in net.tensors]
-    nodes, steps = op.contraction_tree(il)
+    nodes, steps = op.contraction_tree(il, order)
     dims = op.label_dims(arrays, il)
     S = op.choose_slice_labels(nodes, steps, dims, max_log2, 1)
     f, _, _, _ = op.tree_cost(nodes, steps, dims, S)
@@ -344,9 +353,11 @@ def run_reference(args):
     if args.workload == "cfg4":
         return run_reference_cfg4(args)
     if args.workload == "cfg3":
-        run, nsl, flops = oracle_cfg3_sampler(args.cpu_max_log2)
+        run, nsl, flops = oracle_cfg3_sampler(args.cpu_max_log2, args.order, args.search_trials)
         sample = "1 of %d slices per step (oracle slicing to <=2^%d elements), all host BLAS threads" % (nsl, args.cpu_max_log2)
         name = "cfg3: 36-qubit 6x6 RQC, 16 cycles, single amplitude, reference treewidth order, sliced"
+        if args.order == "search":
+            name = name.replace("reference treewidth order", "EXTENSION searched order (qtn_order_search, %d trials)" % args.search_trials)
     else:
         run, nsl, flops = oracle_cfg2_sampler()
         sample = "1 full amplitude per step"
@@ -572,8 +583,8 @@ def main():
         cpu = None
         if not args.no_cpu_baseline and world == 1:
             if args.workload == "cfg3":
-                run, nsl, _ = oracle_cfg3_sampler(args.cpu_max_log2)
-                sample = "1 of %d slices (oracle slicing to <=2^%d elements), numpy + OpenBLAS zgemm" % (nsl, args.cpu_max_log2)
+                run, nsl, _ = oracle_cfg3_sampler(args.cpu_max_log2, args.order if args.open_wires == 0 else "reference", args.search_trials)
+                sample = "1 of %d slices (oracle slicing to <=2^%d elements, %s order), numpy + OpenBLAS zgemm" % (nsl, args.cpu_max_log2, args.order)
             else:
                 run, nsl, _ = oracle_cfg2_sampler()
                 sample = "1 full amplitude"

@@ -266,3 +266,33 @@ def test_order_search_general_networks_and_mirror(q):
         q.optimize_contraction_order(net, method="nope")
     with pytest.raises(q.QtnError):
         q.search_order([(2, 2), (2, 2)], [[1, 2], [2, 1]], 0, 0, -1)  # ntrials < 1
+
+
+def test_order_search_random_general_networks_vs_oracle(q):
+    """Searched orders on random general networks (mixed extents, open legs, self-contractions, memory targets):
+    complete label sequence, reported cost == planner cost == oracle cost of that sequence, oracle slice rule agrees."""
+    rng = np.random.default_rng(17)
+    for trial in range(30):
+        nt = int(rng.integers(2, 10))
+        net = _random_general_network(q, rng, nt, int(rng.integers(1, 14)), int(rng.integers(0, 4)))
+        il = q.contract_rep(net)
+        arrays = [t.data for t in net.tensors]
+        shapes = [a.shape for a in arrays]
+        dims = oplan.label_dims(arrays, il)
+        ncon = len(net.contractions)
+        order, info = q.search_order(shapes, il, 24, trial, -1)
+        assert sorted(order) == list(range(1, ncon + 1))
+        nodes, steps = oplan.contraction_tree(il, order)
+        f, b, mx, _ = oplan.tree_cost(nodes, steps, dims)
+        assert (info["total_flops"], info["nslices"], round(2.0 ** info["log2_max_elems"])) == (f, 1.0, mx)
+        plan = q.ContractionPlan(shapes, il, order)
+        assert (plan.flops_per_slice, plan.bytes_per_slice) == (f, b)
+        # with a memory target: the slice set of the returned order under the deterministic rule, oracle side
+        lim = max(int(np.log2(max(mx, 2))) - 2, 1)
+        order2, info2 = q.search_order(shapes, il, 24, trial, lim)
+        nodes2, steps2 = oplan.contraction_tree(il, order2)
+        S = oplan.choose_slice_labels(nodes2, steps2, dims, lim, 1)
+        assert S == q.choose_slices(shapes, il, order2, lim, 1)
+        f2, _, _, _ = oplan.tree_cost(nodes2, steps2, dims, S)
+        nsl = int(np.prod([dims[l] for l in S])) if S else 1
+        assert (info2["flops_per_slice"], info2["nslices"]) == (f2, float(nsl))

@@ -38,4 +38,4 @@ for (M, N, K) in ((1024, 32, 1 << 16), (16, 16, 1 << 18), (4096, 24, 40), (300, 
     err = np.abs(got - want).max() / np.abs(want).max()
     worst = max(worst, err)
     assert err < 1e-12, ("kmajor", M, N, K, err)
-print("QTN_SKINNY=%s ok, worst rel err %.2e, launches %d" % (os.environ.get("QTN_SKINNY", "0"), worst, q.launch_count()))
+print("QTN_SKINNY=%s ok, worst rel err %.2e, launches %d" % (os.environ.get("QTN_SKINNY", "1 (default)"), worst, q.launch_count()))

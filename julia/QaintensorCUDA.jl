@@ -89,6 +89,64 @@ function search_order(dims::Vector{Vector{Int64}}, network::Vector{Vector{Int}};
     Int.(order[1:n[]]), (total_flops=cost[1], flops_per_slice=cost[2], nslices=cost[3], log2_max_elems=cost[4])
 end
 
+# ---- library-side network builder (qtn_net_*, csrc/network.cpp): circuit -> amplitude without Julia-side symbolics ----
+mutable struct NativeNetwork
+    h::Ptr{Cvoid}
+    function NativeNetwork(h::Ptr{Cvoid})
+        n = new(h)
+        finalizer(x -> ccall((:qtn_net_destroy, LIB), Cint, (Ptr{Cvoid},), x.h), n)
+        n
+    end
+end
+
+# GeneralTensorNetwork(tensors, contractions, openidx): pairs = [(t1, l1, t2, l2), ...], openidx = [(t, l), ...] (1-based)
+function native_network(tensors::Vector{<:Array{ComplexF64}}, pairs::Vector{NTuple{4,Int}}, openidx::Vector{NTuple{2,Int}})
+    ranks = Cint[ndims(t) for t in tensors]
+    dims = [Int64[size(t)...] for t in tensors]
+    tptr = Ptr{Cvoid}[pointer(t) for t in tensors]
+    dptr = Ptr{Int64}[pointer(d) for d in dims]
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve tensors dims begin
+        check(ccall((:qtn_net_create, LIB), Cint,
+            (Cint, Ptr{Ptr{Cvoid}}, Ptr{Cint}, Ptr{Ptr{Int64}}, Cint, Ptr{Cint}, Cint, Ptr{Cint}, Ref{Ptr{Cvoid}}),
+            length(tensors), tptr, ranks, dptr, length(pairs), Cint[x for p in pairs for x in p],
+            length(openidx), Cint[x for p in openidx for x in p], h))
+    end
+    NativeNetwork(h[])
+end
+
+# tensor_circuit!(psi, cgc), non-decomposed branch (src/tensor_circuit.jl:44-51): gates = [(iwire::Tuple, matrix), ...]
+function tensor_circuit!(net::NativeNetwork, gates::Vector{<:Tuple})
+    mats = [Matrix{ComplexF64}(g[2]) for g in gates]
+    nw = Cint[length(g[1]) for g in gates]
+    wires = Cint[w for g in gates for w in g[1]]
+    mptr = Ptr{Cvoid}[pointer(m) for m in mats]
+    GC.@preserve mats check(ccall((:qtn_net_tensor_circuit, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Cint}, Ptr{Cint}, Ptr{Ptr{Cvoid}}),
+                                  net.h, length(gates), nw, wires, mptr))
+    net
+end
+
+close_wires!(net::NativeNetwork, bits) = (check(ccall((:qtn_net_close, LIB), Cint, (Ptr{Cvoid}, Ptr{Cint}), net.h, Cint.(bits))); net)
+
+# optimize_contraction_order!(net): method = :treewidth (reference, bit-exact) or :search (extension)
+function optimize_contraction_order!(net::NativeNetwork; method::Symbol=:treewidth, ntrials::Integer=256, seed::Integer=0,
+                                     max_log2_elems::Integer=-1)
+    check(ccall((:qtn_net_optimize_order, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, UInt64, Cint),
+                net.h, method == :search ? 1 : 0, ntrials, UInt64(seed), max_log2_elems))
+    net
+end
+
+# contract(net) (src/contract.jl:242-264); nout = product of the open legs' extents (1 for a closed network)
+function contract(net::NativeNetwork, nout::Integer=1; max_log2_elems::Integer=-1)
+    out = Vector{ComplexF64}(undef, max(nout, 1))
+    rank = Ref{Cint}(0)
+    odims = zeros(Int64, 64)
+    check(ccall((:qtn_net_contract, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Cvoid}, Ref{Cint}, Ptr{Int64}),
+                net.h, QTN_C128, max_log2_elems, out, rank, odims))
+    r = Int(rank[])
+    r == 0 ? fill(out[1]) : reshape(out, Tuple(odims[1:r]))
+end
+
 # ---- LinearAlgebra.svd + tail-norm rule (src/svd.jl:26-33) + max-bond cap (extension) ------------------
 function svd_trunc(A::Matrix{ComplexF64}; er::Float64=-1.0, maxdim::Integer=0)
     m, n = size(A)

@@ -20,6 +20,14 @@ import sys
 import tempfile
 import time
 
+# The CPU legs (``--impl reference`` and the in-line ``cpu_baseline``) must use every host core: torchrun exports
+# OMP_NUM_THREADS=1 to its workers, and OpenBLAS sizes its pool when numpy is first imported -- so fix the
+# environment BEFORE that import.  The GPU arm's own work never depends on the host BLAS.
+_HOST_CORES = os.cpu_count() or 1
+if "reference" in sys.argv or int(os.environ.get("RANK", "0")) == 0:
+    for _k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_k] = str(_HOST_CORES)
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -38,8 +46,11 @@ def parse():
     ap.add_argument("--slices-per-step", type=int, default=1)
     ap.add_argument("--max-log2", type=int, default=31,
                     help="slice until the largest tensor has <= 2^k elements (31: 2048 slices, 1.05x flop overhead, 109 GB arena)")
-    ap.add_argument("--cpu-max-log2", type=int, default=26, help="slicing level of the CPU baseline sample")
+    ap.add_argument("--cpu-max-log2", type=int, default=27,
+                    help="slicing level of the CPU sample (one sub-slice of the arm's slice; rate is converted at the arm's flop count)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true",
+                    help="default (cfg3) run only: skip the cfg4 / cfg5 measurements that fill the line's `secondary` object")
     ap.add_argument("--open-wires", type=int, default=0,
                     help="cfg2 only: leave the first K output wires open -> 2^K amplitudes per contraction (SURVEY 8f item 2)")
     ap.add_argument("--order", default="reference", choices=["reference", "search"],
@@ -111,32 +122,94 @@ def cpu_threads():
         return os.cpu_count() or 1
 
 
-def oracle_cfg3_sampler(max_log2, order_mode="reference", search_trials=512):
-    """CPU arm: the oracle's per-slice tree execution (numpy transpose + OpenBLAS zgemm, all
-    host threads) on ONE slice of the same amplitude; returns (run_one_slice, nslices, flops).
-    order_mode "search": the same searched label sequence the GPU arm uses (host-only planner call,
-    no device code involved), so that both arms execute the same tree."""
+def blas_info():
+    """BLAS library / version / threading layer behind numpy (BASELINE.md section 2 asks for it)."""
+    try:
+        from threadpoolctl import threadpool_info
+        for i in threadpool_info():
+            if i.get("user_api") == "blas":
+                return "%s %s (%s, %s)" % (i.get("internal_api"), i.get("version"), i.get("threading_layer"), i.get("architecture"))
+    except Exception:
+        pass
+    return "unknown"
+
+
+class blas_threads:
+    """Context manager: run the enclosed CPU sample with exactly `n` BLAS threads."""
+
+    def __init__(self, n):
+        self.n = n
+
+    def __enter__(self):
+        try:
+            from threadpoolctl import threadpool_limits
+            self.ctx = threadpool_limits(limits=self.n, user_api="blas")
+            self.ctx.__enter__()
+        except Exception:
+            self.ctx = None
+
+    def __exit__(self, *a):
+        if self.ctx is not None:
+            self.ctx.__exit__(*a)
+
+
+def cfg3_name(args):
+    name = "cfg3: 36-qubit 6x6 RQC, 16 cycles, single amplitude, reference treewidth order, sliced"
+    if args.order == "search":
+        name = name.replace("reference treewidth order", "EXTENSION searched order (qtn_order_search, %d trials)" % args.search_trials)
+    return name
+
+
+def cfg3_cpu_measure(args, budget_s, min_reps=2, max_reps=20, steps=None):
+    """CPU leg shared by `--impl reference` and the in-line `cpu_baseline`.
+
+    The arm's unit of work is one slice at `--max-log2` (2^31 elements: 1.5e14 flop, a 109 GB arena) -- minutes of
+    CPU time -- so the bounded sample is ONE SUB-SLICE of it: the oracle's slice rule is nested, the labels chosen
+    at 2^`cpu_max_log2` extend the arm's set.  The sample's flop rate is converted to amplitudes/s at the ARM's flop
+    count per amplitude (same tree, same slicing level), so the CPU is not charged the finer slicing's extra flops.
+    Returns a dict with the all-thread value, the 1-thread rate and what was run."""
     from oracle import circuits as ocirc, contract as oc, network2graph as o2g, plan as op
     net, _, _ = ocirc.cfg3_network()
     order = None
-    if order_mode == "search":
+    if args.order == "search":
         import __graft_entry__ as graft
         q = graft.load_package()
         il = oc.contract_rep(net)
-        order, _ = q.search_order([t.data.shape for t in net.tensors], il, search_trials, 0, max_log2)
+        order, _ = q.search_order([t.data.shape for t in net.tensors], il, args.search_trials, 0, args.max_log2)
     else:
         o2g.optimize_contraction_order(net)
         il = oc.contract_rep(net)
     arrays = [t.data for t in net.tensors]
-    nodes, steps = op.contraction_tree(il, order)
+    nodes, tsteps = op.contraction_tree(il, order)
     dims = op.label_dims(arrays, il)
-    S = op.choose_slice_labels(nodes, steps, dims, max_log2, 1)
-    f, _, _, _ = op.tree_cost(nodes, steps, dims, S)
+    S_arm = op.choose_slice_labels(nodes, tsteps, dims, args.max_log2, 1)
+    f_arm, _, _, _ = op.tree_cost(nodes, tsteps, dims, S_arm)
+    flops_per_amp = f_arm * 2.0 ** len(S_arm)
+    S = op.choose_slice_labels(nodes, tsteps, dims, min(args.cpu_max_log2, args.max_log2), 1)
+    f, _, _, _ = op.tree_cost(nodes, tsteps, dims, S)
     nsl = 2 ** len(S)
 
     def run(sid):
-        return op.execute_tree(arrays, il, nodes, steps, op.slice_assignment(S, dims, sid % nsl))
-    return run, nsl, f
+        return op.execute_tree(arrays, il, nodes, tsteps, op.slice_assignment(S, dims, sid % nsl))
+    run(0)  # warm-up (page faults, BLAS pool)
+    t0 = time.perf_counter()
+    n = 0
+    while (steps is not None and n < steps) or (steps is None and (n < min_reps or (time.perf_counter() - t0 < budget_s and n < max_reps))):
+        run(1 + n)
+        n += 1
+    dt = (time.perf_counter() - t0) / n
+    rate = f / dt
+    # 1-thread figure on a smaller sub-slice (bounded: ~10 s), BASELINE.md section 2
+    S1 = op.choose_slice_labels(nodes, tsteps, dims, min(24, args.max_log2), 1)
+    f1, _, _, _ = op.tree_cost(nodes, tsteps, dims, S1)
+    with blas_threads(1):
+        t1 = time.perf_counter()
+        op.execute_tree(arrays, il, nodes, tsteps, op.slice_assignment(S1, dims, 0))
+        dt1 = time.perf_counter() - t1
+    return {"value": rate / flops_per_amp, "seconds_per_sample": dt, "samples": n, "sample_flops": f, "gflops": rate / 1e9,
+            "gflops_1_thread": f1 / dt1 / 1e9, "flops_per_amplitude": flops_per_amp, "arm_slices": 2 ** len(S_arm),
+            "sub_slices_per_arm_slice": nsl // 2 ** len(S_arm), "cpu_level": min(args.cpu_max_log2, args.max_log2),
+            "threads": cpu_threads(), "blas": blas_info()}
 
 
 def oracle_cfg2_sampler():
@@ -205,16 +278,17 @@ def run_reference_cfg4(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": cfg4_name(args), "note": "oracle port (numpy zgemm + LAPACK zgesdd); each step = %d central gates, "
                        "value = gates/(sites-1)/time" % ng},
-            "cpu_baseline": {"value": val, "unit": "layers/s", "cores": cpu_threads(), "kind": "port",
+            "cpu_baseline": {"value": val, "unit": "layers/s", "cores": cpu_threads(), "kind": "port", "blas": blas_info(),
                              "sample": "%d of %d gates of one layer per step" % (ng, args.sites - 1)},
             "e2e": {"value": val, "unit": "layers/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
-def run_cfg4(args, q, _lib, torch, ext):
-    """MPS path (single GPU: it does not shard -- replicas only)."""
+def run_cfg4(args, q, _lib, torch, ext, nsteps=None, nwarm=None, N=None):
+    """MPS path (single GPU: it does not shard -- replicas only).  Returns the JSON line (dict)."""
     rng = np.random.default_rng(20261017 + 4000)
-    N, chi = args.sites, args.chi
+    N, chi = (N or args.sites), args.chi
+    args = argparse.Namespace(**{**vars(args), "sites": N, "steps": nsteps or args.steps, "warmup": nwarm if nwarm is not None else args.warmup})
     mps = q.DeviceMPS(saturated_mps(N, chi, rng), chi)
     halves = [q.brickwork_layer_sites(N, 0), q.brickwork_layer_sites(N, 1)]
 
@@ -263,16 +337,23 @@ def run_cfg4(args, q, _lib, torch, ext):
                          "kernel": "jacobi_round_kernel", "peak_source": "FP64 DMMA ceiling measured in this run",
                          "note": "achieved = SURVEY 8(d) model flops per layer (sweep-independent SVD count) / time"},
             "cpu_baseline": cpu}
-    print(json.dumps(line))
+    mps.close()
+    return line
 
 
-def run_cfg5(args, q, _lib, torch, ext):
-    """cfg 5: TFI MPO (D = 3) applied to an MPS at chi, compressed back to chi, plus <psi|H|psi>."""
+def run_cfg5(args, q, _lib, torch, ext, nsteps=None, nwarm=None, N=None):
+    """cfg 5: TFI MPO (D = 3) applied to an MPS at chi, compressed back to chi, plus <psi|H|psi>.  Returns the line."""
     rng = np.random.default_rng(20261017 + 5000)
-    N, chi = args.sites, args.chi
+    N, chi = (N or args.sites), args.chi
+    args = argparse.Namespace(**{**vars(args), "sites": N, "steps": nsteps or args.steps, "warmup": nwarm if nwarm is not None else args.warmup})
     sites = saturated_mps(N, chi, rng)
     mpo = q.tfi_mpo(N, 1.0, 1.0)
     mps = q.DeviceMPS(sites, chi)
+    nrm2 = mps.overlap(mps).real          # normalise the random state so that <H> is an energy, not a scale
+    sites[N // 2] = sites[N // 2] / np.sqrt(nrm2)
+    mps.close()
+    mps = q.DeviceMPS(sites, chi)
+    e_before = mps.expect_mpo(mpo)
 
     def step():
         mps.apply_mpo(mpo, er=1e-10, maxdim=chi)
@@ -285,8 +366,10 @@ def run_cfg5(args, q, _lib, torch, ext):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(ext)
     t0 = time.perf_counter()
+    discs = []
     for _ in range(args.steps):
-        val = step()
+        discs = mps.apply_mpo(mpo, er=1e-10, maxdim=chi)
+        val = mps.expect_mpo(mpo)
     e1.record(ext)
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
@@ -331,7 +414,9 @@ def run_cfg5(args, q, _lib, torch, ext):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "cfg5: %d-site TFI MPO (D=3, J=h=1) x MPS chi=%d, compress er=1e-10 to chi, <H>" % (N, chi),
-                       "initial_state": "random MPS, saturated bond profile", "energy": [val.real, val.imag],
+                       "initial_state": "random MPS, saturated bond profile, normalised",
+                       "energy_before": [e_before.real, e_before.imag], "energy_after_last_apply": [val.real, val.imag],
+                       "max_discarded_weight": float(max(discs)) if discs else 0.0,
                        "model_flops_per_apply": flops, "l2": "fat sites (chi*D)^2*2*16 B = %.0f MB exceed L2" % (chi * 3 * chi * 3 * 32 / 1e6),
                        "parallelism": "single GPU (sequential sweep; replicas only)"},
             "clocks": clocks, "e2e": {"value": args.steps / wall, "unit": "applies/s", "h2d_bytes_per_step": int(sum(w.size for w in mpo) * 16 * 2),
@@ -341,27 +426,56 @@ def run_cfg5(args, q, _lib, torch, ext):
                          "kernel": "jacobi_round_kernel", "peak_source": "FP64 DMMA ceiling measured in this run",
                          "note": "achieved = thin-SVD model flops (sweep-independent) of the two sweeps / time"},
             "cpu_baseline": cpu}
-    print(json.dumps(line))
+    mps.close()
+    return line
+
+
+def cfg3_config(args, world, n_slice_labels, flops_per_slice, max_log2):
+    """`config` of the cfg3 line -- built from numbers both arms can compute (the oracle's planner and the product's
+    planner agree on the slice set and its cost, tests/test_host_planner.py), so the two arms print the same dict."""
+    return {"workload": cfg3_name(args), "slices_per_amplitude": int(2 ** n_slice_labels), "slice_labels": int(n_slice_labels),
+            "max_tensor_elems_log2": int(max_log2), "flops_per_slice": float(flops_per_slice),
+            "flops_per_amplitude": float(flops_per_slice) * 2.0 ** n_slice_labels, "order": args.order,
+            "l2": "per-slice intermediates (tensors of up to 2^%d elements, %.1f GB each) exceed the 126 MB L2; no explicit flush"
+                  % (max_log2, 16.0 * 2.0 ** max_log2 / 1e9),
+            "value_definition": "(slices processed / slices per amplitude) / time; a full amplitude is %d slices; "
+                                "a CPU step is one sub-slice, converted at this config's flops_per_amplitude" % 2 ** n_slice_labels,
+            "parallelism": "slice-parallel x%d, one 16-byte ncclAllReduce per step" % world}
 
 
 def run_reference(args):
     """`--impl reference`: the reference's CPU path.  Julia cannot run here (no `julia` binary,
     arithmetic in un-vendored packages), so this times the oracle restatement -- the same
-    algorithm class (pairwise TTGT, OpenBLAS zgemm) -- on the host cores.  Rank 0 only."""
+    algorithm class (pairwise TTGT, OpenBLAS zgemm) -- on ALL host cores (the BLAS thread count is
+    set explicitly at import time, see the top of this file).  Rank 0 only."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
     if args.workload == "cfg4":
         return run_reference_cfg4(args)
     if args.workload == "cfg3":
-        run, nsl, flops = oracle_cfg3_sampler(args.cpu_max_log2, args.order, args.search_trials)
-        sample = "1 of %d slices per step (oracle slicing to <=2^%d elements), all host BLAS threads" % (nsl, args.cpu_max_log2)
-        name = "cfg3: 36-qubit 6x6 RQC, 16 cycles, single amplitude, reference treewidth order, sliced"
-        if args.order == "search":
-            name = name.replace("reference treewidth order", "EXTENSION searched order (qtn_order_search, %d trials)" % args.search_trials)
-    else:
-        run, nsl, flops = oracle_cfg2_sampler()
-        sample = "1 full amplitude per step"
-        name = "cfg2: 24-qubit brickwork depth 20, single amplitude, reference treewidth order"
+        # W untimed + K timed steps, each = one sub-slice of the arm's slice (see cfg3_cpu_measure)
+        from oracle import circuits as ocirc, contract as oc, network2graph as o2g, plan as op
+        t_all = time.perf_counter()
+        m = cfg3_cpu_measure(args, 0.0, steps=args.steps + args.warmup)   # mean over W + K identical samples
+        dt_step = m["seconds_per_sample"]
+        val = m["value"]
+        n_labels = int(np.log2(m["arm_slices"]))
+        config = cfg3_config(args, args.gpus, n_labels, m["flops_per_amplitude"] / m["arm_slices"], args.max_log2)
+        sample = ("per step: 1 of the %d sub-slices (<=2^%d elements, %.3g flop) of one of the arm's %d slices; %d BLAS threads, %s; "
+                  "%.1f GFLOP/s (1 thread: %.1f GFLOP/s); value = flop rate / flops_per_amplitude of the arm's config"
+                  % (m["sub_slices_per_arm_slice"], m["cpu_level"], m["sample_flops"], m["arm_slices"], m["threads"], m["blas"],
+                     m["gflops"], m["gflops_1_thread"]))
+        line = {"impl": "reference", "metric": "amplitudes/s", "value": val, "unit": "amplitudes/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt_step, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": val, "unit": "amplitudes/s", "cores": m["threads"], "kind": "port", "sample": sample,
+                                 "gflops": m["gflops"], "gflops_1_thread": m["gflops_1_thread"], "blas": m["blas"],
+                                 "host_cores": _HOST_CORES},
+                "e2e": {"value": val, "unit": "amplitudes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "wall_s": time.perf_counter() - t_all}
+        print(json.dumps(line))
+        return
+    run, nsl, flops = oracle_cfg2_sampler()
     for i in range(args.warmup):
         run(i)
     t0 = time.perf_counter()
@@ -372,11 +486,34 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "amplitudes/s", "value": val, "unit": "amplitudes/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": name, "cpu_slices_per_amplitude": nsl, "flops_per_step": flops,
-                       "note": "oracle port of the reference CPU path (Julia unavailable); value = steps/slices_per_amplitude/time"},
-            "cpu_baseline": {"value": val, "unit": "amplitudes/s", "cores": cpu_threads(), "kind": "port", "sample": sample},
+            "config": {"workload": "cfg2: 24-qubit brickwork depth 20, single amplitude, reference treewidth order", "flops_per_step": flops,
+                       "note": "oracle port of the reference CPU path (Julia unavailable)"},
+            "cpu_baseline": {"value": val, "unit": "amplitudes/s", "cores": cpu_threads(), "kind": "port", "blas": blas_info(),
+                             "sample": "1 full amplitude per step"},
             "e2e": {"value": val, "unit": "amplitudes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
+
+
+def multi_rank_parity_check(q, rank, world):
+    """Before timing: the complete cfg-2 amplitude (24 qubits, depth 20), sliced into >= 64 slices, summed over ALL
+    ranks through the public sliced entry point (per-rank slice block + one NCCL allreduce) and compared with the
+    committed golden value (tests/golden/golden_r01.json, written by the oracle).  Proves the N-rank sum, not just
+    its speed."""
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "golden_r01.json")))["cfg2"]
+    net, _, _ = q.circuits.cfg2_network()
+    q.optimize_contraction_order(net)
+    il = q.contract_rep(net)
+    arrays = [t.data for t in net.tensors]
+    shapes = [a.shape for a in arrays]
+    S = q.choose_slices(shapes, il, None, 12, 64)
+    plan = q.ContractionPlan(shapes, il, None, S)
+    res = plan.contract_sliced(arrays, rank, world, 0, plan.nslices)
+    plan.close()
+    want = complex(*g["amplitude"])
+    got = complex(np.asarray(res).reshape(-1)[0])
+    return {"network": "cfg2 (24 qubits, depth 20), full amplitude", "slices": int(plan.nslices), "ranks": world,
+            "slice_labels_match_golden": list(S) == list(g["slices_2^12_min64"]),
+            "rel_err": abs(got - want) / abs(want), "golden": "tests/golden/golden_r01.json:cfg2.amplitude"}
 
 
 def main():
@@ -412,7 +549,7 @@ def main():
     ext = torch.cuda.ExternalStream(_lib.stream_ptr())
     if args.workload in ("cfg4", "cfg5"):
         if rank == 0:
-            (run_cfg4 if args.workload == "cfg4" else run_cfg5)(args, q, _lib, torch, ext)
+            print(json.dumps((run_cfg4 if args.workload == "cfg4" else run_cfg5)(args, q, _lib, torch, ext)))
         if world > 1:
             dist.barrier()
             dist.destroy_process_group()
@@ -476,6 +613,7 @@ def main():
             plan.close()
             S, plan = make_plan(level)
     sps = args.slices_per_step if plan.nslices > 1 else 1
+    parity = multi_rank_parity_check(q, rank, world) if args.workload == "cfg3" and args.open_wires == 0 else None
     plan.upload(arrays)
     out = torch.zeros(2 * plan.out_numel, dtype=torch.float64 if args.precision == "c128" else torch.float32, device="cuda")
 
@@ -582,36 +720,61 @@ def main():
                      "whole_slice_tflops": plan.flops_per_slice / (ms * 1e-3 / (args.steps * sps)) / 1e12})
         cpu = None
         if not args.no_cpu_baseline and world == 1:
-            if args.workload == "cfg3":
-                run, nsl, _ = oracle_cfg3_sampler(args.cpu_max_log2, args.order if args.open_wires == 0 else "reference", args.search_trials)
-                sample = "1 of %d slices (oracle slicing to <=2^%d elements, %s order), numpy + OpenBLAS zgemm" % (nsl, args.cpu_max_log2, args.order)
-            else:
+            if args.workload == "cfg3" and args.open_wires == 0:
+                m = cfg3_cpu_measure(args, 12.0)
+                cpu = {"value": m["value"], "unit": "amplitudes/s", "cores": m["threads"], "kind": "port",
+                       "gflops": m["gflops"], "gflops_1_thread": m["gflops_1_thread"], "blas": m["blas"], "host_cores": _HOST_CORES,
+                       "sample": "%d x 1 of the %d sub-slices (<=2^%d elements, %.3g flop, %.2f s each) of one of the %d slices; numpy "
+                                 "transpose + OpenBLAS zgemm; value = flop rate / flops_per_amplitude of this config"
+                                 % (m["samples"], m["sub_slices_per_arm_slice"], m["cpu_level"], m["sample_flops"], m["seconds_per_sample"],
+                                    m["arm_slices"])}
+            elif args.workload == "cfg2" and args.open_wires == 0:
                 run, nsl, _ = oracle_cfg2_sampler()
-                sample = "1 full amplitude"
-            run(1)
-            t0 = time.perf_counter()
-            nrep = 0
-            while nrep < 2 or (time.perf_counter() - t0 < 10 and nrep < 20):
-                run(nrep)
-                nrep += 1
-            cdt = (time.perf_counter() - t0) / nrep
-            cpu = {"value": 1.0 / (nsl * cdt), "unit": "amplitudes/s", "cores": cpu_threads(), "kind": "port",
-                   "sample": sample + "; %.2f s per sample" % cdt}
+                run(1)
+                t0 = time.perf_counter()
+                nrep = 0
+                while nrep < 2 or (time.perf_counter() - t0 < 10 and nrep < 20):
+                    run(nrep)
+                    nrep += 1
+                cdt = (time.perf_counter() - t0) / nrep
+                cpu = {"value": 1.0 / (nsl * cdt), "unit": "amplitudes/s", "cores": cpu_threads(), "kind": "port", "blas": blas_info(),
+                       "sample": "1 full amplitude; %.2f s per sample" % cdt}
+        if args.workload == "cfg3" and args.open_wires == 0:
+            config = cfg3_config(args, world, len(S), plan.flops_per_slice, int(np.log2(plan.max_elems)))
+        else:
+            config = {"workload": name, "slices_per_amplitude": plan.nslices, "slice_labels": len(S),
+                      "max_tensor_elems_log2": int(np.log2(plan.max_elems)), "flops_per_slice": plan.flops_per_slice,
+                      "l2": "per-slice intermediates (%.1f GB arena) exceed the 126 MB L2; no explicit flush" % (plan.arena_bytes / 1e9)
+                            if plan.arena_bytes > 2e8 else "working set fits L2 (latency-bound workload); no flush",
+                      "parallelism": "slice-parallel x%d, one %d-byte ncclAllReduce per step" % (world, 16 * plan.out_numel),
+                      "order": args.order}
+        details = {"slices_per_step_per_gpu": sps, "pairwise_steps_per_slice": plan.nsteps - plan.n_invariant,
+                   "arena_gb": plan.arena_bytes / 1e9, "order_search": search_info}
+        # ---- secondary workloads of the BASELINE metric ("MPS brickwork layers/s at chi=512"; cfg 5) ----
+        secondary = None
+        if args.workload == "cfg3" and args.open_wires == 0 and args.order == "reference" and not args.no_secondary:
+            plan.close()
+            del out
+            torch.cuda.empty_cache()
+            secondary = {}
+            for key, fn, kw in (("cfg4", run_cfg4, {"nsteps": 3, "nwarm": 3, "N": 50}), ("cfg5", run_cfg5, {"nsteps": 1, "nwarm": 1, "N": 40})):
+                try:
+                    ln = fn(args, q, _lib, torch, ext, **kw)
+                    secondary[key] = {k: ln[k] for k in ("metric", "value", "unit", "steps", "warmup", "ms_per_step", "config", "e2e",
+                                                         "gpu_launches", "roofline", "cpu_baseline", "clocks")}
+                except Exception as exc:  # the headline line must still print
+                    secondary[key] = {"error": "%s: %s" % (type(exc).__name__, exc)}
         line = {"metric": "amplitudes/s", "value": value, "unit": "amplitudes/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64" if args.precision == "c128" else "f32", "data": "synthetic",
-                "config": {"workload": name, "slices_per_amplitude": plan.nslices, "slices_per_step_per_gpu": sps,
-                           "slice_labels": len(S), "max_tensor_elems_log2": int(np.log2(plan.max_elems)),
-                           "flops_per_slice": plan.flops_per_slice, "pairwise_steps_per_slice": plan.nsteps - plan.n_invariant,
-                           "l2": "per-slice intermediates (%.1f GB arena) exceed the 126 MB L2; no explicit flush" % (plan.arena_bytes / 1e9)
-                                 if plan.arena_bytes > 2e8 else "working set fits L2 (latency-bound workload); no flush",
-                           "value_definition": "(slices processed / slices per amplitude) / time; a full amplitude is "
-                                               "%d slices" % plan.nslices,
-                           "parallelism": "slice-parallel x%d, one %d-byte ncclAllReduce per step" % (world, 16 * plan.out_numel),
-                           "order": args.order, "order_search": search_info},
+                "config": config, "details": details,
                 "slices_per_s": args.steps * world * sps / (ms * 1e-3),
                 "clocks": clocks, "e2e": {"value": e2e_val, "unit": "amplitudes/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu}
+        if parity is not None:
+            line["parity_check"] = parity
+        if secondary is not None:
+            line["secondary"] = secondary
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

@@ -44,7 +44,8 @@ def overlap(a, b):
     """<a|b> by transfer matrices."""
     E = np.ones((1, 1), dtype=np.complex128)
     for A, B in zip(a, b):
-        E = np.einsum("xy,xpa,ypb->ab", E, np.conj(A), B)
+        T = np.tensordot(E, B, axes=(1, 0))                      # (x, p, b): two GEMM-shaped steps, O(chi^3)
+        E = np.tensordot(np.conj(A), T, axes=((0, 1), (0, 1)))   # (a, b)
     return complex(E[0, 0])
 
 
@@ -127,5 +128,8 @@ def expect_mpo(sites, mpo):
     """<psi| MPO |psi> by left environments E[la, a, lb]."""
     E = np.ones((1, 1, 1), dtype=np.complex128)
     for A, W in zip(sites, mpo):
-        E = np.einsum("xay,xqr,aqpb,yps->rbs", E, np.conj(A), W, A)
+        T = np.tensordot(E, A, axes=(2, 0))                      # (x, a, p, s)
+        T = np.tensordot(T, W, axes=((1, 2), (0, 2)))            # (x, s, q, b)
+        E = np.tensordot(np.conj(A), T, axes=((0, 1), (0, 2)))   # (r, s, b)
+        E = np.transpose(E, (0, 2, 1))                           # (r, b, s)
     return complex(E[0, 0, 0])

@@ -390,6 +390,344 @@ jacobi_round_kernel(const SvdProblem* __restrict__ probs, int round, double tol,
     }
 }
 
+// =============================================================================================================
+// Split round (default): the same block schedule as above, but the three phases are three kernels, so the
+// tensor-pipe work (Gram, update) streams at GEMM efficiency and the latency-bound 32 x 32 eigensolves of ALL block
+// pairs of a round run side by side instead of idling the DMMA pipe of the CTA that owns the pair:
+//   jacobi_gram_kernel    partial Grams of every active (matrix, pair), rows split over S CTAs; operands go
+//                         global -> registers as DMMA fragments (each element is read exactly once), no shared-memory
+//                         staging and no barrier in the main loop; fixed-order cross-warp tree -> deterministic sums
+//   jacobi_eig_kernel     one CTA per (matrix, pair): G = sum of the S partials (fixed order), Hermitian Jacobi sweep,
+//                         W and the pair's "apply" flag to global memory, convergence stamps
+//   jacobi_update_kernel  P <- P W for the A panel and the V panel, 8-row groups per warp, W in shared memory
+// =============================================================================================================
+constexpr int GP_ELEMS = 10 * 64;   // upper block triangle of the 4 x 4 grid of 8 x 8 blocks of a 32 x 32 Gram
+constexpr int GRAM_THREADS = 128;
+
+// block pair of `pair` in `round` (circle method); false when this (round, pair) has nothing to do for the problem
+__device__ __forceinline__ bool round_pair(const SvdProblem& pr, int round, int pair, int& bi, int& bj) {
+    const int nb = pr.nblocks;
+    if (nb < 2 || pair >= nb / 2 || round >= nb - 1) return false;
+    if (pair == 0) { bi = nb - 1; bj = round; }
+    else { bi = (round + pair) % (nb - 1); bj = (round - pair + (nb - 1)) % (nb - 1); }
+    if (bi > bj) { const int t = bi; bi = bj; bj = t; }
+    return bi * JB < pr.n;  // false: padding block only
+}
+// a pair verified converged stays converged until one of its two blocks is rotated again
+__device__ __forceinline__ bool pair_idle(const SvdProblem& pr, int bi, int bj) {
+    return max(pr.last_mod[bi], pr.last_mod[bj]) < pr.last_ok[bi * pr.nblocks + bj];
+}
+
+__global__ void __launch_bounds__(GRAM_THREADS, 2)
+jacobi_gram_kernel(const SvdProblem* __restrict__ probs, int round, const int* __restrict__ rotated, int S, int maxpairs,
+                   double2* __restrict__ Gpart) {
+    const int b = blockIdx.y, pair = blockIdx.x / S, split = blockIdx.x - pair * S;
+    if (rotated[b] < 0) return;  // matrix converged in an earlier sweep
+    const SvdProblem pr = probs[b];
+    int bi, bj;
+    if (!round_pair(pr, round, pair, bi, bj) || pair_idle(pr, bi, bj)) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+    const int m = pr.m;
+    // lane (g, t) holds P[row 4s + t][column 8i + g] of every 16-row group: the A fragment (as conj) and the B fragment
+    // of mma.m8n8k4 coincide, so one 16-byte load per (s, i) feeds all ten blocks
+    const double2* cp[4];
+    bool cv[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int col = panel_col(i * 8 + g, bi, bj, pr.n);
+        cv[i] = col >= 0;
+        cp[i] = pr.A + (size_t)(col >= 0 ? col : 0) * m;
+    }
+    const int ngroups = (m + 15) >> 4, gper = (ngroups + S - 1) / S;
+    const int g0 = split * gper, g1 = min(ngroups, g0 + gper);
+    double gr[10][2], gi[10][2];
+#pragma unroll
+    for (int k = 0; k < 10; ++k) gr[k][0] = gr[k][1] = gi[k][0] = gi[k][1] = 0.0;
+    double2 v[4][4], w[4][4];
+    auto load = [&](double2 (&dst)[4][4], int grp) {
+        const int r = grp * 16 + t;
+#pragma unroll
+        for (int s = 0; s < 4; ++s)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int row = r + 4 * s;
+                dst[s][i] = (cv[i] && row < m) ? __ldcg(cp[i] + row) : make_double2(0.0, 0.0);
+            }
+    };
+    auto compute = [&](const double2 (&f)[4][4]) {
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+            int k = 0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = i; j < 4; ++j, ++k) {
+                    dmma(gr[k][0], gr[k][1], f[s][i].x, f[s][j].x);
+                    dmma(gr[k][0], gr[k][1], f[s][i].y, f[s][j].y);
+                    dmma(gi[k][0], gi[k][1], f[s][i].x, f[s][j].y);
+                    dmma(gi[k][0], gi[k][1], -f[s][i].y, f[s][j].x);
+                }
+        }
+    };
+    int grp = g0 + warp;
+    constexpr int NW = GRAM_THREADS / 32;
+    if (grp < g1) load(v, grp);
+    while (grp < g1) {  // register double buffering: the next group's 16 loads are in flight during the 160 DMMAs
+        if (grp + NW < g1) load(w, grp + NW);
+        compute(v);
+        grp += NW;
+        if (grp >= g1) break;
+        if (grp + NW < g1) load(v, grp + NW);
+        compute(w);
+        grp += NW;
+    }
+    // fixed-order tree over the 4 warps (deterministic, unlike atomics): 3+2 -> 1+0, then 1 -> 0
+    __shared__ double red[2][40][32];
+#pragma unroll
+    for (int stage = 0; stage < 2; ++stage) {
+        const int half = stage == 0 ? 2 : 1;  // warps [half, 2*half) hand over to warps [0, half)
+        if (warp >= half && warp < 2 * half) {
+#pragma unroll
+            for (int k = 0; k < 10; ++k) {
+                red[warp - half][4 * k + 0][lane] = gr[k][0];
+                red[warp - half][4 * k + 1][lane] = gr[k][1];
+                red[warp - half][4 * k + 2][lane] = gi[k][0];
+                red[warp - half][4 * k + 3][lane] = gi[k][1];
+            }
+        }
+        __syncthreads();
+        if (warp < half) {
+#pragma unroll
+            for (int k = 0; k < 10; ++k) {
+                gr[k][0] += red[warp][4 * k + 0][lane];
+                gr[k][1] += red[warp][4 * k + 1][lane];
+                gi[k][0] += red[warp][4 * k + 2][lane];
+                gi[k][1] += red[warp][4 * k + 3][lane];
+            }
+        }
+        __syncthreads();
+    }
+    if (warp == 0) {  // block k as 8 x 8 row-major: lane (g, t) owns columns 2t, 2t+1 of row g -> 32 contiguous bytes
+        double2* out = Gpart + ((size_t)((size_t)b * maxpairs + pair) * S + split) * GP_ELEMS;
+#pragma unroll
+        for (int k = 0; k < 10; ++k) {
+            out[k * 64 + g * 8 + 2 * t] = make_double2(gr[k][0], gi[k][0]);
+            out[k * 64 + g * 8 + 2 * t + 1] = make_double2(gr[k][1], gi[k][1]);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(JTHREADS)
+jacobi_eig_kernel(const SvdProblem* __restrict__ probs, int round, double tol, int* __restrict__ rotated,
+                  const double* __restrict__ fro2, int inner_sweeps, int* __restrict__ stat, int stamp, int S, int maxpairs,
+                  const double2* __restrict__ Gpart, double2* __restrict__ Wbuf, int* __restrict__ pflag) {
+    const int b = blockIdx.y, pair = blockIdx.x, tid = threadIdx.x;
+    int* flag = pflag + (size_t)b * maxpairs + pair;
+    const SvdProblem pr = probs[b];
+    int bi = 0, bj = 0;
+    const bool live = rotated[b] >= 0 && round_pair(pr, round, pair, bi, bj);
+    if (!live || pair_idle(pr, bi, bj)) {
+        if (tid == 0) {
+            *flag = 0;
+            if (live && stat) atomicAdd(&stat[0], 1);
+        }
+        return;
+    }
+    const int nb = pr.nblocks;
+    const double dthr = 1e-30 * fro2[b];  // deflation threshold, see jacobi_round_kernel
+    __shared__ double2 G[JP * JPITCH], W[JP * JPITCH];
+    __shared__ double2 rot[JB], rph[JB];
+    __shared__ int s_pq[2 * JB];
+    __shared__ int s_any, s_sweep_any, s_rot;
+    __shared__ int s_cols[JP];
+    if (tid < JP) s_cols[tid] = panel_col(tid, bi, bj, pr.n);
+    if (tid == 0) { s_any = 0; s_rot = 0; }
+    for (int i = tid; i < JP * JPITCH; i += JTHREADS) W[i] = make_double2(0, 0);
+    {
+        const double2* gp = Gpart + (size_t)((size_t)b * maxpairs + pair) * S * GP_ELEMS;
+        for (int e = tid; e < GP_ELEMS; e += JTHREADS) {
+            double2 acc = make_double2(0, 0);
+            for (int s = 0; s < S; ++s) {  // fixed order: deterministic
+                const double2 v = __ldcg(gp + (size_t)s * GP_ELEMS + e);
+                acc.x += v.x;
+                acc.y += v.y;
+            }
+            const int k = e >> 6, r8 = (e >> 3) & 7, c8 = e & 7;
+            // k -> (i, j), j >= i: rows of the upper block triangle hold 4, 3, 2, 1 blocks
+            const int i = k < 4 ? 0 : (k < 7 ? 1 : (k < 9 ? 2 : 3));
+            const int j = k - (i == 0 ? 0 : (i == 1 ? 4 : (i == 2 ? 7 : 9))) + i;
+            G[(i * 8 + r8) * JPITCH + j * 8 + c8] = acc;
+        }
+    }
+    __syncthreads();
+    for (int e = tid; e < JP * JP; e += JTHREADS) {  // mirror the strictly-lower block triangle, W = I
+        const int r = e / JP, c = e % JP;
+        if ((r >> 3) > (c >> 3)) { const double2 v = G[c * JPITCH + r]; G[r * JPITCH + c] = make_double2(v.x, -v.y); }
+        if (r == c) W[r * JPITCH + c] = make_double2(1.0, 0.0);
+    }
+    __syncthreads();
+    for (int sweep = 0; sweep < inner_sweeps; ++sweep) {
+        if (tid == 0) s_sweep_any = 0;
+        __syncthreads();
+        for (int step = 0; step < JP - 1; ++step) {
+            if (tid < JB) {
+                int p, q;
+                if (tid == 0) { p = JP - 1; q = step; }
+                else { p = (step + tid) % (JP - 1); q = (step - tid + (JP - 1)) % (JP - 1); }
+                if (p > q) { int tt = p; p = q; q = tt; }
+                const double alpha = G[p * JPITCH + p].x, beta = G[q * JPITCH + q].x;
+                const double2 gg = G[p * JPITCH + q];
+                const double ag2 = gg.x * gg.x + gg.y * gg.y;
+                double c = 1.0, s = 0.0;
+                double2 ph = make_double2(1.0, 0.0);
+                const bool real_cols = s_cols[p] >= 0 && s_cols[q] >= 0;  // never touch padding slots
+                if (!real_cols) {
+                    // identity
+                } else if (ag2 > tol * tol * fabs(alpha) * fabs(beta) && ag2 > 0.0 && alpha > dthr && beta > dthr) {
+                    const double rg = rsqrt(ag2), ag = ag2 * rg;
+                    ph = make_double2(gg.x * rg, gg.y * rg);
+                    const double zeta = 0.5 * (beta - alpha) * rg;
+                    const double z1 = 1.0 + zeta * zeta;
+                    double tt = 1.0 / (fabs(zeta) + z1 * rsqrt(z1));
+                    if (zeta < 0) tt = -tt;
+                    c = rsqrt(1.0 + tt * tt);
+                    s = c * tt;
+                    const double ap = alpha - tt * ag, bq = beta + tt * ag;  // de Rijk: larger diagonal entry first
+                    if (ap < bq) { const double c2 = s, s2 = -c; c = c2; s = s2; }
+                    s_sweep_any = 1;
+                    s_rot = 1;
+                } else if (alpha < beta && beta > dthr) {
+                    c = 0.0; s = -1.0;  // pure swap
+                    s_sweep_any = 1;
+                }
+                rot[tid] = make_double2(c, s);
+                rph[tid] = ph;
+                s_pq[2 * tid] = p;
+                s_pq[2 * tid + 1] = q;
+            }
+            __syncthreads();
+            {
+                const int k1 = tid >> 4, k2 = tid & 15;
+                const double c1 = rot[k1].x, s1 = rot[k1].y, c2 = rot[k2].x, s2 = rot[k2].y;
+                const bool id1 = (c1 == 1.0 && s1 == 0.0), id2 = (c2 == 1.0 && s2 == 0.0);
+                if (!(id1 && id2)) {
+                    const double2 ph1 = rph[k1], ph2 = rph[k2];
+                    const int p1 = s_pq[2 * k1], q1 = s_pq[2 * k1 + 1], p2 = s_pq[2 * k2], q2 = s_pq[2 * k2 + 1];
+                    double2 g00 = G[p1 * JPITCH + p2], g01 = G[p1 * JPITCH + q2];
+                    double2 g10 = G[q1 * JPITCH + p2], g11 = G[q1 * JPITCH + q2];
+                    auto mulph = [](double2 ph, double2 v) { return make_double2(ph.x * v.x - ph.y * v.y, ph.x * v.y + ph.y * v.x); };
+                    auto mulphc = [](double2 ph, double2 v) { return make_double2(ph.x * v.x + ph.y * v.y, ph.x * v.y - ph.y * v.x); };
+                    if (!id1) {
+                        const double2 e10 = mulph(ph1, g10), e11 = mulph(ph1, g11), f00 = mulphc(ph1, g00), f01 = mulphc(ph1, g01);
+                        const double2 n00 = make_double2(c1 * g00.x - s1 * e10.x, c1 * g00.y - s1 * e10.y);
+                        const double2 n01 = make_double2(c1 * g01.x - s1 * e11.x, c1 * g01.y - s1 * e11.y);
+                        const double2 n10 = make_double2(s1 * f00.x + c1 * g10.x, s1 * f00.y + c1 * g10.y);
+                        const double2 n11 = make_double2(s1 * f01.x + c1 * g11.x, s1 * f01.y + c1 * g11.y);
+                        g00 = n00; g01 = n01; g10 = n10; g11 = n11;
+                    }
+                    if (!id2) {
+                        const double2 e01 = mulphc(ph2, g01), e11 = mulphc(ph2, g11), f00 = mulph(ph2, g00), f10 = mulph(ph2, g10);
+                        const double2 n00 = make_double2(c2 * g00.x - s2 * e01.x, c2 * g00.y - s2 * e01.y);
+                        const double2 n10 = make_double2(c2 * g10.x - s2 * e11.x, c2 * g10.y - s2 * e11.y);
+                        const double2 n01 = make_double2(s2 * f00.x + c2 * g01.x, s2 * f00.y + c2 * g01.y);
+                        const double2 n11 = make_double2(s2 * f10.x + c2 * g11.x, s2 * f10.y + c2 * g11.y);
+                        g00 = n00; g01 = n01; g10 = n10; g11 = n11;
+                    }
+                    G[p1 * JPITCH + p2] = g00; G[p1 * JPITCH + q2] = g01;
+                    G[q1 * JPITCH + p2] = g10; G[q1 * JPITCH + q2] = g11;
+                }
+                if (!id2) {  // W <- W J (columns), rows k1 and k1 + 16
+                    const double2 ph2 = rph[k2];
+                    const int p2 = s_pq[2 * k2], q2 = s_pq[2 * k2 + 1];
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int r = k1 + 16 * h;
+                        const double2 xp = W[r * JPITCH + p2], xq = W[r * JPITCH + q2];
+                        const double2 eq = make_double2(ph2.x * xq.x + ph2.y * xq.y, ph2.x * xq.y - ph2.y * xq.x);
+                        const double2 ep = make_double2(ph2.x * xp.x - ph2.y * xp.y, ph2.x * xp.y + ph2.y * xp.x);
+                        W[r * JPITCH + p2] = make_double2(c2 * xp.x - s2 * eq.x, c2 * xp.y - s2 * eq.y);
+                        W[r * JPITCH + q2] = make_double2(s2 * ep.x + c2 * xq.x, s2 * ep.y + c2 * xq.y);
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        const int any_now = s_sweep_any;
+        if (any_now && tid == 0) s_any = 1;
+        __syncthreads();
+        if (!any_now) break;
+    }
+    const int any = s_any;
+    if (tid == 0) {
+        if (stat) atomicAdd(&stat[any ? 1 : 0], 1);
+        if (any) { pr.last_mod[bi] = stamp; pr.last_mod[bj] = stamp; }
+        else pr.last_ok[bi * nb + bj] = stamp;
+        *flag = any;
+        if (any && s_rot) rotated[b] = 1;  // pure re-ordering swaps do not keep the sweeps going
+    }
+    if (!any) return;
+    double2* wout = Wbuf + (size_t)((size_t)b * maxpairs + pair) * (JP * JP);
+    for (int e = tid; e < JP * JP; e += JTHREADS) wout[e] = W[(e >> 5) * JPITCH + (e & 31)];
+}
+
+__global__ void __launch_bounds__(JTHREADS, 2)
+jacobi_update_kernel(const SvdProblem* __restrict__ probs, int round, const int* __restrict__ rotated, int SU, int maxpairs,
+                     const double2* __restrict__ Wbuf, const int* __restrict__ pflag) {
+    const int b = blockIdx.y, pair = blockIdx.x / SU, chunk = blockIdx.x - pair * SU;
+    if (rotated[b] < 0 || pflag[(size_t)b * maxpairs + pair] == 0) return;
+    const SvdProblem pr = probs[b];
+    int bi, bj;
+    if (!round_pair(pr, round, pair, bi, bj)) return;
+    __shared__ double2 Ws[JP * JPITCH];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+    {
+        const double2* wsrc = Wbuf + (size_t)((size_t)b * maxpairs + pair) * (JP * JP);
+        for (int e = tid; e < JP * JP; e += JTHREADS) Ws[(e >> 5) * JPITCH + (e & 31)] = __ldcg(wsrc + e);
+    }
+    int colk[8], colo[4][2];  // global columns of this lane's A-fragment slots (k = 4 k4 + t) and output slots
+#pragma unroll
+    for (int k4 = 0; k4 < 8; ++k4) colk[k4] = panel_col(k4 * 4 + t, bi, bj, pr.n);
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int q = 0; q < 2; ++q) colo[j][q] = panel_col(j * 8 + 2 * t + q, bi, bj, pr.n);
+    __syncthreads();
+    // row groups of 8: first those of A (m rows), then those of V (n rows) when V is accumulated
+    const int ga = (pr.m + 7) >> 3, gv = pr.V ? (pr.n + 7) >> 3 : 0, gt = ga + gv;
+    const int gper = (gt + SU - 1) / SU, c0 = chunk * gper, c1 = min(gt, c0 + gper);
+    for (int gi = c0 + warp; gi < c1; gi += JTHREADS / 32) {
+        double2* base = gi < ga ? pr.A : pr.V;
+        const int nrows = gi < ga ? pr.m : pr.n;
+        const int row = (gi < ga ? gi : gi - ga) * 8 + g;
+        const bool rok = row < nrows;
+        double2 a[8];
+#pragma unroll
+        for (int k4 = 0; k4 < 8; ++k4)
+            a[k4] = (rok && colk[k4] >= 0) ? __ldcg(base + (size_t)colk[k4] * nrows + row) : make_double2(0.0, 0.0);
+        double cr[4][2], ci[4][2];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) cr[j][0] = cr[j][1] = ci[j][0] = ci[j][1] = 0.0;
+#pragma unroll
+        for (int k4 = 0; k4 < 8; ++k4) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const double2 bb = Ws[(k4 * 4 + t) * JPITCH + j * 8 + g];
+                dmma(cr[j][0], cr[j][1], a[k4].x, bb.x);
+                dmma(cr[j][0], cr[j][1], -a[k4].y, bb.y);
+                dmma(ci[j][0], ci[j][1], a[k4].x, bb.y);
+                dmma(ci[j][0], ci[j][1], a[k4].y, bb.x);
+            }
+        }
+        if (rok) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int q = 0; q < 2; ++q)
+                    if (colo[j][q] >= 0) base[(size_t)colo[j][q] * nrows + row] = make_double2(cr[j][q], ci[j][q]);
+        }
+    }
+}
+
 __global__ void set_int_kernel(int* p, int n, int v) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
@@ -522,7 +860,8 @@ __global__ void scatter_factors_kernel(const SvdProblem* probs, double* const* s
 // B = A^H (n x m from m x n)
 __global__ void conj_transpose_kernel(const double2* __restrict__ A, double2* __restrict__ B, int m, int n) {
     __shared__ double2 t[32][33];
-    const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
+    const int tiles_x = (m + 31) / 32;  // 1-D grid: either dimension may exceed the 65535 limit of grid.y
+    const int bx = (int)(blockIdx.x % tiles_x) * 32, by = (int)(blockIdx.x / tiles_x) * 32;
     for (int j = threadIdx.y; j < 32; j += blockDim.y) {
         const int r = bx + threadIdx.x, c = by + j;
         if (r < m && c < n) t[j][threadIdx.x] = A[(size_t)c * m + r];
@@ -648,7 +987,10 @@ int svd_batched_device(int batch, const SvdJob* jobs, double er, int64_t maxdim,
     for (int b = 0; b < batch; ++b) {
         const int64_t m0 = jobs[b].m0, n0 = jobs[b].n0;
         if (m0 < 1 || n0 < 1) return fail(QTN_EINVAL, "svd: empty matrix");
-        if (m0 > 32768 || n0 > 32768) return fail(QTN_EINVAL, "svd: matrix too large");
+        // only the Jacobi column count min(m0, n0) is bounded (block-pair tables are O(n^2 / 256)); the long
+        // dimension may be large (MPS(psi): 2 x 2^(M-1); contract_svd_mps: rows grow as 2^j) -- row offsets are 64-bit
+        if (std::min(m0, n0) > 32768 || std::max(m0, n0) > ((int64_t)1 << 30) || m0 * n0 > ((int64_t)1 << 33))
+            return fail(QTN_EINVAL, "svd: matrix too large (min dimension <= 32768, max dimension <= 2^30, <= 2^33 elements)");
         tr[b] = m0 < n0;
         const int64_t m = tr[b] ? n0 : m0, n = tr[b] ? m0 : n0;
         auto al = [&](size_t bytes) { size_t o = dev_bytes; dev_bytes += (bytes + 255) / 256 * 256; return o; };
@@ -663,6 +1005,30 @@ int svd_batched_device(int batch, const SvdJob* jobs, double er, int64_t maxdim,
         }
         maxn = std::max<int>(maxn, (int)n);
         maxm = std::max<int>(maxm, (int)m);
+    }
+    // split-round buffers: partial Grams [batch][pairs][S][640], rotations W [batch][pairs][32*32], apply flags
+    int max_nb = (maxn + JB - 1) / JB;
+    if (max_nb & 1) ++max_nb;
+    const int maxpairs = std::max(max_nb / 2, 1);
+    const bool fused = [] { const char* e = getenv("QTN_JACOBI"); return e && strcmp(e, "fused") == 0; }();
+    bool any_v = false;
+    for (int b = 0; b < batch; ++b) any_v = any_v || jobs[b].need_v || tr[b];
+    int S = 1, SU = 1;
+    {
+        // enough CTAs for ~8 per SM, but at least two 16-row (Gram) / 8-row (update) groups per warp
+        const long units = (long)maxpairs * batch, target = 148 * 8;
+        const long ngroups = (maxm + 15) / 16, ugroups = (maxm + 7) / 8 + (any_v ? (maxn + 7) / 8 : 0);
+        S = (int)std::max<long>(1, std::min<long>((target + units - 1) / units, ngroups / 8));
+        SU = (int)std::max<long>(1, std::min<long>((target + units - 1) / units, ugroups / 16));
+        if (const char* e = getenv("QTN_JACOBI_S")) S = std::max(1, atoi(e));
+        if (const char* e = getenv("QTN_JACOBI_SU")) SU = std::max(1, atoi(e));
+    }
+    size_t offG = 0, offW = 0, offF = 0;
+    if (!fused) {
+        auto al = [&](size_t bytes) { size_t o = dev_bytes; dev_bytes += (bytes + 255) / 256 * 256; return o; };
+        offG = al((size_t)batch * maxpairs * S * GP_ELEMS * 16);
+        offW = al((size_t)batch * maxpairs * JP * JP * 16);
+        offF = al((size_t)batch * maxpairs * 4);
     }
     size_t tab = dev_bytes;
     size_t tab_bytes = (size_t)batch * (sizeof(SvdProblem) + sizeof(FinishArgs) + 2 * sizeof(void*) + 8 + 8 + 8 + 4 + 4) + 1024;
@@ -719,18 +1085,16 @@ int svd_batched_device(int batch, const SvdJob* jobs, double er, int64_t maxdim,
     double* dfro = (double*)dptr(hfro);
     for (int b = 0; b < batch; ++b)
         if (tr[b]) {
-            dim3 g((unsigned)((jobs[b].m0 + 31) / 32), (unsigned)((jobs[b].n0 + 31) / 32));
+            const unsigned g = (unsigned)(((jobs[b].m0 + 31) / 32) * ((jobs[b].n0 + 31) / 32));
             conj_transpose_kernel<<<g, dim3(32, 8), 0, st>>>((const double2*)jobs[b].A, hp[b].A, (int)jobs[b].m0, (int)jobs[b].n0);
             count_launch(1);
         }
-    set_identity_kernel<<<dim3(std::min(148 * 4, (maxn * maxn + 255) / 256), batch), 256, 0, st>>>(dp);
-    fro_norm_kernel<<<dim3(std::min(148, (maxn * maxm + 255) / 256), batch), 256, 0, st>>>(dp, dfro);
+    set_identity_kernel<<<dim3((unsigned)std::min<int64_t>(148 * 4, ((int64_t)maxn * maxn + 255) / 256), batch), 256, 0, st>>>(dp);
+    fro_norm_kernel<<<dim3((unsigned)std::min<int64_t>(148, ((int64_t)maxn * maxm + 255) / 256), batch), 256, 0, st>>>(dp, dfro);
     count_launch(2);
     const size_t smem = (size_t)(2 * JP * JRP + 2 * JP * JPITCH + 2 * JB) * 16 + JB * 8 + 64;
     static bool attr = false;
     if (!attr) { CUDA_TRY(cudaFuncSetAttribute(jacobi_round_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
-    int max_nb = (maxn + JB - 1) / JB;
-    if (max_nb & 1) ++max_nb;
     double tol = 1e-15 * std::sqrt((double)std::max(maxm, 1)) * 0.5 + 2.3e-16;
     if (const char* e = getenv("QTN_JACOBI_TOL")) tol *= atof(e);
     // cluster size: split the panel rows over up to 8 CTAs when the (pairs x batch) grid alone cannot
@@ -747,11 +1111,25 @@ int svd_batched_device(int batch, const SvdJob* jobs, double er, int64_t maxdim,
     if (const char* e = getenv("QTN_JACOBI_INNER")) inner = std::max(1, atoi(e));
     int sweeps = 0, stamp = 1;
     const int kMaxSweeps = 60;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    if (dstat) { cudaEventCreate(&ev0); cudaEventCreate(&ev1); cudaEventRecord(ev0, st); }
     if (max_nb >= 2) {
         for (; sweeps < kMaxSweeps; ++sweeps) {
             // flags: 0 = no rotation yet this sweep, 1 = rotated, -1 = converged (its CTAs exit at once)
             CUDA_TRY(cudaMemcpyAsync(drot, hrot, (size_t)batch * 4, cudaMemcpyHostToDevice, st));
-            for (int round = 0; round < max_nb - 1; ++round) {
+            for (int round = 0; round < max_nb - 1 && !fused; ++round) {
+                ++stamp;
+                int* st_ptr = dstat ? dstat + 2 * sweeps : (int*)nullptr;
+                jacobi_gram_kernel<<<dim3((unsigned)(maxpairs * S), (unsigned)batch), GRAM_THREADS, 0, st>>>(
+                    dp, round, drot, S, maxpairs, (double2*)(base + offG));
+                jacobi_eig_kernel<<<dim3((unsigned)maxpairs, (unsigned)batch), JTHREADS, 0, st>>>(
+                    dp, round, tol, drot, (const double*)dfro, inner, st_ptr, stamp, S, maxpairs, (const double2*)(base + offG),
+                    (double2*)(base + offW), (int*)(base + offF));
+                jacobi_update_kernel<<<dim3((unsigned)(maxpairs * SU), (unsigned)batch), JTHREADS, 0, st>>>(
+                    dp, round, drot, SU, maxpairs, (const double2*)(base + offW), (const int*)(base + offF));
+            }
+            if (!fused) { CUDA_TRY(cudaGetLastError()); count_launch(2 * (int64_t)(max_nb - 1)); }
+            for (int round = 0; round < max_nb - 1 && fused; ++round) {
                 cudaLaunchConfig_t cfg = {};
                 cfg.gridDim = dim3((unsigned)(max_nb / 2 * cl), (unsigned)batch, 1);
                 cfg.blockDim = dim3(JTHREADS, 1, 1);
@@ -779,8 +1157,15 @@ int svd_batched_device(int batch, const SvdJob* jobs, double er, int64_t maxdim,
     }
     if (dstat) {
         int hs[128];
+        float ms = 0;
+        cudaEventRecord(ev1, st);
+        cudaEventSynchronize(ev1);
+        cudaEventElapsedTime(&ms, ev0, ev1);
+        cudaEventDestroy(ev0);
+        cudaEventDestroy(ev1);
         cudaMemcpy(hs, dstat, sizeof(hs), cudaMemcpyDeviceToHost);
-        fprintf(stderr, "[jacobi] batch=%d maxn=%d cl=%d sweeps=%d (idle,active) pairs per sweep:", batch, maxn, cl, sweeps);
+        fprintf(stderr, "[jacobi] %s batch=%d maxm=%d maxn=%d v=%d cl=%d S=%d SU=%d sweeps=%d %.3f ms (%.3f ms/sweep) (idle,active) pairs per sweep:",
+                fused ? "fused" : "split", batch, maxm, maxn, (int)any_v, cl, S, SU, sweeps, ms, ms / std::max(sweeps, 1));
         for (int i = 0; i < sweeps && i < 64; ++i) fprintf(stderr, " (%d,%d)", hs[2 * i], hs[2 * i + 1]);
         fprintf(stderr, "\n");
         cudaFree(dstat);

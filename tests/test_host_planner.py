@@ -48,6 +48,24 @@ def test_hand_traced_vector(q):
     assert set(n2.contractions) == set(net.contractions) and n2.tensors == net.tensors and n2.openidx == net.openidx
 
 
+def _hand_traced():
+    import json
+    import os
+    k = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "hand_traced_orders.json")))
+    return {n: v for n, v in k.items() if not n.startswith("_")}
+
+
+@pytest.mark.parametrize("name", sorted(_hand_traced()))
+def test_hand_traced_orders_cxx(q, name):
+    """qtn_order_treewidth against the hand traces of tests/golden/hand_traced_orders.json."""
+    k = _hand_traced()[name]
+    net = q.GeneralTensorNetwork([q.Tensor(np.ones((2,) * l, dtype=complex)) for l in k["legs"]],
+                                 [q.Summation([tuple(p) for p in c]) for c in k["contractions"]], [])
+    perm, tw = q.network2graph.contraction_order_perm(net)
+    assert perm == k["perm"] and tw == k["tw"]
+    assert [list(t) for t in q.contraction_order(net)] == k["order"]
+
+
 def test_treewidth_known_answers_cxx(q):  # test/test_treewidth.jl:204-221 through the C ABI
     for n in (10, 25, 50):
         tw, order = q.tree_decomposition_width(n, complete_graph(n).edges())

@@ -93,6 +93,33 @@ def test_hand_traced_order_vector():  # SURVEY.md Appendix B (regression KAT)
     assert abs(oc.contract(net) - v) < 1e-13 * abs(v) and abs(oc.contract(n2) - v) < 1e-13 * abs(v)
 
 
+def hand_traced():
+    import json
+    import os
+    k = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "hand_traced_orders.json")))
+    return {n: v for n, v in k.items() if not n.startswith("_")}
+
+
+@pytest.mark.parametrize("name", sorted(hand_traced()))
+def test_hand_traced_orders_all_stages(name):
+    """tests/golden/hand_traced_orders.json: four networks (4-cycle, self-contraction, parallel edges, a 5-cycle whose
+    line graph needs two fill edges) traced by hand through src/network2graph.jl -- every intermediate stage."""
+    k = hand_traced()[name]
+    rng = np.random.default_rng(3)
+    net = on.Network([on.Tensor(rng.standard_normal((2,) * l) + 0j) for l in k["legs"]],
+                     [on.Summation([tuple(p) for p in c]) for c in k["contractions"]], [])
+    LG, nodeinfo = o2g.line_graph(net)
+    assert [list(t) for t in nodeinfo] == k["nodeinfo"] and LG.adj == k["lg_adj"]
+    assert o2g.min_fill_ordering(LG) == k["min_fill"]
+    tw, _, bags = o2g.tree_decomposition(LG)
+    assert tw == k["tw"] and bags == k["bags"]
+    assert [list(t) for t in o2g.contraction_order(net)] == k["order"]
+    n2 = net.copy()
+    assert o2g.optimize_contraction_order(n2) == k["perm"]
+    v = oc.contract(net)
+    assert abs(oc.contract(n2) - v) <= 1e-12 * abs(v)      # test/test_treewidth.jl:327: the value is order-invariant
+
+
 def test_nodeinfo_random_tn():  # test/test_treewidth.jl:129-139
     rng = np.random.default_rng(3)
     cons = []

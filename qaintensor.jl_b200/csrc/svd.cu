@@ -4,17 +4,18 @@
 //
 // Algorithm: blocked one-sided (Hestenes) Jacobi, batched over independent matrices.
 //   A (m x n, m >= n) is orthogonalised in place, V accumulates the column rotations.
-//   Columns are grouped in blocks of 16; a round-robin schedule pairs the blocks, and
-//   one CTA owns one (matrix, block pair) per round:
-//     1. Gram   G = P^H P of its 32-column panel P, on the FP64 tensor pipe (DMMA),
-//     2. eig    two-sided cyclic Jacobi on the 32x32 Hermitian G in shared memory
-//               (parallel ordering, de Rijk-style sorting), accumulating W,
-//     3. update P <- P W and the matching V panel <- V W, again on DMMA.
-//   Sweeps repeat until no CTA applied a rotation (scaled off-diagonal <= tol).
+//   Columns are grouped in blocks of 16; a round-robin (circle method) schedule pairs the blocks.  One round =
+//   three kernels over every (matrix, block pair) of a sub-batch:
+//     1. Gram   partial G = P^H P of each 32-column panel P on the FP64 tensor pipe (DMMA), rows split over S CTAs,
+//     2. eig    two-sided cyclic Jacobi sweep on the 32x32 Hermitian G (parallel ordering, de Rijk-style sorting),
+//               accumulating W; convergence stamps per block pair,
+//     3. update P <- P W for the A panel and the matching V panel, again on DMMA.
+//   The batch is sorted by size and cut into up to four sub-batches that run on their own streams: the
+//   latency-bound eigensolves of one sub-batch overlap the tensor-pipe kernels of the others, and partial
+//   last waves are back-filled.  Sweeps repeat until no pair of a sub-batch applied a rotation.
 //   Finalisation: sigma_j = ||a_j||, stable descending sort, U = A/sigma, Vh = V^H.
 //   Truncation (K6): k = n - r* + 1 with r* the first r whose reverse-cumulated tail
 //   sqrt(s_n^2 + ... + s_{n-r+1}^2) exceeds er (strict), then k <- min(k, maxdim).
-#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -42,9 +43,8 @@ int launch_gemm(GemmArgs& g, int variant, int split_k, cudaStream_t st);
 constexpr int JB = 16;        // column block width
 constexpr int JP = 2 * JB;    // panel width (columns per CTA)
 constexpr int JPITCH = JP + 2;
-constexpr int JROWS = 64;     // panel rows staged per chunk
-constexpr int JTHREADS = 256;
-constexpr int JRP = JROWS + 4;  // allocated row pitch of a chunk buffer column (phase 1 uses +4, phase 3 uses +2)
+constexpr int JTHREADS = 256;    // update kernel: 8 warps
+constexpr int ETHREADS = 128;    // eigensolve kernel: small CTAs that co-reside with the DMMA kernels of another stream
 constexpr int kInnerSweeps = 1;  // one eigen-sweep per Gram visit measured fastest (1: 108 ms, 2: 153, 3: 165, 6: 187 ms for 1024^2)
 
 struct SvdProblem {
@@ -56,26 +56,6 @@ struct SvdProblem {
     int* last_ok;   // [nblocks * nblocks] launch stamp at which a block pair was last found converged
 };
 
-// ---- TMA bulk copy (cp.async.bulk, SASS UBLKCP) + mbarrier helpers -----------------------------------------
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
-    unsigned ok;
-    do {
-        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    } while (!ok);
-}
-
 __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
     asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
@@ -86,323 +66,21 @@ __device__ __forceinline__ int panel_col(int c, int bi, int bj, int n) {
     return col < n ? col : -1;
 }
 
-namespace cg = cooperative_groups;
-
-// One round of the block schedule.  grid = (max pairs * CL, batch); a thread-block cluster of CL CTAs
-// shares one (matrix, block pair): the panel rows are dealt out chunk-wise over the cluster, the
-// partial Gram matrices are summed through distributed shared memory, every CTA then runs the
-// identical eigensolve (same W, no broadcast) and updates its own row chunks.
-__global__ void __launch_bounds__(JTHREADS, 2)
-jacobi_round_kernel(const SvdProblem* __restrict__ probs, int round, double tol, int* __restrict__ rotated,
-                    const double* __restrict__ fro2, int inner_sweeps, int* __restrict__ stat, int stamp) {
-    cg::cluster_group cluster = cg::this_cluster();
-    const int CL = (int)cluster.num_blocks(), crank = (int)cluster.block_rank();
-    const int pair = blockIdx.x / CL;
-    if (rotated[blockIdx.y] < 0) return;  // this matrix converged in an earlier sweep (cluster-uniform)
-    const SvdProblem pr = probs[blockIdx.y];
-    // deflation: a column below 1e-15 * ||A||_F is rounding noise (LAPACK resolves nothing there
-    // either); rotating it against a large, exactly parallel column would only shrink it by eps
-    // per sweep until it underflows (rank-deficient product states hit exactly this)
-    const double dthr = 1e-30 * fro2[blockIdx.y];
-    const int nb = pr.nblocks;
-    if (nb < 2 || pair >= nb / 2 || round >= nb - 1) return;
-    // circle method: pair 0 = (nb-1, round); pair k = ((round+k) % (nb-1), (round-k) % (nb-1))
-    int bi, bj;
-    if (pair == 0) { bi = nb - 1; bj = round; }
-    else { bi = (round + pair) % (nb - 1); bj = (round - pair + (nb - 1)) % (nb - 1); }
-    if (bi > bj) { int t = bi; bi = bj; bj = t; }
-    if (bi * JB >= pr.n) return;  // padding block only
-    // a pair verified converged stays converged until one of its two blocks is rotated again:
-    // skipping it saves the whole Gram pass in the tail sweeps (cluster-uniform decision)
-    if (max(pr.last_mod[bi], pr.last_mod[bj]) < pr.last_ok[bi * nb + bj]) {
-        if (stat && threadIdx.x == 0 && crank == 0) atomicAdd(&stat[0], 1);
-        return;
-    }
-
-    // shared memory: two panel-chunk buffers [col][row] (filled by TMA bulk copies), G, W, rotation scratch.
-    // The partial Gram Gpart aliases chunk buffer 1 (the buffers are idle between phase 1 and phase 3).
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    double2* Pc = reinterpret_cast<double2*>(smem_raw);                  // [2][JP][JRP]
-    double2* G = Pc + 2 * JP * JRP;                                       // [JP][JPITCH]
-    double2* W = G + JP * JPITCH;                                         // [JP][JPITCH]
-    double2* rot = W + JP * JPITCH;                                       // [JB] (c, s)
-    double2* rph = rot + JB;                                              // [JB] e^{i phi}, then [2*JB] ints (p, q)
-    double2* Gpart = Pc + JP * JRP;                                       // alias of chunk buffer 1
-    __shared__ int s_any, s_sweep_any, s_rot;
-    __shared__ int s_cols[JP];
-    __shared__ __align__(8) unsigned long long s_full[2];
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid < JP) s_cols[tid] = panel_col(tid, bi, bj, pr.n);
-    if (tid == 0) {
-        s_any = 0; s_rot = 0;
-        mbar_init(&s_full[0], 1);
-        mbar_init(&s_full[1], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    for (int i = tid; i < JP * JPITCH; i += JTHREADS) { G[i] = make_double2(0, 0); W[i] = make_double2(0, 0); }
-    for (int i = tid; i < 2 * JP * JRP; i += JTHREADS) Pc[i] = make_double2(0, 0);
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // zeros visible to the async (TMA) proxy
-    __syncthreads();
-
-    // Chunk pipeline: thread 0 issues one cp.async.bulk per panel column (JROWS rows = 1 KB, contiguous in the
-    // column-major matrix) into buffer `it & 1` with pitch `rp`, completion on an mbarrier; chunk it+1 is in
-    // flight while the DMMAs of chunk it run.  Padding columns are never written (stay zero); a partial last
-    // chunk re-zeroes its buffer first.
-    unsigned issued = 0, waited = 0;  // running chunk counters (parity of the two mbarriers)
-    auto issue = [&](const double2* base, int ld, int r0, int nrows, int rp) {
-        const int buf = issued & 1;
-        const int rows = min(JROWS, nrows - r0);
-        if (rows < JROWS) {  // uniform branch: partial chunk, clear stale rows
-            for (int i = tid; i < JP * JRP; i += JTHREADS) Pc[buf * JP * JRP + i] = make_double2(0, 0);
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            __syncthreads();
-        }
-        if (warp == 0) {  // lane c issues the bulk copy of panel column c: 32 copies in flight at once
-            const int col = s_cols[lane];
-            const unsigned ncol = __popc(__ballot_sync(0xffffffffu, col >= 0));
-            if (lane == 0) mbar_expect_tx(&s_full[buf], ncol * (unsigned)(rows * 16));
-            __syncwarp();
-            if (col >= 0)
-                bulk_g2s(Pc + (size_t)buf * JP * JRP + lane * rp, base + (size_t)col * ld + r0, (unsigned)(rows * 16), &s_full[buf]);
-        }
-        ++issued;
-    };
-    auto wait_chunk = [&]() -> const double2* {
-        const int buf = waited & 1;
-        mbar_wait(&s_full[buf], (waited >> 1) & 1);
-        ++waited;
-        return Pc + (size_t)buf * JP * JRP;
-    };
-    const int cstep = CL * JROWS;  // this CTA takes chunks crank, crank + CL, ...
-
-    // ---------------- phase 1: G = P^H P (warp w takes k-rows [8w, 8w+8) of every chunk) -----------
-    double gr[4][4][2], gi[4][4][2];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) gr[i][j][0] = gr[i][j][1] = gi[i][j][0] = gi[i][j][1] = 0.0;
-    constexpr int RP1 = JROWS + 4;  // pitch = 4 mod 8 (16-B units): conflict-free LDS.128 for the Gram fragments
-    if (crank * JROWS < pr.m) issue(pr.A, pr.m, crank * JROWS, pr.m, RP1);
-    for (int r0 = crank * JROWS; r0 < pr.m; r0 += cstep) {
-        if (r0 + cstep < pr.m) issue(pr.A, pr.m, r0 + cstep, pr.m, RP1);
-        const double2* Ps = wait_chunk();
-#pragma unroll
-        for (int k4 = 0; k4 < 2; ++k4) {
-            const int kr = warp * 8 + k4 * 4 + (lane & 3);
-            double2 f[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) f[i] = Ps[(i * 8 + (lane >> 2)) * RP1 + kr];
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    if (j < i) continue;  // Hermitian: upper block triangle only
-                    dmma(gr[i][j][0], gr[i][j][1], f[i].x, f[j].x);
-                    dmma(gr[i][j][0], gr[i][j][1], f[i].y, f[j].y);
-                    dmma(gi[i][j][0], gi[i][j][1], f[i].x, f[j].y);
-                    dmma(gi[i][j][0], gi[i][j][1], -f[i].y, f[j].x);
-                }
-        }
-        __syncthreads();  // buffer free for the chunk after next
-    }
-    // cross-warp reduction into Gpart (aliases chunk buffer 1: all chunk reads are complete)
-    for (int i = tid; i < JP * JPITCH; i += JTHREADS) Gpart[i] = make_double2(0, 0);
-    __syncthreads();
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            if (j < i) continue;
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                const int row = i * 8 + (lane >> 2), col = j * 8 + 2 * (lane & 3) + q;
-                atomicAdd(&Gpart[row * JPITCH + col].x, gr[i][j][q]);
-                atomicAdd(&Gpart[row * JPITCH + col].y, gi[i][j][q]);
-            }
-        }
-    cluster.sync();  // every CTA's partial Gram is complete (also a CTA barrier)
-    for (int e = tid; e < JP * JPITCH; e += JTHREADS) {
-        double2 acc = make_double2(0, 0);
-        for (int r = 0; r < CL; ++r) {  // fixed order: every CTA of the cluster gets bit-identical sums
-            const double2 v = cluster.map_shared_rank(Gpart, r)[e];
-            acc.x += v.x;
-            acc.y += v.y;
-        }
-        G[e] = acc;
-    }
-    cluster.sync();  // remote reads done before anyone may leave or re-use the buffer
-    // mirror the strictly-lower block triangle, set W = I
-    for (int e = tid; e < JP * JP; e += JTHREADS) {
-        const int r = e / JP, c = e % JP;
-        if ((r >> 3) > (c >> 3)) { const double2 v = G[c * JPITCH + r]; G[r * JPITCH + c] = make_double2(v.x, -v.y); }
-        if (r == c) W[r * JPITCH + c] = make_double2(1.0, 0.0);
-    }
-    __syncthreads();
-
-    // ---------------- phase 2: Hermitian Jacobi on G, W accumulates the rotations -------------------
-    for (int sweep = 0; sweep < inner_sweeps; ++sweep) {
-        if (tid == 0) s_sweep_any = 0;
-        __syncthreads();
-        for (int step = 0; step < JP - 1; ++step) {
-            if (tid < JB) {
-                int p, q;
-                if (tid == 0) { p = JP - 1; q = step; }
-                else { p = (step + tid) % (JP - 1); q = (step - tid + (JP - 1)) % (JP - 1); }
-                if (p > q) { int t = p; p = q; q = t; }
-                const double alpha = G[p * JPITCH + p].x, beta = G[q * JPITCH + q].x;
-                const double2 g = G[p * JPITCH + q];
-                const double ag2 = g.x * g.x + g.y * g.y;
-                double c = 1.0, s = 0.0;
-                double2 ph = make_double2(1.0, 0.0);
-                const bool real_cols = s_cols[p] >= 0 && s_cols[q] >= 0;  // never touch padding slots
-                if (!real_cols) {
-                    // identity
-                } else if (ag2 > tol * tol * fabs(alpha) * fabs(beta) && ag2 > 0.0 && alpha > dthr && beta > dthr) {
-                    // three rsqrt + one division (FP64 sqrt/div chains are the critical path of a step)
-                    const double rg = rsqrt(ag2), ag = ag2 * rg;
-                    ph = make_double2(g.x * rg, g.y * rg);
-                    const double zeta = 0.5 * (beta - alpha) * rg;
-                    const double z1 = 1.0 + zeta * zeta;
-                    double t = 1.0 / (fabs(zeta) + z1 * rsqrt(z1));
-                    if (zeta < 0) t = -t;
-                    c = rsqrt(1.0 + t * t);
-                    s = c * t;
-                    // de Rijk ordering: keep the larger diagonal entry at the lower index
-                    const double ap = alpha - t * ag, bq = beta + t * ag;
-                    if (ap < bq) { const double c2 = s, s2 = -c; c = c2; s = s2; }
-                    s_sweep_any = 1;
-                    s_rot = 1;
-                } else if (alpha < beta && beta > dthr) {
-                    c = 0.0; s = -1.0;  // pure swap: a significant column moves in front of a smaller one
-                    s_sweep_any = 1;
-                }
-                rot[tid] = make_double2(c, s);
-                rph[tid] = ph;
-                // store the pair for the appliers
-                reinterpret_cast<int*>(rph + JB)[2 * tid] = p;
-                reinterpret_cast<int*>(rph + JB)[2 * tid + 1] = q;
-            }
-            __syncthreads();
-            const int* pq = reinterpret_cast<const int*>(rph + JB);
-            {
-                // fused two-sided update: thread (k1, k2) owns the 2x2 block G[{p1,q1}][{p2,q2}]:
-                // G' = J1^H G J2 with J = [[c, s e^{i phi}], [-s e^{-i phi}, c]] acting on columns
-                const int k1 = tid >> 4, k2 = tid & 15;
-                const double c1 = rot[k1].x, s1 = rot[k1].y, c2 = rot[k2].x, s2 = rot[k2].y;
-                const bool id1 = (c1 == 1.0 && s1 == 0.0), id2 = (c2 == 1.0 && s2 == 0.0);
-                if (!(id1 && id2)) {
-                    const double2 ph1 = rph[k1], ph2 = rph[k2];
-                    const int p1 = pq[2 * k1], q1 = pq[2 * k1 + 1], p2 = pq[2 * k2], q2 = pq[2 * k2 + 1];
-                    double2 g00 = G[p1 * JPITCH + p2], g01 = G[p1 * JPITCH + q2];
-                    double2 g10 = G[q1 * JPITCH + p2], g11 = G[q1 * JPITCH + q2];
-                    auto mulph = [](double2 ph, double2 v) { return make_double2(ph.x * v.x - ph.y * v.y, ph.x * v.y + ph.y * v.x); };
-                    auto mulphc = [](double2 ph, double2 v) { return make_double2(ph.x * v.x + ph.y * v.y, ph.x * v.y - ph.y * v.x); };
-                    if (!id1) {  // rows: y_p' = c y_p - s e^{i phi} y_q ; y_q' = s e^{-i phi} y_p + c y_q
-                        const double2 e10 = mulph(ph1, g10), e11 = mulph(ph1, g11), f00 = mulphc(ph1, g00), f01 = mulphc(ph1, g01);
-                        const double2 n00 = make_double2(c1 * g00.x - s1 * e10.x, c1 * g00.y - s1 * e10.y);
-                        const double2 n01 = make_double2(c1 * g01.x - s1 * e11.x, c1 * g01.y - s1 * e11.y);
-                        const double2 n10 = make_double2(s1 * f00.x + c1 * g10.x, s1 * f00.y + c1 * g10.y);
-                        const double2 n11 = make_double2(s1 * f01.x + c1 * g11.x, s1 * f01.y + c1 * g11.y);
-                        g00 = n00; g01 = n01; g10 = n10; g11 = n11;
-                    }
-                    if (!id2) {  // columns: x_p' = c x_p - s e^{-i phi} x_q ; x_q' = s e^{i phi} x_p + c x_q
-                        const double2 e01 = mulphc(ph2, g01), e11 = mulphc(ph2, g11), f00 = mulph(ph2, g00), f10 = mulph(ph2, g10);
-                        const double2 n00 = make_double2(c2 * g00.x - s2 * e01.x, c2 * g00.y - s2 * e01.y);
-                        const double2 n10 = make_double2(c2 * g10.x - s2 * e11.x, c2 * g10.y - s2 * e11.y);
-                        const double2 n01 = make_double2(s2 * f00.x + c2 * g01.x, s2 * f00.y + c2 * g01.y);
-                        const double2 n11 = make_double2(s2 * f10.x + c2 * g11.x, s2 * f10.y + c2 * g11.y);
-                        g00 = n00; g01 = n01; g10 = n10; g11 = n11;
-                    }
-                    G[p1 * JPITCH + p2] = g00; G[p1 * JPITCH + q2] = g01;
-                    G[q1 * JPITCH + p2] = g10; G[q1 * JPITCH + q2] = g11;
-                }
-                // W <- W J (columns), rows r and r + 16 for pair k2
-                if (!id2) {
-                    const double2 ph2 = rph[k2];
-                    const int p2 = pq[2 * k2], q2 = pq[2 * k2 + 1];
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const int r = k1 + 16 * h;
-                        const double2 xp = W[r * JPITCH + p2], xq = W[r * JPITCH + q2];
-                        const double2 eq = make_double2(ph2.x * xq.x + ph2.y * xq.y, ph2.x * xq.y - ph2.y * xq.x);
-                        const double2 ep = make_double2(ph2.x * xp.x - ph2.y * xp.y, ph2.x * xp.y + ph2.y * xp.x);
-                        W[r * JPITCH + p2] = make_double2(c2 * xp.x - s2 * eq.x, c2 * xp.y - s2 * eq.y);
-                        W[r * JPITCH + q2] = make_double2(s2 * ep.x + c2 * xq.x, s2 * ep.y + c2 * xq.y);
-                    }
-                }
-            }
-            __syncthreads();
-        }
-        const int any_now = s_sweep_any;
-        if (any_now && tid == 0) s_any = 1;
-        __syncthreads();
-        if (!any_now) break;
-    }
-    if (stat && tid == 0 && crank == 0) atomicAdd(&stat[s_any ? 1 : 0], 1);
-    if (tid == 0 && crank == 0) {
-        if (s_any) { pr.last_mod[bi] = stamp; pr.last_mod[bj] = stamp; }
-        else pr.last_ok[bi * nb + bj] = stamp;
-    }
-    if (!s_any) return;  // panel already orthogonal and ordered: nothing to update
-    if (tid == 0 && s_rot && crank == 0) rotated[blockIdx.y] = 1;  // pure re-ordering swaps do not keep the sweeps going
-
-    // ---------------- phase 3: P <- P W for the A panel and the V panel ---------------------------------
-    // warp w owns rows [8w, 8w+8) of each 64-row chunk: C(8 x 32) = P(8 x 32) W(32 x 32)
-    constexpr int RP3 = JROWS + 2;  // pitch = 2 mod 8: conflict-free A-fragment loads for the update
-    for (int i = tid; i < 2 * JP * JRP; i += JTHREADS) Pc[i] = make_double2(0, 0);  // Gpart lived here; padding must read 0
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    __syncthreads();
-    for (int which = 0; which < (pr.V ? 2 : 1); ++which) {
-        double2* base = which ? pr.V : pr.A;
-        const int nrows = which ? pr.n : pr.m;
-        if (crank * JROWS < nrows) issue(base, nrows, crank * JROWS, nrows, RP3);
-        for (int r0 = crank * JROWS; r0 < nrows; r0 += cstep) {
-            if (r0 + cstep < nrows) issue(base, nrows, r0 + cstep, nrows, RP3);
-            const double2* Ps = wait_chunk();
-            double cr[4][2], ci[4][2];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) cr[j][0] = cr[j][1] = ci[j][0] = ci[j][1] = 0.0;
-#pragma unroll
-            for (int k4 = 0; k4 < JP / 4; ++k4) {
-                const double2 a = Ps[(k4 * 4 + (lane & 3)) * RP3 + warp * 8 + (lane >> 2)];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const double2 b = W[(k4 * 4 + (lane & 3)) * JPITCH + j * 8 + (lane >> 2)];
-                    dmma(cr[j][0], cr[j][1], a.x, b.x);
-                    dmma(cr[j][0], cr[j][1], -a.y, b.y);
-                    dmma(ci[j][0], ci[j][1], a.x, b.y);
-                    dmma(ci[j][0], ci[j][1], a.y, b.x);
-                }
-            }
-            const int row = r0 + warp * 8 + (lane >> 2);
-            if (row < nrows) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-#pragma unroll
-                    for (int q = 0; q < 2; ++q) {
-                        const int col = s_cols[j * 8 + 2 * (lane & 3) + q];
-                        if (col >= 0) base[(size_t)col * nrows + row] = make_double2(cr[j][q], ci[j][q]);
-                    }
-            }
-            __syncthreads();  // buffer free for the chunk after next
-        }
-    }
-}
-
 // =============================================================================================================
-// Split round (default): the same block schedule as above, but the three phases are three kernels, so the
-// tensor-pipe work (Gram, update) streams at GEMM efficiency and the latency-bound 32 x 32 eigensolves of ALL block
-// pairs of a round run side by side instead of idling the DMMA pipe of the CTA that owns the pair:
+// The round kernels.  The three phases are separate kernels so that the tensor-pipe work (Gram, update) streams at
+// GEMM efficiency and the latency-bound 32 x 32 eigensolves of ALL block pairs of a round run side by side:
 //   jacobi_gram_kernel    partial Grams of every active (matrix, pair), rows split over S CTAs; operands go
 //                         global -> registers as DMMA fragments (each element is read exactly once), no shared-memory
 //                         staging and no barrier in the main loop; fixed-order cross-warp tree -> deterministic sums
-//   jacobi_eig_kernel     one CTA per (matrix, pair): G = sum of the S partials (fixed order), Hermitian Jacobi sweep,
-//                         W and the pair's "apply" flag to global memory, convergence stamps
+//   jacobi_eig_kernel     one small CTA per (matrix, pair): G = sum of the S partials (fixed order), Hermitian Jacobi
+//                         sweep, W and the pair's "apply" flag to global memory, convergence stamps
 //   jacobi_update_kernel  P <- P W for the A panel and the V panel, 8-row groups per warp, W in shared memory
 // =============================================================================================================
 constexpr int GP_ELEMS = 10 * 64;   // upper block triangle of the 4 x 4 grid of 8 x 8 blocks of a 32 x 32 Gram
 constexpr int GRAM_THREADS = 128;
+#ifndef GRAM_MAXREG
+#define GRAM_MAXREG 224  // 2 CTAs x 128 x 224 = 56 K registers: leaves exactly one eigensolve CTA (128 x 64) of another stream
+#endif
 
 // block pair of `pair` in `round` (circle method); false when this (round, pair) has nothing to do for the problem
 __device__ __forceinline__ bool round_pair(const SvdProblem& pr, int round, int pair, int& bi, int& bj) {
@@ -418,7 +96,7 @@ __device__ __forceinline__ bool pair_idle(const SvdProblem& pr, int bi, int bj) 
     return max(pr.last_mod[bi], pr.last_mod[bj]) < pr.last_ok[bi * pr.nblocks + bj];
 }
 
-__global__ void __launch_bounds__(GRAM_THREADS, 2)
+__global__ void __maxnreg__(GRAM_MAXREG)
 jacobi_gram_kernel(const SvdProblem* __restrict__ probs, int round, const int* __restrict__ rotated, int S, int maxpairs,
                    double2* __restrict__ Gpart) {
     const int b = blockIdx.y, pair = blockIdx.x / S, split = blockIdx.x - pair * S;
@@ -517,7 +195,10 @@ jacobi_gram_kernel(const SvdProblem* __restrict__ probs, int round, const int* _
     }
 }
 
-__global__ void __launch_bounds__(JTHREADS)
+// Rotation of the Hermitian 2x2 pivot [[alpha, g], [conj(g), beta]]: J = [[c, s e^{i phi}], [-s e^{-i phi}, c]].
+struct JRot { double c, s; double2 ph; };
+
+__global__ void __launch_bounds__(ETHREADS, 8)
 jacobi_eig_kernel(const SvdProblem* __restrict__ probs, int round, double tol, int* __restrict__ rotated,
                   const double* __restrict__ fro2, int inner_sweeps, int* __restrict__ stat, int stamp, int S, int maxpairs,
                   const double2* __restrict__ Gpart, double2* __restrict__ Wbuf, int* __restrict__ pflag) {
@@ -534,7 +215,10 @@ jacobi_eig_kernel(const SvdProblem* __restrict__ probs, int round, double tol, i
         return;
     }
     const int nb = pr.nblocks;
-    const double dthr = 1e-30 * fro2[b];  // deflation threshold, see jacobi_round_kernel
+    // deflation: a column below 1e-15 * ||A||_F is rounding noise (LAPACK resolves nothing there either); rotating it
+    // against a large, exactly parallel column would only shrink it by eps per sweep until it underflows
+    // (rank-deficient product states hit exactly this)
+    const double dthr = 1e-30 * fro2[b];
     __shared__ double2 G[JP * JPITCH], W[JP * JPITCH];
     __shared__ double2 rot[JB], rph[JB];
     __shared__ int s_pq[2 * JB];
@@ -542,10 +226,10 @@ jacobi_eig_kernel(const SvdProblem* __restrict__ probs, int round, double tol, i
     __shared__ int s_cols[JP];
     if (tid < JP) s_cols[tid] = panel_col(tid, bi, bj, pr.n);
     if (tid == 0) { s_any = 0; s_rot = 0; }
-    for (int i = tid; i < JP * JPITCH; i += JTHREADS) W[i] = make_double2(0, 0);
+    for (int i = tid; i < JP * JPITCH; i += ETHREADS) W[i] = make_double2(0, 0);
     {
         const double2* gp = Gpart + (size_t)((size_t)b * maxpairs + pair) * S * GP_ELEMS;
-        for (int e = tid; e < GP_ELEMS; e += JTHREADS) {
+        for (int e = tid; e < GP_ELEMS; e += ETHREADS) {
             double2 acc = make_double2(0, 0);
             for (int s = 0; s < S; ++s) {  // fixed order: deterministic
                 const double2 v = __ldcg(gp + (size_t)s * GP_ELEMS + e);
@@ -560,12 +244,14 @@ jacobi_eig_kernel(const SvdProblem* __restrict__ probs, int round, double tol, i
         }
     }
     __syncthreads();
-    for (int e = tid; e < JP * JP; e += JTHREADS) {  // mirror the strictly-lower block triangle, W = I
+    for (int e = tid; e < JP * JP; e += ETHREADS) {  // mirror the strictly-lower block triangle, W = I
         const int r = e / JP, c = e % JP;
         if ((r >> 3) > (c >> 3)) { const double2 v = G[c * JPITCH + r]; G[r * JPITCH + c] = make_double2(v.x, -v.y); }
         if (r == c) W[r * JPITCH + c] = make_double2(1.0, 0.0);
     }
     __syncthreads();
+    auto mulph = [](double2 ph, double2 v) { return make_double2(ph.x * v.x - ph.y * v.y, ph.x * v.y + ph.y * v.x); };
+    auto mulphc = [](double2 ph, double2 v) { return make_double2(ph.x * v.x + ph.y * v.y, ph.x * v.y - ph.y * v.x); };
     for (int sweep = 0; sweep < inner_sweeps; ++sweep) {
         if (tid == 0) s_sweep_any = 0;
         __syncthreads();
@@ -584,20 +270,23 @@ jacobi_eig_kernel(const SvdProblem* __restrict__ probs, int round, double tol, i
                 if (!real_cols) {
                     // identity
                 } else if (ag2 > tol * tol * fabs(alpha) * fabs(beta) && ag2 > 0.0 && alpha > dthr && beta > dthr) {
-                    const double rg = rsqrt(ag2), ag = ag2 * rg;
+                    // inner rotation (|theta| <= pi/4) from two rsqrt levels: with a = (beta - alpha)/2, r = sqrt(a^2 + |g|^2):
+                    // cos^2 = (1 + |a|/r)/2, sin = sign(a) |g| / (2 r cos); the phase needs a third, independent rsqrt
+                    const double a = 0.5 * (beta - alpha);
+                    const double rg = rsqrt(ag2), rr = rsqrt(a * a + ag2);
                     ph = make_double2(gg.x * rg, gg.y * rg);
-                    const double zeta = 0.5 * (beta - alpha) * rg;
-                    const double z1 = 1.0 + zeta * zeta;
-                    double tt = 1.0 / (fabs(zeta) + z1 * rsqrt(z1));
-                    if (zeta < 0) tt = -tt;
-                    c = rsqrt(1.0 + tt * tt);
-                    s = c * tt;
-                    const double ap = alpha - tt * ag, bq = beta + tt * ag;  // de Rijk: larger diagonal entry first
-                    if (ap < bq) { const double c2 = s, s2 = -c; c = c2; s = s2; }
+                    const double c2 = 0.5 + 0.5 * fabs(a) * rr;
+                    const double rc = rsqrt(c2);
+                    c = c2 * rc;
+                    s = 0.5 * (ag2 * rg) * rr * rc;
+                    if (a < 0) s = -s;
+                    // de Rijk ordering: keep the larger diagonal entry at the lower index (t = s / c)
+                    const double t_ag = (s * rc) * (ag2 * rg);
+                    if (alpha - t_ag < beta + t_ag) { const double cc = s, ss = -c; c = cc; s = ss; }
                     s_sweep_any = 1;
                     s_rot = 1;
                 } else if (alpha < beta && beta > dthr) {
-                    c = 0.0; s = -1.0;  // pure swap
+                    c = 0.0; s = -1.0;  // pure swap: a significant column moves in front of a smaller one
                     s_sweep_any = 1;
                 }
                 rot[tid] = make_double2(c, s);
@@ -607,17 +296,24 @@ jacobi_eig_kernel(const SvdProblem* __restrict__ probs, int round, double tol, i
             }
             __syncthreads();
             {
-                const int k1 = tid >> 4, k2 = tid & 15;
-                const double c1 = rot[k1].x, s1 = rot[k1].y, c2 = rot[k2].x, s2 = rot[k2].y;
-                const bool id1 = (c1 == 1.0 && s1 == 0.0), id2 = (c2 == 1.0 && s2 == 0.0);
-                if (!(id1 && id2)) {
-                    const double2 ph1 = rph[k1], ph2 = rph[k2];
-                    const int p1 = s_pq[2 * k1], q1 = s_pq[2 * k1 + 1], p2 = s_pq[2 * k2], q2 = s_pq[2 * k2 + 1];
+                // fused two-sided update: a thread owns the 2x2 blocks G[{p1,q1}][{p2,q2}] of pairs (k1, k2) and
+                // (k1 + 8, k2): G' = J1^H G J2 acting on rows (J1) and columns (J2)
+                const int k2 = tid & 15;
+                const double c2 = rot[k2].x, s2 = rot[k2].y;
+                const bool id2 = (c2 == 1.0 && s2 == 0.0);
+                const double2 ph2 = rph[k2];
+                const int p2 = s_pq[2 * k2], q2 = s_pq[2 * k2 + 1];
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                    const int k1 = (tid >> 4) + 8 * hh;
+                    const double c1 = rot[k1].x, s1 = rot[k1].y;
+                    const bool id1 = (c1 == 1.0 && s1 == 0.0);
+                    if (id1 && id2) continue;
+                    const double2 ph1 = rph[k1];
+                    const int p1 = s_pq[2 * k1], q1 = s_pq[2 * k1 + 1];
                     double2 g00 = G[p1 * JPITCH + p2], g01 = G[p1 * JPITCH + q2];
                     double2 g10 = G[q1 * JPITCH + p2], g11 = G[q1 * JPITCH + q2];
-                    auto mulph = [](double2 ph, double2 v) { return make_double2(ph.x * v.x - ph.y * v.y, ph.x * v.y + ph.y * v.x); };
-                    auto mulphc = [](double2 ph, double2 v) { return make_double2(ph.x * v.x + ph.y * v.y, ph.x * v.y - ph.y * v.x); };
-                    if (!id1) {
+                    if (!id1) {  // rows: y_p' = c y_p - s e^{i phi} y_q ; y_q' = s e^{-i phi} y_p + c y_q
                         const double2 e10 = mulph(ph1, g10), e11 = mulph(ph1, g11), f00 = mulphc(ph1, g00), f01 = mulphc(ph1, g01);
                         const double2 n00 = make_double2(c1 * g00.x - s1 * e10.x, c1 * g00.y - s1 * e10.y);
                         const double2 n01 = make_double2(c1 * g01.x - s1 * e11.x, c1 * g01.y - s1 * e11.y);
@@ -625,7 +321,7 @@ jacobi_eig_kernel(const SvdProblem* __restrict__ probs, int round, double tol, i
                         const double2 n11 = make_double2(s1 * f01.x + c1 * g11.x, s1 * f01.y + c1 * g11.y);
                         g00 = n00; g01 = n01; g10 = n10; g11 = n11;
                     }
-                    if (!id2) {
+                    if (!id2) {  // columns: x_p' = c x_p - s e^{-i phi} x_q ; x_q' = s e^{i phi} x_p + c x_q
                         const double2 e01 = mulphc(ph2, g01), e11 = mulphc(ph2, g11), f00 = mulph(ph2, g00), f10 = mulph(ph2, g10);
                         const double2 n00 = make_double2(c2 * g00.x - s2 * e01.x, c2 * g00.y - s2 * e01.y);
                         const double2 n10 = make_double2(c2 * g10.x - s2 * e11.x, c2 * g10.y - s2 * e11.y);
@@ -636,15 +332,12 @@ jacobi_eig_kernel(const SvdProblem* __restrict__ probs, int round, double tol, i
                     G[p1 * JPITCH + p2] = g00; G[p1 * JPITCH + q2] = g01;
                     G[q1 * JPITCH + p2] = g10; G[q1 * JPITCH + q2] = g11;
                 }
-                if (!id2) {  // W <- W J (columns), rows k1 and k1 + 16
-                    const double2 ph2 = rph[k2];
-                    const int p2 = s_pq[2 * k2], q2 = s_pq[2 * k2 + 1];
+                if (!id2) {  // W <- W J (columns), rows (tid >> 4) + 8 h for pair k2
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const int r = k1 + 16 * h;
+                    for (int h = 0; h < 4; ++h) {
+                        const int r = (tid >> 4) + 8 * h;
                         const double2 xp = W[r * JPITCH + p2], xq = W[r * JPITCH + q2];
-                        const double2 eq = make_double2(ph2.x * xq.x + ph2.y * xq.y, ph2.x * xq.y - ph2.y * xq.x);
-                        const double2 ep = make_double2(ph2.x * xp.x - ph2.y * xp.y, ph2.x * xp.y + ph2.y * xp.x);
+                        const double2 eq = mulphc(ph2, xq), ep = mulph(ph2, xp);
                         W[r * JPITCH + p2] = make_double2(c2 * xp.x - s2 * eq.x, c2 * xp.y - s2 * eq.y);
                         W[r * JPITCH + q2] = make_double2(s2 * ep.x + c2 * xq.x, s2 * ep.y + c2 * xq.y);
                     }
@@ -667,7 +360,7 @@ jacobi_eig_kernel(const SvdProblem* __restrict__ probs, int round, double tol, i
     }
     if (!any) return;
     double2* wout = Wbuf + (size_t)((size_t)b * maxpairs + pair) * (JP * JP);
-    for (int e = tid; e < JP * JP; e += JTHREADS) wout[e] = W[(e >> 5) * JPITCH + (e & 31)];
+    for (int e = tid; e < JP * JP; e += ETHREADS) wout[e] = W[(e >> 5) * JPITCH + (e & 31)];
 }
 
 __global__ void __launch_bounds__(JTHREADS, 2)
@@ -974,69 +667,129 @@ static int work_reserve(size_t bytes, size_t hbytes) {
     return QTN_OK;
 }
 
-// Runs the batch; k_out / disc_out are host arrays (batch).  Synchronises the stream.
-int svd_batched_device(int batch, const SvdJob* jobs, double er, int64_t maxdim, int64_t* k_out, double* disc_out,
+// Sub-batch streams: independent groups of matrices run their rounds concurrently (created once, never destroyed).
+constexpr int kMaxGroups = 4;
+static cudaStream_t g_sub[kMaxGroups] = {nullptr, nullptr, nullptr, nullptr};
+static cudaEvent_t g_sub_ev = nullptr;
+
+static int sub_streams_init() {
+    if (g_sub_ev) return QTN_OK;
+    for (int g = 0; g < kMaxGroups; ++g) CUDA_TRY(cudaStreamCreateWithFlags(&g_sub[g], cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&g_sub_ev, cudaEventDisableTiming));
+    return QTN_OK;
+}
+
+// One sub-batch: problems [b0, b1) of the (size-sorted) table.
+struct SvdGroup {
+    int b0 = 0, b1 = 0;
+    int max_nb = 2, maxpairs = 1, maxm = 1, maxn = 1;
+    bool any_v = false;
+    int S = 1, SU = 1;
+    size_t offG = 0, offW = 0, offF = 0;
+    bool active = true;
+    int sweeps = 0;
+};
+
+// Runs the batch; k_out / disc_out are host arrays (batch).  Synchronises the library stream.
+int svd_batched_device(int batch, const SvdJob* jobs_in, double er, int64_t maxdim, int64_t* k_out, double* disc_out,
                        int* sweeps_out) {
     if (batch <= 0) return QTN_OK;
     cudaStream_t st = stream();
-    // workspace layout (device): per problem: [At (if transposed) m*n] [V n*n] [sig n] [rank n]
-    size_t dev_bytes = 0;
-    std::vector<size_t> offAt(batch), offV(batch), offSig(batch), offRank(batch), offStamp(batch);
-    std::vector<int> tr(batch);
-    int maxn = 0, maxm = 0;
+    int rc = sub_streams_init();
+    if (rc) return rc;
+    // ---- validate; sort by size (columns, then rows, descending) so that sub-batches are homogeneous ----------
+    std::vector<int> perm(batch), tr_in(batch);
     for (int b = 0; b < batch; ++b) {
-        const int64_t m0 = jobs[b].m0, n0 = jobs[b].n0;
+        const int64_t m0 = jobs_in[b].m0, n0 = jobs_in[b].n0;
         if (m0 < 1 || n0 < 1) return fail(QTN_EINVAL, "svd: empty matrix");
         // only the Jacobi column count min(m0, n0) is bounded (block-pair tables are O(n^2 / 256)); the long
         // dimension may be large (MPS(psi): 2 x 2^(M-1); contract_svd_mps: rows grow as 2^j) -- row offsets are 64-bit
         if (std::min(m0, n0) > 32768 || std::max(m0, n0) > ((int64_t)1 << 30) || m0 * n0 > ((int64_t)1 << 33))
             return fail(QTN_EINVAL, "svd: matrix too large (min dimension <= 32768, max dimension <= 2^30, <= 2^33 elements)");
-        tr[b] = m0 < n0;
-        const int64_t m = tr[b] ? n0 : m0, n = tr[b] ? m0 : n0;
-        auto al = [&](size_t bytes) { size_t o = dev_bytes; dev_bytes += (bytes + 255) / 256 * 256; return o; };
+        perm[b] = b;
+        tr_in[b] = m0 < n0;
+    }
+    auto cols = [&](int b) { return std::min(jobs_in[b].m0, jobs_in[b].n0); };
+    auto rows = [&](int b) { return std::max(jobs_in[b].m0, jobs_in[b].n0); };
+    std::stable_sort(perm.begin(), perm.end(), [&](int x, int y) { return cols(x) != cols(y) ? cols(x) > cols(y) : rows(x) > rows(y); });
+    std::vector<SvdJob> jobs(batch);
+    std::vector<int> tr(batch);
+    for (int i = 0; i < batch; ++i) { jobs[i] = jobs_in[perm[i]]; tr[i] = tr_in[perm[i]]; }
+
+    // ---- workspace layout (device): per problem [At (if transposed) m*n] [V n*n] [sig n] [rank n] [stamps] ------
+    size_t dev_bytes = 0;
+    auto al = [&](size_t bytes) { size_t o = dev_bytes; dev_bytes += (bytes + 255) / 256 * 256; return o; };
+    std::vector<size_t> offAt(batch), offV(batch), offSig(batch), offRank(batch), offStamp(batch);
+    std::vector<double> work(batch);
+    int maxn = 0, maxm = 0;
+    double total_work = 0;
+    for (int b = 0; b < batch; ++b) {
+        const int64_t m = rows(perm[b]), n = cols(perm[b]);
         offAt[b] = tr[b] ? al((size_t)m * n * 16) : 0;
         offV[b] = al((size_t)n * n * 16);
         offSig[b] = al((size_t)n * 8);
         offRank[b] = al((size_t)n * 4);
-        {
-            int nbk = (int)((n + JB - 1) / JB);
-            if (nbk & 1) ++nbk;
-            offStamp[b] = al((size_t)(nbk + (size_t)nbk * nbk) * 4);
-        }
+        int nbk = (int)((n + JB - 1) / JB);
+        if (nbk & 1) ++nbk;
+        offStamp[b] = al((size_t)(nbk + (size_t)nbk * nbk) * 4);
         maxn = std::max<int>(maxn, (int)n);
         maxm = std::max<int>(maxm, (int)m);
+        work[b] = (double)(m + ((jobs[b].need_v || tr[b]) ? n : 0)) * n * n;  // ~ flops of one sweep
+        total_work += work[b];
     }
-    // split-round buffers: partial Grams [batch][pairs][S][640], rotations W [batch][pairs][32*32], apply flags
-    int max_nb = (maxn + JB - 1) / JB;
-    if (max_nb & 1) ++max_nb;
-    const int maxpairs = std::max(max_nb / 2, 1);
-    const bool fused = [] { const char* e = getenv("QTN_JACOBI"); return e && strcmp(e, "fused") == 0; }();
-    bool any_v = false;
-    for (int b = 0; b < batch; ++b) any_v = any_v || jobs[b].need_v || tr[b];
-    int S = 1, SU = 1;
+    // ---- sub-batches: contiguous in the sorted order, about equal work each -----------------------------------
+    int ngroups = std::min(batch, kMaxGroups);
+    if (const char* e = getenv("QTN_JACOBI_GROUPS")) ngroups = std::max(1, std::min(std::min(batch, kMaxGroups), atoi(e)));
+    if (total_work < 4e9) ngroups = 1;  // small problems: launch-latency-bound, one stream
+    std::vector<SvdGroup> groups;
     {
-        // enough CTAs for ~8 per SM, but at least two 16-row (Gram) / 8-row (update) groups per warp
-        const long units = (long)maxpairs * batch, target = 148 * 8;
-        const long ngroups = (maxm + 15) / 16, ugroups = (maxm + 7) / 8 + (any_v ? (maxn + 7) / 8 : 0);
-        S = (int)std::max<long>(1, std::min<long>((target + units - 1) / units, ngroups / 8));
-        SU = (int)std::max<long>(1, std::min<long>((target + units - 1) / units, ugroups / 16));
-        if (const char* e = getenv("QTN_JACOBI_S")) S = std::max(1, atoi(e));
-        if (const char* e = getenv("QTN_JACOBI_SU")) SU = std::max(1, atoi(e));
+        double acc = 0;
+        int start = 0;
+        for (int b = 0; b < batch; ++b) {
+            acc += work[b];
+            const int g = (int)groups.size();
+            if (b + 1 == batch || (g + 1 < ngroups && acc >= total_work * (g + 1) / ngroups && batch - (b + 1) >= ngroups - (g + 1))) {
+                SvdGroup grp;
+                grp.b0 = start;
+                grp.b1 = b + 1;
+                groups.push_back(grp);
+                start = b + 1;
+            }
+        }
     }
-    size_t offG = 0, offW = 0, offF = 0;
-    if (!fused) {
-        auto al = [&](size_t bytes) { size_t o = dev_bytes; dev_bytes += (bytes + 255) / 256 * 256; return o; };
-        offG = al((size_t)batch * maxpairs * S * GP_ELEMS * 16);
-        offW = al((size_t)batch * maxpairs * JP * JP * 16);
-        offF = al((size_t)batch * maxpairs * 4);
+    ngroups = (int)groups.size();
+    for (auto& grp : groups) {
+        long units = 0;  // (matrix, pair) work items of one round
+        for (int b = grp.b0; b < grp.b1; ++b) {
+            const int m = (int)rows(perm[b]), n = (int)cols(perm[b]);
+            int nbk = (n + JB - 1) / JB;
+            if (nbk & 1) ++nbk;
+            grp.max_nb = std::max(grp.max_nb, nbk);
+            grp.maxm = std::max(grp.maxm, m);
+            grp.maxn = std::max(grp.maxn, n);
+            grp.any_v = grp.any_v || jobs[b].need_v || tr[b];
+            units += nbk / 2;
+        }
+        grp.maxpairs = std::max(grp.max_nb / 2, 1);
+        // row splits: enough CTAs for ~8 per SM over the whole batch, at least two 16-row (Gram) / 8-row (update)
+        // groups per warp
+        const long target = std::max<long>(148 * 8 / ngroups, 1);
+        const long ggroups = (grp.maxm + 15) / 16, ugroups = (grp.maxm + 7) / 8 + (grp.any_v ? (grp.maxn + 7) / 8 : 0);
+        grp.S = (int)std::max<long>(1, std::min<long>((target + units - 1) / units, ggroups / 8));
+        grp.SU = (int)std::max<long>(1, std::min<long>((target + units - 1) / units, ugroups / 16));
+        if (const char* e = getenv("QTN_JACOBI_S")) grp.S = std::max(1, atoi(e));
+        if (const char* e = getenv("QTN_JACOBI_SU")) grp.SU = std::max(1, atoi(e));
+        const size_t nb_ = (size_t)(grp.b1 - grp.b0);
+        grp.offG = al(nb_ * grp.maxpairs * grp.S * GP_ELEMS * 16);   // partial Grams [problem][pair][S][640]
+        grp.offW = al(nb_ * grp.maxpairs * JP * JP * 16);            // rotations W   [problem][pair][32*32]
+        grp.offF = al(nb_ * grp.maxpairs * 4);                       // apply flags   [problem][pair]
     }
     size_t tab = dev_bytes;
     size_t tab_bytes = (size_t)batch * (sizeof(SvdProblem) + sizeof(FinishArgs) + 2 * sizeof(void*) + 8 + 8 + 8 + 4 + 4) + 1024;
     dev_bytes += (tab_bytes + 255) / 256 * 256;
-    int rc = work_reserve(dev_bytes, tab_bytes);
-    if (rc) return rc;
+    if ((rc = work_reserve(dev_bytes, tab_bytes))) return rc;
     char* base = (char*)g_work.dev;
-    // host-side table image
+    // ---- host-side table image ---------------------------------------------------------------------------------
     CUDA_TRY(cudaStreamSynchronize(st));
     char* h = (char*)g_work.host;
     SvdProblem* hp = (SvdProblem*)h;
@@ -1092,67 +845,64 @@ int svd_batched_device(int batch, const SvdJob* jobs, double er, int64_t maxdim,
     set_identity_kernel<<<dim3((unsigned)std::min<int64_t>(148 * 4, ((int64_t)maxn * maxn + 255) / 256), batch), 256, 0, st>>>(dp);
     fro_norm_kernel<<<dim3((unsigned)std::min<int64_t>(148, ((int64_t)maxn * maxm + 255) / 256), batch), 256, 0, st>>>(dp, dfro);
     count_launch(2);
-    const size_t smem = (size_t)(2 * JP * JRP + 2 * JP * JPITCH + 2 * JB) * 16 + JB * 8 + 64;
-    static bool attr = false;
-    if (!attr) { CUDA_TRY(cudaFuncSetAttribute(jacobi_round_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
     double tol = 1e-15 * std::sqrt((double)std::max(maxm, 1)) * 0.5 + 2.3e-16;
     if (const char* e = getenv("QTN_JACOBI_TOL")) tol *= atof(e);
-    // cluster size: split the panel rows over up to 8 CTAs when the (pairs x batch) grid alone cannot
-    // fill the 148 SMs (single large matrices, e.g. the sequential MPO compression sweeps)
-    int cl = 1;
-    {
-        const long ctas = (long)(max_nb / 2) * batch;
-        const int chunks = (maxm + JROWS - 1) / JROWS;
-        while (cl < 8 && ctas * cl * 2 <= 2 * 148 && cl * 2 <= chunks) cl *= 2;
-    }
     int* dstat = nullptr;  // QTN_JACOBI_STATS=1: per-sweep counts of (idle, active) block pairs, printed to stderr
     if (getenv("QTN_JACOBI_STATS")) { cudaMalloc((void**)&dstat, 2 * 64 * sizeof(int)); cudaMemsetAsync(dstat, 0, 2 * 64 * sizeof(int), st); }
     int inner = kInnerSweeps;
     if (const char* e = getenv("QTN_JACOBI_INNER")) inner = std::max(1, atoi(e));
-    int sweeps = 0, stamp = 1;
-    const int kMaxSweeps = 60;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     if (dstat) { cudaEventCreate(&ev0); cudaEventCreate(&ev1); cudaEventRecord(ev0, st); }
-    if (max_nb >= 2) {
-        for (; sweeps < kMaxSweeps; ++sweeps) {
-            // flags: 0 = no rotation yet this sweep, 1 = rotated, -1 = converged (its CTAs exit at once)
-            CUDA_TRY(cudaMemcpyAsync(drot, hrot, (size_t)batch * 4, cudaMemcpyHostToDevice, st));
-            for (int round = 0; round < max_nb - 1 && !fused; ++round) {
-                ++stamp;
-                int* st_ptr = dstat ? dstat + 2 * sweeps : (int*)nullptr;
-                jacobi_gram_kernel<<<dim3((unsigned)(maxpairs * S), (unsigned)batch), GRAM_THREADS, 0, st>>>(
-                    dp, round, drot, S, maxpairs, (double2*)(base + offG));
-                jacobi_eig_kernel<<<dim3((unsigned)maxpairs, (unsigned)batch), JTHREADS, 0, st>>>(
-                    dp, round, tol, drot, (const double*)dfro, inner, st_ptr, stamp, S, maxpairs, (const double2*)(base + offG),
-                    (double2*)(base + offW), (int*)(base + offF));
-                jacobi_update_kernel<<<dim3((unsigned)(maxpairs * SU), (unsigned)batch), JTHREADS, 0, st>>>(
-                    dp, round, drot, SU, maxpairs, (const double2*)(base + offW), (const int*)(base + offF));
+    // the sub-batch streams start after the set-up work on the library stream
+    CUDA_TRY(cudaEventRecord(g_sub_ev, st));
+    for (int g = 0; g < ngroups; ++g) CUDA_TRY(cudaStreamWaitEvent(g_sub[g], g_sub_ev, 0));
+    int sweeps = 0, stamp = 1;
+    const int kMaxSweeps = 60;
+    bool any_active = true;
+    for (; sweeps < kMaxSweeps && any_active; ++sweeps) {
+        // flags: 0 = no rotation yet this sweep, 1 = rotated, -1 = converged (its CTAs exit at once)
+        int max_rounds = 0;
+        for (int g = 0; g < ngroups; ++g) {
+            SvdGroup& grp = groups[g];
+            if (!grp.active) continue;
+            CUDA_TRY(cudaMemcpyAsync(drot + grp.b0, hrot + grp.b0, (size_t)(grp.b1 - grp.b0) * 4, cudaMemcpyHostToDevice, g_sub[g]));
+            max_rounds = std::max(max_rounds, grp.max_nb - 1);
+        }
+        int* st_ptr = dstat ? dstat + 2 * std::min(sweeps, 63) : (int*)nullptr;
+        for (int round = 0; round < max_rounds; ++round) {
+            ++stamp;
+            for (int g = 0; g < ngroups; ++g) {  // round-robin over the streams: none is starved by the enqueue order
+                const SvdGroup& grp = groups[g];
+                if (!grp.active || round >= grp.max_nb - 1) continue;
+                const unsigned nb_ = (unsigned)(grp.b1 - grp.b0);
+                jacobi_gram_kernel<<<dim3((unsigned)(grp.maxpairs * grp.S), nb_), GRAM_THREADS, 0, g_sub[g]>>>(
+                    dp + grp.b0, round, drot + grp.b0, grp.S, grp.maxpairs, (double2*)(base + grp.offG));
+                jacobi_eig_kernel<<<dim3((unsigned)grp.maxpairs, nb_), ETHREADS, 0, g_sub[g]>>>(
+                    dp + grp.b0, round, tol, drot + grp.b0, (const double*)dfro + grp.b0, inner, st_ptr, stamp, grp.S, grp.maxpairs,
+                    (const double2*)(base + grp.offG), (double2*)(base + grp.offW), (int*)(base + grp.offF));
+                jacobi_update_kernel<<<dim3((unsigned)(grp.maxpairs * grp.SU), nb_), JTHREADS, 0, g_sub[g]>>>(
+                    dp + grp.b0, round, drot + grp.b0, grp.SU, grp.maxpairs, (const double2*)(base + grp.offW), (const int*)(base + grp.offF));
+                count_launch(3);
             }
-            if (!fused) { CUDA_TRY(cudaGetLastError()); count_launch(2 * (int64_t)(max_nb - 1)); }
-            for (int round = 0; round < max_nb - 1 && fused; ++round) {
-                cudaLaunchConfig_t cfg = {};
-                cfg.gridDim = dim3((unsigned)(max_nb / 2 * cl), (unsigned)batch, 1);
-                cfg.blockDim = dim3(JTHREADS, 1, 1);
-                cfg.dynamicSmemBytes = smem;
-                cfg.stream = st;
-                cudaLaunchAttribute at[1];
-                at[0].id = cudaLaunchAttributeClusterDimension;
-                at[0].val.clusterDim.x = (unsigned)cl;
-                at[0].val.clusterDim.y = 1;
-                at[0].val.clusterDim.z = 1;
-                cfg.attrs = at;
-                cfg.numAttrs = 1;
-                CUDA_TRY(cudaLaunchKernelEx(&cfg, jacobi_round_kernel, dp, round, tol, drot, (const double*)dfro, inner, dstat ? dstat + 2 * sweeps : (int*)nullptr, ++stamp));
-            }
-            count_launch(max_nb - 1);
-            CUDA_TRY(cudaMemcpyAsync(hrot, drot, (size_t)batch * 4, cudaMemcpyDeviceToHost, st));
-            CUDA_TRY(cudaStreamSynchronize(st));
+        }
+        CUDA_TRY(cudaGetLastError());
+        for (int g = 0; g < ngroups; ++g) {
+            const SvdGroup& grp = groups[g];
+            if (grp.active) CUDA_TRY(cudaMemcpyAsync(hrot + grp.b0, drot + grp.b0, (size_t)(grp.b1 - grp.b0) * 4, cudaMemcpyDeviceToHost, g_sub[g]));
+        }
+        any_active = false;
+        for (int g = 0; g < ngroups; ++g) {
+            SvdGroup& grp = groups[g];
+            if (!grp.active) continue;
+            CUDA_TRY(cudaStreamSynchronize(g_sub[g]));
             bool any = false;
-            for (int b = 0; b < batch; ++b) {
+            for (int b = grp.b0; b < grp.b1; ++b) {
                 if (hrot[b] > 0) { any = true; hrot[b] = 0; }
                 else hrot[b] = -1;
             }
-            if (!any) { ++sweeps; break; }
+            grp.sweeps = sweeps + 1;
+            grp.active = any;
+            any_active = any_active || any;
         }
     }
     if (dstat) {
@@ -1164,12 +914,16 @@ int svd_batched_device(int batch, const SvdJob* jobs, double er, int64_t maxdim,
         cudaEventDestroy(ev0);
         cudaEventDestroy(ev1);
         cudaMemcpy(hs, dstat, sizeof(hs), cudaMemcpyDeviceToHost);
-        fprintf(stderr, "[jacobi] %s batch=%d maxm=%d maxn=%d v=%d cl=%d S=%d SU=%d sweeps=%d %.3f ms (%.3f ms/sweep) (idle,active) pairs per sweep:",
-                fused ? "fused" : "split", batch, maxm, maxn, (int)any_v, cl, S, SU, sweeps, ms, ms / std::max(sweeps, 1));
+        fprintf(stderr, "[jacobi] batch=%d maxm=%d maxn=%d sweeps=%d %.3f ms (%.3f ms/sweep); groups:", batch, maxm, maxn, sweeps, ms,
+                ms / std::max(sweeps, 1));
+        for (const auto& grp : groups)
+            fprintf(stderr, " [%d..%d) n<=%d m<=%d v=%d S=%d SU=%d sweeps=%d;", grp.b0, grp.b1, grp.maxn, grp.maxm, (int)grp.any_v, grp.S, grp.SU, grp.sweeps);
+        fprintf(stderr, " (idle,active) pairs per sweep:");
         for (int i = 0; i < sweeps && i < 64; ++i) fprintf(stderr, " (%d,%d)", hs[2 * i], hs[2 * i + 1]);
         fprintf(stderr, "\n");
         cudaFree(dstat);
     }
+    // every sub-stream was synchronised by the host above: the library stream continues with the finalisation
     column_norms_kernel<<<dim3(std::min(148 * 2, (maxn + 7) / 8), batch), 256, 0, st>>>(dp, dsig);
     sort_truncate_kernel<<<batch, 256, 0, st>>>(dp, dsig, drank, df, er, (long long)maxdim, (const double*)dfro, (int*)dptr(hdead));
     scatter_factors_kernel<<<dim3(148 * 2, batch), 256, 0, st>>>(dp, dsig, drank, df, (const double*)dfro);
@@ -1179,8 +933,8 @@ int svd_batched_device(int batch, const SvdJob* jobs, double er, int64_t maxdim,
     CUDA_TRY(cudaStreamSynchronize(st));
     CUDA_TRY(cudaGetLastError());
     for (int b = 0; b < batch; ++b) {
-        if (k_out) k_out[b] = hk[b];
-        if (disc_out) disc_out[b] = hdisc[b];
+        if (k_out) k_out[perm[b]] = hk[b];
+        if (disc_out) disc_out[perm[b]] = hdisc[b];
     }
     // rank-deficient inputs (rare path): the zeroed null vectors become an orthonormal completion.  The pinned
     // table image is not touched by the GEMMs below, but copy what is needed first: orth_cholqr2 may not reuse it.
@@ -1188,7 +942,7 @@ int svd_batched_device(int batch, const SvdJob* jobs, double er, int64_t maxdim,
     for (int b = 0; b < batch; ++b)
         if (dead[b] > 0 && (rc = complete_null_vectors(jobs[b], tr[b] != 0, dead[b]))) return rc;
     if (sweeps_out) *sweeps_out = sweeps;
-    if (sweeps >= kMaxSweeps) return fail(QTN_ECUDA, "Jacobi SVD did not converge in %d sweeps", kMaxSweeps);
+    if (any_active) return fail(QTN_ECUDA, "Jacobi SVD did not converge in %d sweeps", kMaxSweeps);
     return QTN_OK;
 }
 

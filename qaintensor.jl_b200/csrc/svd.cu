@@ -54,6 +54,7 @@ struct SvdProblem {
     int nblocks;  // ceil(n / JB), rounded up to even
     int* last_mod;  // [nblocks]  launch stamp of the last rotation that touched a column block
     int* last_ok;   // [nblocks * nblocks] launch stamp at which a block pair was last found converged
+    double2* D;     // [nblocks][16 x 16] Gram of each column block (row-major), kept current by the eigensolve kernel
 };
 
 __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
@@ -195,13 +196,122 @@ jacobi_gram_kernel(const SvdProblem* __restrict__ probs, int round, const int* _
     }
 }
 
+// Cross-only Gram (linear-convergence phase): only the 16 x 16 block A_I^H A_J is computed; the two diagonal blocks
+// A_I^H A_I, A_J^H A_J come from the per-block cache SvdProblem::D, which the eigensolve kernel transforms along with
+// every rotation (D' = W^H G W restricted to the block: exact up to rounding, refreshed by a full Gram in round 0 of
+// every sweep and in all polishing sweeps).  4 of the 10 blocks remain, and conj(a) b takes 3 real products:
+//   M1 = x_i x_j, M2 = y_i y_j, M3 = (x_i + y_i)(x_j - y_j):  re = M1 + M2, im = M1 - M2 - M3
+// -> 12 DMMAs per 4 rows instead of 40; the kernel is HBM-bound (every panel element is still read once).
+__global__ void __launch_bounds__(GRAM_THREADS, 2)
+jacobi_gram_cross_kernel(const SvdProblem* __restrict__ probs, int round, const int* __restrict__ rotated, int S, int maxpairs,
+                         double2* __restrict__ Gpart) {
+    const int b = blockIdx.y, pair = blockIdx.x / S, split = blockIdx.x - pair * S;
+    if (rotated[b] < 0) return;
+    const SvdProblem pr = probs[b];
+    int bi, bj;
+    if (!round_pair(pr, round, pair, bi, bj) || pair_idle(pr, bi, bj)) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+    const int m = pr.m;
+    const double2* cp[4];
+    bool cv[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int col = panel_col(i * 8 + g, bi, bj, pr.n);
+        cv[i] = col >= 0;
+        cp[i] = pr.A + (size_t)(col >= 0 ? col : 0) * m;
+    }
+    const int ngroups = (m + 15) >> 4, gper = (ngroups + S - 1) / S;
+    const int g0 = split * gper, g1 = min(ngroups, g0 + gper);
+    double m1[4][2], m2[4][2], m3[4][2];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) m1[k][0] = m1[k][1] = m2[k][0] = m2[k][1] = m3[k][0] = m3[k][1] = 0.0;
+    double2 v[4][4], w[4][4];
+    auto load = [&](double2 (&dst)[4][4], int grp) {
+        const int r = grp * 16 + t;
+#pragma unroll
+        for (int s = 0; s < 4; ++s)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int row = r + 4 * s;
+                dst[s][i] = (cv[i] && row < m) ? __ldcg(cp[i] + row) : make_double2(0.0, 0.0);
+            }
+    };
+    auto compute = [&](const double2 (&f)[4][4]) {
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+            const double sa0 = f[s][0].x + f[s][0].y, sa1 = f[s][1].x + f[s][1].y;
+            const double db2 = f[s][2].x - f[s][2].y, db3 = f[s][3].x - f[s][3].y;
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const int k = 2 * i + j;
+                    dmma(m1[k][0], m1[k][1], f[s][i].x, f[s][2 + j].x);
+                    dmma(m2[k][0], m2[k][1], f[s][i].y, f[s][2 + j].y);
+                    dmma(m3[k][0], m3[k][1], i ? sa1 : sa0, j ? db3 : db2);
+                }
+        }
+    };
+    int grp = g0 + warp;
+    constexpr int NW = GRAM_THREADS / 32;
+    if (grp < g1) load(v, grp);
+    while (grp < g1) {
+        if (grp + NW < g1) load(w, grp + NW);
+        compute(v);
+        grp += NW;
+        if (grp >= g1) break;
+        if (grp + NW < g1) load(v, grp + NW);
+        compute(w);
+        grp += NW;
+    }
+    double gr[4][2], gi[4][2];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int q = 0; q < 2; ++q) { gr[k][q] = m1[k][q] + m2[k][q]; gi[k][q] = m1[k][q] - m2[k][q] - m3[k][q]; }
+    __shared__ double red[2][16][32];
+#pragma unroll
+    for (int stage = 0; stage < 2; ++stage) {  // fixed-order tree over the 4 warps, as in the full kernel
+        const int half = stage == 0 ? 2 : 1;
+        if (warp >= half && warp < 2 * half) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                red[warp - half][4 * k + 0][lane] = gr[k][0];
+                red[warp - half][4 * k + 1][lane] = gr[k][1];
+                red[warp - half][4 * k + 2][lane] = gi[k][0];
+                red[warp - half][4 * k + 3][lane] = gi[k][1];
+            }
+        }
+        __syncthreads();
+        if (warp < half) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                gr[k][0] += red[warp][4 * k + 0][lane];
+                gr[k][1] += red[warp][4 * k + 1][lane];
+                gi[k][0] += red[warp][4 * k + 2][lane];
+                gi[k][1] += red[warp][4 * k + 3][lane];
+            }
+        }
+        __syncthreads();
+    }
+    if (warp == 0) {  // block k = 2 i + (j - 2) as 8 x 8 row-major in the first 256 elements of the partial
+        double2* out = Gpart + ((size_t)((size_t)b * maxpairs + pair) * S + split) * GP_ELEMS;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            out[k * 64 + g * 8 + 2 * t] = make_double2(gr[k][0], gi[k][0]);
+            out[k * 64 + g * 8 + 2 * t + 1] = make_double2(gr[k][1], gi[k][1]);
+        }
+    }
+}
+
 // Rotation of the Hermitian 2x2 pivot [[alpha, g], [conj(g), beta]]: J = [[c, s e^{i phi}], [-s e^{-i phi}, c]].
 struct JRot { double c, s; double2 ph; };
 
 __global__ void __launch_bounds__(ETHREADS, 8)
 jacobi_eig_kernel(const SvdProblem* __restrict__ probs, int round, double tol, int* __restrict__ rotated,
                   const double* __restrict__ fro2, int inner_sweeps, int* __restrict__ stat, int stamp, int S, int maxpairs,
-                  const double2* __restrict__ Gpart, double2* __restrict__ Wbuf, int* __restrict__ pflag) {
+                  const double2* __restrict__ Gpart, double2* __restrict__ Wbuf, int* __restrict__ pflag, int cross,
+                  int* __restrict__ nactive) {
     const int b = blockIdx.y, pair = blockIdx.x, tid = threadIdx.x;
     int* flag = pflag + (size_t)b * maxpairs + pair;
     const SvdProblem pr = probs[b];
@@ -227,9 +337,12 @@ jacobi_eig_kernel(const SvdProblem* __restrict__ probs, int round, double tol, i
     if (tid < JP) s_cols[tid] = panel_col(tid, bi, bj, pr.n);
     if (tid == 0) { s_any = 0; s_rot = 0; }
     for (int i = tid; i < JP * JPITCH; i += ETHREADS) W[i] = make_double2(0, 0);
+    double2* DI = pr.D + (size_t)bi * (JB * JB);
+    double2* DJ = pr.D + (size_t)bj * (JB * JB);
     {
         const double2* gp = Gpart + (size_t)((size_t)b * maxpairs + pair) * S * GP_ELEMS;
-        for (int e = tid; e < GP_ELEMS; e += ETHREADS) {
+        const int nel = cross ? 4 * 64 : GP_ELEMS;
+        for (int e = tid; e < nel; e += ETHREADS) {
             double2 acc = make_double2(0, 0);
             for (int s = 0; s < S; ++s) {  // fixed order: deterministic
                 const double2 v = __ldcg(gp + (size_t)s * GP_ELEMS + e);
@@ -237,16 +350,25 @@ jacobi_eig_kernel(const SvdProblem* __restrict__ probs, int round, double tol, i
                 acc.y += v.y;
             }
             const int k = e >> 6, r8 = (e >> 3) & 7, c8 = e & 7;
-            // k -> (i, j), j >= i: rows of the upper block triangle hold 4, 3, 2, 1 blocks
-            const int i = k < 4 ? 0 : (k < 7 ? 1 : (k < 9 ? 2 : 3));
-            const int j = k - (i == 0 ? 0 : (i == 1 ? 4 : (i == 2 ? 7 : 9))) + i;
+            int i, j;
+            if (cross) { i = k >> 1; j = 2 + (k & 1); }  // the four blocks of A_I^H A_J
+            else {
+                // k -> (i, j), j >= i: rows of the upper block triangle hold 4, 3, 2, 1 blocks
+                i = k < 4 ? 0 : (k < 7 ? 1 : (k < 9 ? 2 : 3));
+                j = k - (i == 0 ? 0 : (i == 1 ? 4 : (i == 2 ? 7 : 9))) + i;
+            }
             G[(i * 8 + r8) * JPITCH + j * 8 + c8] = acc;
         }
+        if (cross)  // diagonal blocks from the cache
+            for (int e = tid; e < 2 * JB * JB; e += ETHREADS) {
+                const int h = e >> 8, r = (e >> 4) & 15, c = e & 15;
+                G[(h * JB + r) * JPITCH + h * JB + c] = __ldcg((h ? DJ : DI) + (e & 255));
+            }
     }
     __syncthreads();
     for (int e = tid; e < JP * JP; e += ETHREADS) {  // mirror the strictly-lower block triangle, W = I
         const int r = e / JP, c = e % JP;
-        if ((r >> 3) > (c >> 3)) { const double2 v = G[c * JPITCH + r]; G[r * JPITCH + c] = make_double2(v.x, -v.y); }
+        if (cross ? (r >= JB && c < JB) : ((r >> 3) > (c >> 3))) { const double2 v = G[c * JPITCH + r]; G[r * JPITCH + c] = make_double2(v.x, -v.y); }
         if (r == c) W[r * JPITCH + c] = make_double2(1.0, 0.0);
     }
     __syncthreads();
@@ -357,7 +479,15 @@ jacobi_eig_kernel(const SvdProblem* __restrict__ probs, int round, double tol, i
         else pr.last_ok[bi * nb + bj] = stamp;
         *flag = any;
         if (any && s_rot) rotated[b] = 1;  // pure re-ordering swaps do not keep the sweeps going
+        if (any) atomicAdd(&nactive[b], 1);
     }
+    // the block Grams after this visit: W^H G W restricted to each block (a full-Gram visit refreshes the cache even
+    // when nothing was rotated)
+    if (any || !cross)
+        for (int e = tid; e < 2 * JB * JB; e += ETHREADS) {
+            const int h = e >> 8, r = (e >> 4) & 15, c = e & 15;
+            (h ? DJ : DI)[e & 255] = G[(h * JB + r) * JPITCH + h * JB + c];
+        }
     if (!any) return;
     double2* wout = Wbuf + (size_t)((size_t)b * maxpairs + pair) * (JP * JP);
     for (int e = tid; e < JP * JP; e += ETHREADS) wout[e] = W[(e >> 5) * JPITCH + (e & 31)];
@@ -372,10 +502,16 @@ jacobi_update_kernel(const SvdProblem* __restrict__ probs, int round, const int*
     int bi, bj;
     if (!round_pair(pr, round, pair, bi, bj)) return;
     __shared__ double2 Ws[JP * JPITCH];
+    constexpr int SP = JP + 4;                 // pitch of the sum plane: conflict-free LDS.64 for the B fragments
+    __shared__ double Wsum[JP * SP];           // re + im of W: the third operand of the 3-multiplication product
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
     {
         const double2* wsrc = Wbuf + (size_t)((size_t)b * maxpairs + pair) * (JP * JP);
-        for (int e = tid; e < JP * JP; e += JTHREADS) Ws[(e >> 5) * JPITCH + (e & 31)] = __ldcg(wsrc + e);
+        for (int e = tid; e < JP * JP; e += JTHREADS) {
+            const double2 wv = __ldcg(wsrc + e);
+            Ws[(e >> 5) * JPITCH + (e & 31)] = wv;
+            Wsum[(e >> 5) * SP + (e & 31)] = wv.x + wv.y;
+        }
     }
     int colk[8], colo[4][2];  // global columns of this lane's A-fragment slots (k = 4 k4 + t) and output slots
 #pragma unroll
@@ -397,18 +533,22 @@ jacobi_update_kernel(const SvdProblem* __restrict__ probs, int round, const int*
 #pragma unroll
         for (int k4 = 0; k4 < 8; ++k4)
             a[k4] = (rok && colk[k4] >= 0) ? __ldcg(base + (size_t)colk[k4] * nrows + row) : make_double2(0.0, 0.0);
-        double cr[4][2], ci[4][2];
+        // 3-multiplication complex product: P1 = sum ar br, P2 = sum ai bi, P3 = sum (ar + ai)(br + bi);
+        // re = P1 - P2, im = P3 - P1 - P2 (96 DMMAs per 8 x 32 tile instead of 128; the rotations stay unitary to
+        // rounding either way, and the Jacobi iteration corrects what the different rounding leaves)
+        double p1[4][2], p2[4][2], p3[4][2];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) cr[j][0] = cr[j][1] = ci[j][0] = ci[j][1] = 0.0;
+        for (int j = 0; j < 4; ++j) p1[j][0] = p1[j][1] = p2[j][0] = p2[j][1] = p3[j][0] = p3[j][1] = 0.0;
 #pragma unroll
         for (int k4 = 0; k4 < 8; ++k4) {
+            const double asum = a[k4].x + a[k4].y;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const double2 bb = Ws[(k4 * 4 + t) * JPITCH + j * 8 + g];
-                dmma(cr[j][0], cr[j][1], a[k4].x, bb.x);
-                dmma(cr[j][0], cr[j][1], -a[k4].y, bb.y);
-                dmma(ci[j][0], ci[j][1], a[k4].x, bb.y);
-                dmma(ci[j][0], ci[j][1], a[k4].y, bb.x);
+                const double bs = Wsum[(k4 * 4 + t) * SP + j * 8 + g];
+                dmma(p1[j][0], p1[j][1], a[k4].x, bb.x);
+                dmma(p2[j][0], p2[j][1], a[k4].y, bb.y);
+                dmma(p3[j][0], p3[j][1], asum, bs);
             }
         }
         if (rok) {
@@ -416,7 +556,8 @@ jacobi_update_kernel(const SvdProblem* __restrict__ probs, int round, const int*
             for (int j = 0; j < 4; ++j)
 #pragma unroll
                 for (int q = 0; q < 2; ++q)
-                    if (colo[j][q] >= 0) base[(size_t)colo[j][q] * nrows + row] = make_double2(cr[j][q], ci[j][q]);
+                    if (colo[j][q] >= 0)
+                        base[(size_t)colo[j][q] * nrows + row] = make_double2(p1[j][q] - p2[j][q], p3[j][q] - p1[j][q] - p2[j][q]);
         }
     }
 }
@@ -688,6 +829,11 @@ struct SvdGroup {
     size_t offG = 0, offW = 0, offF = 0;
     bool active = true;
     int sweeps = 0;
+    long pairs_per_sweep = 0;   // (matrix, block pair) visits of one sweep
+    long prev_active = -1;      // pairs that rotated in the previous sweep (-1: no sweep yet)
+    bool cross = false;         // this sweep runs rounds >= 1 with the cross-only Gram kernel
+    bool was_cross = false;
+    int cross_sweeps = 0;
 };
 
 // Runs the batch; k_out / disc_out are host arrays (batch).  Synchronises the library stream.
@@ -719,7 +865,7 @@ int svd_batched_device(int batch, const SvdJob* jobs_in, double er, int64_t maxd
     // ---- workspace layout (device): per problem [At (if transposed) m*n] [V n*n] [sig n] [rank n] [stamps] ------
     size_t dev_bytes = 0;
     auto al = [&](size_t bytes) { size_t o = dev_bytes; dev_bytes += (bytes + 255) / 256 * 256; return o; };
-    std::vector<size_t> offAt(batch), offV(batch), offSig(batch), offRank(batch), offStamp(batch);
+    std::vector<size_t> offAt(batch), offV(batch), offSig(batch), offRank(batch), offStamp(batch), offD(batch);
     std::vector<double> work(batch);
     int maxn = 0, maxm = 0;
     double total_work = 0;
@@ -732,6 +878,7 @@ int svd_batched_device(int batch, const SvdJob* jobs_in, double er, int64_t maxd
         int nbk = (int)((n + JB - 1) / JB);
         if (nbk & 1) ++nbk;
         offStamp[b] = al((size_t)(nbk + (size_t)nbk * nbk) * 4);
+        offD[b] = al((size_t)nbk * JB * JB * 16);
         maxn = std::max<int>(maxn, (int)n);
         maxm = std::max<int>(maxm, (int)m);
         work[b] = (double)(m + ((jobs[b].need_v || tr[b]) ? n : 0)) * n * n;  // ~ flops of one sweep
@@ -769,6 +916,7 @@ int svd_batched_device(int batch, const SvdJob* jobs_in, double er, int64_t maxd
             grp.maxn = std::max(grp.maxn, n);
             grp.any_v = grp.any_v || jobs[b].need_v || tr[b];
             units += nbk / 2;
+            grp.pairs_per_sweep += (long)(nbk / 2) * (nbk - 1);
         }
         grp.maxpairs = std::max(grp.max_nb / 2, 1);
         // row splits: enough CTAs for ~8 per SM over the whole batch, at least two 16-row (Gram) / 8-row (update)
@@ -785,7 +933,7 @@ int svd_batched_device(int batch, const SvdJob* jobs_in, double er, int64_t maxd
         grp.offF = al(nb_ * grp.maxpairs * 4);                       // apply flags   [problem][pair]
     }
     size_t tab = dev_bytes;
-    size_t tab_bytes = (size_t)batch * (sizeof(SvdProblem) + sizeof(FinishArgs) + 2 * sizeof(void*) + 8 + 8 + 8 + 4 + 4) + 1024;
+    size_t tab_bytes = (size_t)batch * (sizeof(SvdProblem) + sizeof(FinishArgs) + 2 * sizeof(void*) + 8 + 8 + 8 + 4 + 4 + 4) + 1024;
     dev_bytes += (tab_bytes + 255) / 256 * 256;
     if ((rc = work_reserve(dev_bytes, tab_bytes))) return rc;
     char* base = (char*)g_work.dev;
@@ -801,6 +949,7 @@ int svd_batched_device(int batch, const SvdJob* jobs_in, double er, int64_t maxd
     double* hfro = hdisc + batch;
     int* hrot = (int*)(hfro + batch);
     int* hdead = hrot + batch;
+    int* hact = hdead + batch;
     char* dtab = base + tab;
     auto dptr = [&](void* hostp) { return dtab + ((char*)hostp - h); };
     for (int b = 0; b < batch; ++b) {
@@ -815,6 +964,7 @@ int svd_batched_device(int batch, const SvdJob* jobs_in, double er, int64_t maxd
         hp[b].nblocks = nbk;
         hp[b].last_mod = (int*)(base + offStamp[b]);
         hp[b].last_ok = hp[b].last_mod + nbk;
+        hp[b].D = (double2*)(base + offD[b]);
         // last_mod = 1, last_ok = 0: every pair starts "modified after its last check"
         CUDA_TRY(cudaMemsetAsync(hp[b].last_ok, 0, (size_t)nbk * nbk * 4, st));
         set_int_kernel<<<(nbk + 255) / 256, 256, 0, st>>>(hp[b].last_mod, nbk, 1);
@@ -827,6 +977,7 @@ int svd_batched_device(int batch, const SvdJob* jobs_in, double er, int64_t maxd
         hrank[b] = (int*)(base + offRank[b]);
         hrot[b] = 0;
         hdead[b] = 0;
+        hact[b] = 0;
         hfro[b] = 0.0;
     }
     CUDA_TRY(cudaMemcpyAsync(dtab, h, tab_bytes - 1024, cudaMemcpyHostToDevice, st));
@@ -835,6 +986,7 @@ int svd_batched_device(int batch, const SvdJob* jobs_in, double er, int64_t maxd
     double* const* dsig = (double* const*)dptr(hsig);
     int* const* drank = (int* const*)dptr(hrank);
     int* drot = (int*)dptr(hrot);
+    int* dact = (int*)dptr(hact);
     double* dfro = (double*)dptr(hfro);
     for (int b = 0; b < batch; ++b)
         if (tr[b]) {
@@ -851,6 +1003,7 @@ int svd_batched_device(int batch, const SvdJob* jobs_in, double er, int64_t maxd
     if (getenv("QTN_JACOBI_STATS")) { cudaMalloc((void**)&dstat, 2 * 64 * sizeof(int)); cudaMemsetAsync(dstat, 0, 2 * 64 * sizeof(int), st); }
     int inner = kInnerSweeps;
     if (const char* e = getenv("QTN_JACOBI_INNER")) inner = std::max(1, atoi(e));
+    const bool use_cross = [] { const char* e = getenv("QTN_JACOBI_CROSS"); return !(e && atoi(e) == 0); }();  // A/B switch
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     if (dstat) { cudaEventCreate(&ev0); cudaEventCreate(&ev1); cudaEventRecord(ev0, st); }
     // the sub-batch streams start after the set-up work on the library stream
@@ -865,7 +1018,19 @@ int svd_batched_device(int batch, const SvdJob* jobs_in, double er, int64_t maxd
         for (int g = 0; g < ngroups; ++g) {
             SvdGroup& grp = groups[g];
             if (!grp.active) continue;
+            // Gram mode of this sweep: while most pairs still rotate (the linear-convergence phase) only round 0
+            // computes full Grams (which refreshes the per-block cache), the other rounds take the diagonal blocks from
+            // the cache.  The polishing sweeps -- and hence every convergence decision that ends the iteration -- use
+            // full, freshly computed Grams; pairs accepted during a cached sweep are re-verified (stamps reset).
+            grp.cross = use_cross && grp.max_nb > 2 && (grp.prev_active < 0 || grp.prev_active * 4 >= grp.pairs_per_sweep);
+            if (grp.was_cross && !grp.cross)
+                for (int b = grp.b0; b < grp.b1; ++b)
+                    CUDA_TRY(cudaMemsetAsync(hp[b].last_ok, 0, (size_t)hp[b].nblocks * hp[b].nblocks * 4, g_sub[g]));
+            grp.was_cross = grp.cross;
+            grp.cross_sweeps += grp.cross;
+            for (int b = grp.b0; b < grp.b1; ++b) hact[b] = 0;
             CUDA_TRY(cudaMemcpyAsync(drot + grp.b0, hrot + grp.b0, (size_t)(grp.b1 - grp.b0) * 4, cudaMemcpyHostToDevice, g_sub[g]));
+            CUDA_TRY(cudaMemcpyAsync(dact + grp.b0, hact + grp.b0, (size_t)(grp.b1 - grp.b0) * 4, cudaMemcpyHostToDevice, g_sub[g]));
             max_rounds = std::max(max_rounds, grp.max_nb - 1);
         }
         int* st_ptr = dstat ? dstat + 2 * std::min(sweeps, 63) : (int*)nullptr;
@@ -875,11 +1040,16 @@ int svd_batched_device(int batch, const SvdJob* jobs_in, double er, int64_t maxd
                 const SvdGroup& grp = groups[g];
                 if (!grp.active || round >= grp.max_nb - 1) continue;
                 const unsigned nb_ = (unsigned)(grp.b1 - grp.b0);
-                jacobi_gram_kernel<<<dim3((unsigned)(grp.maxpairs * grp.S), nb_), GRAM_THREADS, 0, g_sub[g]>>>(
-                    dp + grp.b0, round, drot + grp.b0, grp.S, grp.maxpairs, (double2*)(base + grp.offG));
+                const int cross = grp.cross && round >= 1;
+                if (cross)
+                    jacobi_gram_cross_kernel<<<dim3((unsigned)(grp.maxpairs * grp.S), nb_), GRAM_THREADS, 0, g_sub[g]>>>(
+                        dp + grp.b0, round, drot + grp.b0, grp.S, grp.maxpairs, (double2*)(base + grp.offG));
+                else
+                    jacobi_gram_kernel<<<dim3((unsigned)(grp.maxpairs * grp.S), nb_), GRAM_THREADS, 0, g_sub[g]>>>(
+                        dp + grp.b0, round, drot + grp.b0, grp.S, grp.maxpairs, (double2*)(base + grp.offG));
                 jacobi_eig_kernel<<<dim3((unsigned)grp.maxpairs, nb_), ETHREADS, 0, g_sub[g]>>>(
                     dp + grp.b0, round, tol, drot + grp.b0, (const double*)dfro + grp.b0, inner, st_ptr, stamp, grp.S, grp.maxpairs,
-                    (const double2*)(base + grp.offG), (double2*)(base + grp.offW), (int*)(base + grp.offF));
+                    (const double2*)(base + grp.offG), (double2*)(base + grp.offW), (int*)(base + grp.offF), cross, dact + grp.b0);
                 jacobi_update_kernel<<<dim3((unsigned)(grp.maxpairs * grp.SU), nb_), JTHREADS, 0, g_sub[g]>>>(
                     dp + grp.b0, round, drot + grp.b0, grp.SU, grp.maxpairs, (const double2*)(base + grp.offW), (const int*)(base + grp.offF));
                 count_launch(3);
@@ -888,7 +1058,9 @@ int svd_batched_device(int batch, const SvdJob* jobs_in, double er, int64_t maxd
         CUDA_TRY(cudaGetLastError());
         for (int g = 0; g < ngroups; ++g) {
             const SvdGroup& grp = groups[g];
-            if (grp.active) CUDA_TRY(cudaMemcpyAsync(hrot + grp.b0, drot + grp.b0, (size_t)(grp.b1 - grp.b0) * 4, cudaMemcpyDeviceToHost, g_sub[g]));
+            if (!grp.active) continue;
+            CUDA_TRY(cudaMemcpyAsync(hrot + grp.b0, drot + grp.b0, (size_t)(grp.b1 - grp.b0) * 4, cudaMemcpyDeviceToHost, g_sub[g]));
+            CUDA_TRY(cudaMemcpyAsync(hact + grp.b0, dact + grp.b0, (size_t)(grp.b1 - grp.b0) * 4, cudaMemcpyDeviceToHost, g_sub[g]));
         }
         any_active = false;
         for (int g = 0; g < ngroups; ++g) {
@@ -896,8 +1068,11 @@ int svd_batched_device(int batch, const SvdJob* jobs_in, double er, int64_t maxd
             if (!grp.active) continue;
             CUDA_TRY(cudaStreamSynchronize(g_sub[g]));
             bool any = false;
+            grp.prev_active = 0;
             for (int b = grp.b0; b < grp.b1; ++b) {
-                if (hrot[b] > 0) { any = true; hrot[b] = 0; }
+                grp.prev_active += hact[b];
+                // a matrix is only retired by a sweep whose convergence checks all used freshly computed Grams
+                if (hrot[b] > 0 || grp.cross) { any = true; hrot[b] = 0; }
                 else hrot[b] = -1;
             }
             grp.sweeps = sweeps + 1;
@@ -917,7 +1092,8 @@ int svd_batched_device(int batch, const SvdJob* jobs_in, double er, int64_t maxd
         fprintf(stderr, "[jacobi] batch=%d maxm=%d maxn=%d sweeps=%d %.3f ms (%.3f ms/sweep); groups:", batch, maxm, maxn, sweeps, ms,
                 ms / std::max(sweeps, 1));
         for (const auto& grp : groups)
-            fprintf(stderr, " [%d..%d) n<=%d m<=%d v=%d S=%d SU=%d sweeps=%d;", grp.b0, grp.b1, grp.maxn, grp.maxm, (int)grp.any_v, grp.S, grp.SU, grp.sweeps);
+            fprintf(stderr, " [%d..%d) n<=%d m<=%d v=%d S=%d SU=%d sweeps=%d (%d cached-Gram);", grp.b0, grp.b1, grp.maxn, grp.maxm, (int)grp.any_v, grp.S,
+                    grp.SU, grp.sweeps, grp.cross_sweeps);
         fprintf(stderr, " (idle,active) pairs per sweep:");
         for (int i = 0; i < sweeps && i < 64; ++i) fprintf(stderr, " (%d,%d)", hs[2 * i], hs[2 * i + 1]);
         fprintf(stderr, "\n");

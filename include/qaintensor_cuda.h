@@ -139,7 +139,9 @@ int qtn_plan_create(int32_t nt, const int32_t* ranks, const int64_t* const* dims
 int qtn_plan_destroy(qtn_plan* plan);
 /* Deterministic greedy slice-label choice (rule in DESIGN.md / oracle/plan.py):
  * slice until the largest tensor has <= 2^max_log2_elems elements and there are
- * at least min_slices slices.  Host-only.  labels_out capacity = ncontr.         */
+ * at least min_slices slices.  Host-only.  labels_out capacity = ncontr.
+ * QTN_EDOMAIN (labels found so far still returned) when the target cannot be met:
+ * the largest tensor has only open / extent-1 labels left, or too few slices exist. */
 int qtn_choose_slices(int32_t nt, const int32_t* ranks, const int64_t* const* dims,
                       const int32_t* const* labels, const int32_t* order, int32_t norder,
                       int32_t max_log2_elems, int64_t min_slices, int32_t* labels_out,

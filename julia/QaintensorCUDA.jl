@@ -67,6 +67,23 @@ function treewidth_perm(ntensors::Integer, pairs::Vector{NTuple{4,Int}})
     Int.(perm[1:nc]), Int(tw[])
 end
 
+# Drop-in for `Qaintensor.optimize_contraction_order!(net)` (src/network2graph.jl:473-479) on the reference's own
+# network types (duck-typed: `tensors`, `contractions::Vector{Summation}` with `idx::Vector{Pair}`, `openidx`): the
+# permutation comes from the bit-exact C++ restatement, the warning and error texts are the reference's
+# (src/network2graph.jl:474 and :122 -- `line_graph` warns too -- and :59).
+function optimize_contraction_order!(net)
+    (length(net.openidx) == 0) || @warn("For TensorNetworks with open indices the treewidth algorithm is unlikely to optimize performance")
+    (length(net.openidx) == 0) || @warn("All open indices are disregarded")
+    pairs = NTuple{4,Int}[]
+    for s in net.contractions
+        length(s.idx) == 2 || error("Contractions of more than 2 tensors not supported")
+        push!(pairs, (Int(s.idx[1].first), Int(s.idx[1].second), Int(s.idx[2].first), Int(s.idx[2].second)))
+    end
+    perm, _ = treewidth_perm(length(net.tensors), pairs)
+    net.contractions = net.contractions[perm]
+    nothing
+end
+
 # ---- EXTENSION: searched contraction order (opt-in replacement of optimize_contraction_order!'s heuristic) ----
 # `network` as for `ncon` (positive labels = contractions); returns the label sequence to pass as `order`,
 # equivalently the permutation `perm` with `net.contractions = net.contractions[perm]`.

@@ -141,8 +141,10 @@ def execute_tree(tensors, network, nodes, steps, fixed=None, stats=None):
     fixed = fixed or {}
     vals = []
     for arr, lab in zip(tensors, network):
-        a, l = _trace_repeated(np.asarray(arr), lab)
-        vals.append(_index_fixed(a, l, fixed))
+        # fix the sliced labels first: a sliced label that sits twice on one tensor (self-contraction) then reads the
+        # diagonal element, and the sum over the slices is the trace; only the remaining repeats are traced here
+        a, l = _index_fixed(np.asarray(arr), list(lab), fixed)
+        vals.append(_trace_repeated(a, l))
     vals += [None] * len(steps)
     for a, b, o, _ in steps:
         A, la = vals[a]

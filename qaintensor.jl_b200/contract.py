@@ -155,16 +155,26 @@ class ContractionPlan:
             pass
 
 
-def choose_slices(shapes, labels, order=None, max_log2_elems=28, min_slices=1):
-    """Deterministic greedy slice-label choice (EXTENSION; rule in DESIGN.md)."""
+def choose_slices(shapes, labels, order=None, max_log2_elems=28, min_slices=1, allow_partial=False):
+    """Deterministic greedy slice-label choice (EXTENSION; rule in DESIGN.md).  Raises ``QtnError`` (QTN_EDOMAIN) when
+    the target cannot be met -- the largest tensor has only open / extent-1 labels left, or fewer than ``min_slices``
+    slices exist; ``allow_partial=True`` returns the labels found up to that point instead."""
     args = NetworkArgs(shapes, labels)
     ncap = max(sum(len(l) for l in labels), 1)
     out = (C.c_int32 * ncap)()
     n = C.c_int32(0)
     ord_arr = arr_i32(order) if order is not None else None
-    check(lib.qtn_choose_slices(args.nt, args.ranks, args.dims, args.labels, ord_arr,
-                                len(order) if order is not None else 0, max_log2_elems, min_slices, out, C.byref(n)))
-    return [int(out[i]) for i in range(n.value)]
+    rc = lib.qtn_choose_slices(args.nt, args.ranks, args.dims, args.labels, ord_arr,
+                               len(order) if order is not None else 0, max_log2_elems, min_slices, out, C.byref(n))
+    found = [int(out[i]) for i in range(n.value)]
+    if rc == _lib.QTN_EDOMAIN and allow_partial:
+        return found
+    if rc == _lib.QTN_EDOMAIN:  # target not reachable (largest tensor has only open / extent-1 labels left, or too few slices)
+        err = _lib.QtnError(rc, lib.qtn_last_error().decode("utf-8", "replace"))
+        err.partial_labels = found   # what the rule found before it ran out of labels
+        raise err
+    check(rc)
+    return found
 
 
 def search_order(shapes, labels, ntrials=256, seed=0, max_log2_elems=-1):

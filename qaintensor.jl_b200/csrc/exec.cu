@@ -196,6 +196,7 @@ struct DevPlan {
     size_t h_stage_bytes = 0;
     cudaGraphExec_t graph = nullptr;
     void* graph_out = nullptr;
+    void* last_out = nullptr;   // output buffer of the previous execute (a graph is captured on its second use)
     bool uploaded = false;
     bool invariants_done = false;
     int graph_launches = 0;
@@ -244,16 +245,22 @@ int plan_device_init(Plan* p) {
     ALLOC(d->pos, pos.size() * 4 + 4);
     ALLOC(d->stride, stride.size() * 8 + 8);
 #undef ALLOC
-    CUDA_TRY(cudaMemcpy(d->tables, p->tables.data(), p->tables.size() * 8, cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaMemcpy(d->first, first.data(), first.size() * 4, cudaMemcpyHostToDevice));
+    // every failure below releases the half-built device state too (p->dev must never survive without its staging
+    // buffer: plan_upload would take the "already initialised" exit and write through a null pointer)
+#define INIT_TRY(expr)                                                                                        \
+    if ((e = (expr)) != cudaSuccess)                                                                          \
+        return guard_fail(fail(QTN_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e), __FILE__, __LINE__));
+    INIT_TRY(cudaMemcpy(d->tables, p->tables.data(), p->tables.size() * 8, cudaMemcpyHostToDevice));
+    INIT_TRY(cudaMemcpy(d->first, first.data(), first.size() * 4, cudaMemcpyHostToDevice));
     if (!pos.empty()) {
-        CUDA_TRY(cudaMemcpy(d->pos, pos.data(), pos.size() * 4, cudaMemcpyHostToDevice));
-        CUDA_TRY(cudaMemcpy(d->stride, stride.data(), stride.size() * 8, cudaMemcpyHostToDevice));
-        CUDA_TRY(cudaMemcpy(d->slice_dims, p->slice_dims.data(), p->slice_dims.size() * 8, cudaMemcpyHostToDevice));
+        INIT_TRY(cudaMemcpy(d->pos, pos.data(), pos.size() * 4, cudaMemcpyHostToDevice));
+        INIT_TRY(cudaMemcpy(d->stride, stride.data(), stride.size() * 8, cudaMemcpyHostToDevice));
+        INIT_TRY(cudaMemcpy(d->slice_dims, p->slice_dims.data(), p->slice_dims.size() * 8, cudaMemcpyHostToDevice));
     }
-    CUDA_TRY(cudaMemset(d->soff, 0, (size_t)p->nt * 8));
+    INIT_TRY(cudaMemset(d->soff, 0, (size_t)p->nt * 8));
     d->h_stage_bytes = (size_t)p->input_elems * d->es;
-    CUDA_TRY(cudaMallocHost(&d->h_stage, std::max<size_t>(d->h_stage_bytes, 256)));
+    INIT_TRY(cudaMallocHost(&d->h_stage, std::max<size_t>(d->h_stage_bytes, 256)));
+#undef INIT_TRY
     return QTN_OK;
 }
 
@@ -484,13 +491,19 @@ int plan_execute(Plan* p, int64_t s0, int64_t s1, void* dev_out) {
         count_launch(1);
     }
     if (!d->graph || d->graph_out != dev_out) {
-        if (d->graph) { cudaGraphExecDestroy(d->graph); d->graph = nullptr; }
+        if (d->graph) { cudaGraphExecDestroy(d->graph); d->graph = nullptr; d->graph_out = nullptr; }
         // make sure every kernel's max-smem attribute is set outside capture: warm-run slice s0 directly
         int64_t before = launch_count(0);
         int rc = enqueue_slice(p, d, dev_out, g_stream, false);
         if (rc) return rc;
         d->graph_launches = (int)(launch_count(0) - before);
         ++s0;
+        // A graph pays only when it is launched: one-shot calls (qtn_contract / ncon / qtn_net_contract, a single-slice
+        // plan's first execute) stop here.  It is captured when slices remain, or on the second execute into the same
+        // output buffer (repeated single-slice executes: amplitude sweeps).
+        const bool again = d->last_out == dev_out;
+        d->last_out = dev_out;
+        if (s0 >= s1 && !again) return QTN_OK;
         cudaGraph_t graph;
         CUDA_TRY(cudaStreamBeginCapture(g_stream, cudaStreamCaptureModeThreadLocal));
         int64_t keep = launch_count(0);

@@ -236,10 +236,15 @@ int qtn_mps_create(int32_t nsites, const void* const* host_sites, const int64_t*
     m->rb.assign(rbond, rbond + nsites);
     const size_t sb = (size_t)2 * m->cap * m->cap * 16;
     for (int i = 0; i < nsites; ++i) {
+        if (!host_sites[i]) { qtn_mps_destroy(m); return fail(QTN_EINVAL, "qtn_mps_create: site %d is a null pointer", i + 1); }
         if (cudaMalloc((void**)&m->site[i], sb) != cudaSuccess) { qtn_mps_destroy(m); return fail(QTN_ENOMEM, "qtn_mps_create: out of device memory"); }
-        cudaMemcpyAsync(m->site[i], host_sites[i], (size_t)lbond[i] * 2 * rbond[i] * 16, cudaMemcpyHostToDevice, stream());
+        cudaError_t e = cudaMemcpyAsync(m->site[i], host_sites[i], (size_t)lbond[i] * 2 * rbond[i] * 16, cudaMemcpyHostToDevice, stream());
+        if (e != cudaSuccess) { qtn_mps_destroy(m); return fail(QTN_ECUDA, "qtn_mps_create: upload of site %d failed: %s", i + 1, cudaGetErrorString(e)); }
     }
-    cudaStreamSynchronize(stream());
+    {
+        cudaError_t e = cudaStreamSynchronize(stream());
+        if (e != cudaSuccess) { qtn_mps_destroy(m); return fail(QTN_ECUDA, "qtn_mps_create: %s", cudaGetErrorString(e)); }
+    }
     *mps_out = m;
     return QTN_OK;
 }
@@ -477,7 +482,11 @@ int qtn_mps_apply_mpo(qtn_mps* m, const void* const* host_mpo_sites, const int64
         rb[i] = r;
         lb[i + 1] = r;
     }
-    // 3. right-to-left sweep: truncate (er, maxdim); site i <- Vh[:k], site i-1 <- site_{i-1} * (U[:, :k] S)
+    // 3. right-to-left sweep: truncate (er, maxdim); site i <- Vh[:k], site i-1 <- site_{i-1} * (U[:, :k] S).
+    // The compressed sites go to temporaries and are committed to the handle only after the whole sweep succeeded:
+    // a failure mid-sweep (memory, SVD non-convergence, capacity) leaves the MPS exactly as it was.
+    std::vector<DevBuf> comp(n);
+    std::vector<int64_t> new_lb(n), new_rb(n);
     for (int i = n - 1; i >= 1; --i) {
         const int64_t mm = lb[i], nn = 2 * rb[i], r = std::min(mm, nn);
         SvdJob job{(double2*)fat[i].p, mm, nn, (double2*)U.p, (double*)S.p, (double2*)Vh.p};
@@ -487,19 +496,25 @@ int qtn_mps_apply_mpo(qtn_mps* m, const void* const* host_mpo_sites, const int64
         k = std::max<int64_t>(k, 1);
         if (disc_out) disc_out[i - 1] = disc;
         if ((size_t)k * nn > (size_t)2 * m->cap * m->cap) return fail(QTN_ENOMEM, "compressed site %d exceeds the MPS capacity", i + 1);
-        if ((rc = scale_copy((double2*)Vh.p, r, m->site[i], k, k, nn, nullptr, 0))) return rc;     // (k, 2, rb)
+        if ((rc = comp[i].alloc((size_t)k * nn * 16))) return rc;
+        if ((rc = scale_copy((double2*)Vh.p, r, (double2*)comp[i].p, k, k, nn, nullptr, 0))) return rc;     // (k, 2, rb)
         if ((rc = scale_copy((double2*)U.p, mm, (double2*)C.p, mm, mm, k, (double*)S.p, 1))) return rc;  // U[:, :k] S
         const int64_t rows = lb[i - 1] * 2;
         if ((rc = qtn_zgemm_device('N', 'N', rows, k, mm, fat[i - 1].p, rows, C.p, mm, T.p, rows))) return rc;
         CUDA_TRY(cudaMemcpyAsync(fat[i - 1].p, T.p, (size_t)rows * k * 16, cudaMemcpyDeviceToDevice, st));
-        m->lb[i] = k;
-        m->rb[i] = rb[i];
+        new_lb[i] = k;
+        new_rb[i] = rb[i];
         rb[i - 1] = k;
     }
     if ((size_t)lb[0] * 2 * rb[0] > (size_t)2 * m->cap * m->cap) return fail(QTN_ENOMEM, "compressed site 1 exceeds the MPS capacity");
-    CUDA_TRY(cudaMemcpyAsync(m->site[0], fat[0].p, (size_t)lb[0] * 2 * rb[0] * 16, cudaMemcpyDeviceToDevice, st));
-    m->lb[0] = lb[0];
-    m->rb[0] = rb[0];
+    CUDA_TRY(cudaStreamSynchronize(st));  // everything computed: commit
+    for (int i = 0; i < n; ++i) {
+        const void* src = i == 0 ? fat[0].p : comp[i].p;
+        const int64_t l = i == 0 ? lb[0] : new_lb[i], r = i == 0 ? rb[0] : new_rb[i];
+        CUDA_TRY(cudaMemcpyAsync(m->site[i], src, (size_t)l * 2 * r * 16, cudaMemcpyDeviceToDevice, st));
+        m->lb[i] = l;
+        m->rb[i] = r;
+    }
     CUDA_TRY(cudaStreamSynchronize(st));
     return QTN_OK;
 }

@@ -167,6 +167,7 @@ int qtn_net_tensor(const qtn_net* net, int32_t i, int32_t* rank_out, int64_t* di
 int qtn_net_tensor_circuit(qtn_net* net, int32_t ngates, const int32_t* nwires, const int32_t* wires,
                            const void* const* matrices) {
     if (!net || ngates < 0 || (ngates > 0 && (!nwires || !wires || !matrices))) return fail(QTN_EINVAL, "qtn_net_tensor_circuit: bad argument");
+    // validate every gate before the first one is appended: a bad gate must not leave a half-extended network
     size_t w0 = 0;
     for (int g = 0; g < ngates; ++g) {
         const int M = nwires[g];
@@ -179,8 +180,13 @@ int qtn_net_tensor_circuit(qtn_net* net, int32_t ngates, const int32_t* nwires, 
             need = std::max(need, w);
         }
         if (need > (int)net->openidx.size()) return fail(QTN_EINVAL, "gate needs more wires than the network has open legs");
+        if (!matrices[g]) return fail(QTN_EINVAL, "gate %d: null matrix", g + 1);
+        w0 += (size_t)M;
+    }
+    w0 = 0;
+    for (int g = 0; g < ngates; ++g) {
+        const int M = nwires[g];
         const cplx* src = static_cast<const cplx*>(matrices[g]);
-        if (!src) return fail(QTN_EINVAL, "gate %d: null matrix", g + 1);
         NetTensor t;
         t.dims.assign(2 * M, 2);
         t.data.assign(src, src + ((size_t)1 << (2 * M)));

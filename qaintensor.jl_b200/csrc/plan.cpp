@@ -286,6 +286,13 @@ int choose_slices(int nt, const int32_t* ranks, const int64_t* const* dims, cons
     SliceChoice R = choose_slices_sym(P, T, max_log2, min_slices);
     for (size_t i = 0; i < R.labels.size(); ++i) labels_out[i] = R.labels[i];
     *nlabels_out = (int)R.labels.size();
+    // the rule runs out of labels when the largest tensor carries only open or extent-1 labels: say so here instead
+    // of letting the caller discover it as a failed allocation (the labels found so far are still returned)
+    if (R.per_slice.mx > ((int64_t)1 << max_log2))
+        return fail(QTN_EDOMAIN, "qtn_choose_slices: cannot slice below 2^%d elements: after %d labels the largest tensor still has %lld "
+                    "(its remaining labels are open or of extent 1)", max_log2, (int)R.labels.size(), (long long)R.per_slice.mx);
+    if (R.nslices < (unsigned __int128)std::max<int64_t>(min_slices, 1))
+        return fail(QTN_EDOMAIN, "qtn_choose_slices: only %lld slices available, %lld requested", (long long)R.nslices, (long long)min_slices);
     return QTN_OK;
 }
 
@@ -699,6 +706,9 @@ int build_plan(int nt, const int32_t* ranks, const int64_t* const* dims, const i
         pl.slice_dims.push_back(P.ldim[l]);
         pl.nslices *= P.ldim[l];
     }
+    // A sliced label that is a self-contraction (both legs on ONE tensor) needs no special case: both legs are
+    // dropped from the node and each contributes its stride to the slice offset, so slice d reads the diagonal
+    // T[.., d, .., d, ..] and the sum over the slices is the trace (tests/test_host_planner.py, test_gpu_contract.py).
     // ---- input nodes (sliced modes dropped, original strides kept) ------------
     std::vector<std::vector<int64_t>> node_strides;
     std::vector<std::vector<int>> full;  // per node: labels incl. sliced ones (drive the walk)
@@ -793,7 +803,6 @@ int build_plan(int nt, const int32_t* ranks, const int64_t* const* dims, const i
         {
             std::vector<int> f;
             for (int l : full[i]) if (std::count(full[i].begin(), full[i].end(), l) == 1) f.push_back(l);
-            for (int l : tr) if (sl.count(l)) return fail(QTN_EINVAL, "slice label %d is a self-contraction", l);
             full.push_back(f);
         }
         pl.steps.push_back(s);

@@ -43,7 +43,10 @@ int launch_gemm(GemmArgs& g, int variant, int split_k, cudaStream_t st);
 constexpr int JB = 16;        // column block width
 constexpr int JP = 2 * JB;    // panel width (columns per CTA)
 constexpr int JPITCH = JP + 2;
-constexpr int JTHREADS = 256;    // update kernel: 8 warps
+#ifndef QTN_UPDATE_THREADS
+#define QTN_UPDATE_THREADS 128
+#endif
+constexpr int JTHREADS = QTN_UPDATE_THREADS;  // update kernel: small CTAs pack next to the eigensolve CTAs of other streams
 constexpr int ETHREADS = 128;    // eigensolve kernel: small CTAs that co-reside with the DMMA kernels of another stream
 constexpr int kInnerSweeps = 1;  // one eigen-sweep per Gram visit measured fastest (1: 108 ms, 2: 153, 3: 165, 6: 187 ms for 1024^2)
 
@@ -59,6 +62,29 @@ struct SvdProblem {
 
 __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
     asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// ---- optional CTA-level tracer (QTN_JACOBI_TRACE=<file>): every working CTA of the round kernels of ONE sweep
+// records (kind, SM id, start, end) from %globaltimer -- the concurrent timeline of the sub-batch streams, which ncu
+// (it serialises kernels) cannot show.  No cost when off (one predictable branch on a __device__ pointer).
+__device__ unsigned long long* d_trace_buf = nullptr;
+__device__ unsigned int d_trace_cap = 0;
+__device__ unsigned int d_trace_cnt = 0;
+__device__ __forceinline__ unsigned long long trace_now() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void trace_end(int kind, unsigned long long t0) {
+    if (d_trace_buf == nullptr || threadIdx.x != 0) return;
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    const unsigned i = atomicAdd(&d_trace_cnt, 1u);
+    if (i < d_trace_cap) {
+        d_trace_buf[3 * (size_t)i] = (unsigned long long)kind | ((unsigned long long)smid << 8) | ((unsigned long long)blockIdx.y << 24);
+        d_trace_buf[3 * (size_t)i + 1] = t0;
+        d_trace_buf[3 * (size_t)i + 2] = trace_now();
+    }
 }
 
 // column index of panel slot c (0..31) or -1 when outside the matrix
@@ -105,6 +131,7 @@ jacobi_gram_kernel(const SvdProblem* __restrict__ probs, int round, const int* _
     const SvdProblem pr = probs[b];
     int bi, bj;
     if (!round_pair(pr, round, pair, bi, bj) || pair_idle(pr, bi, bj)) return;
+    const unsigned long long trace_t0 = d_trace_buf ? trace_now() : 0ull;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
     const int m = pr.m;
     // lane (g, t) holds P[row 4s + t][column 8i + g] of every 16-row group: the A fragment (as conj) and the B fragment
@@ -194,6 +221,7 @@ jacobi_gram_kernel(const SvdProblem* __restrict__ probs, int round, const int* _
             out[k * 64 + g * 8 + 2 * t + 1] = make_double2(gr[k][1], gi[k][1]);
         }
     }
+    trace_end(0, trace_t0);
 }
 
 // Cross-only Gram (linear-convergence phase): only the 16 x 16 block A_I^H A_J is computed; the two diagonal blocks
@@ -210,6 +238,7 @@ jacobi_gram_cross_kernel(const SvdProblem* __restrict__ probs, int round, const 
     const SvdProblem pr = probs[b];
     int bi, bj;
     if (!round_pair(pr, round, pair, bi, bj) || pair_idle(pr, bi, bj)) return;
+    const unsigned long long trace_t0 = d_trace_buf ? trace_now() : 0ull;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
     const int m = pr.m;
     const double2* cp[4];
@@ -302,6 +331,7 @@ jacobi_gram_cross_kernel(const SvdProblem* __restrict__ probs, int round, const 
             out[k * 64 + g * 8 + 2 * t + 1] = make_double2(gr[k][1], gi[k][1]);
         }
     }
+    trace_end(1, trace_t0);
 }
 
 // Rotation of the Hermitian 2x2 pivot [[alpha, g], [conj(g), beta]]: J = [[c, s e^{i phi}], [-s e^{-i phi}, c]].
@@ -324,6 +354,7 @@ jacobi_eig_kernel(const SvdProblem* __restrict__ probs, int round, double tol, i
         }
         return;
     }
+    const unsigned long long trace_t0 = d_trace_buf ? trace_now() : 0ull;
     const int nb = pr.nblocks;
     // deflation: a column below 1e-15 * ||A||_F is rounding noise (LAPACK resolves nothing there either); rotating it
     // against a large, exactly parallel column would only shrink it by eps per sweep until it underflows
@@ -488,12 +519,13 @@ jacobi_eig_kernel(const SvdProblem* __restrict__ probs, int round, double tol, i
             const int h = e >> 8, r = (e >> 4) & 15, c = e & 15;
             (h ? DJ : DI)[e & 255] = G[(h * JB + r) * JPITCH + h * JB + c];
         }
-    if (!any) return;
+    if (!any) { trace_end(2, trace_t0); return; }
     double2* wout = Wbuf + (size_t)((size_t)b * maxpairs + pair) * (JP * JP);
     for (int e = tid; e < JP * JP; e += ETHREADS) wout[e] = W[(e >> 5) * JPITCH + (e & 31)];
+    trace_end(2, trace_t0);
 }
 
-__global__ void __launch_bounds__(JTHREADS, 2)
+__global__ void __launch_bounds__(JTHREADS, 512 / JTHREADS)
 jacobi_update_kernel(const SvdProblem* __restrict__ probs, int round, const int* __restrict__ rotated, int SU, int maxpairs,
                      const double2* __restrict__ Wbuf, const int* __restrict__ pflag) {
     const int b = blockIdx.y, pair = blockIdx.x / SU, chunk = blockIdx.x - pair * SU;
@@ -501,6 +533,7 @@ jacobi_update_kernel(const SvdProblem* __restrict__ probs, int round, const int*
     const SvdProblem pr = probs[b];
     int bi, bj;
     if (!round_pair(pr, round, pair, bi, bj)) return;
+    const unsigned long long trace_t0 = d_trace_buf ? trace_now() : 0ull;
     __shared__ double2 Ws[JP * JPITCH];
     constexpr int SP = JP + 4;                 // pitch of the sum plane: conflict-free LDS.64 for the B fragments
     __shared__ double Wsum[JP * SP];           // re + im of W: the third operand of the 3-multiplication product
@@ -560,6 +593,7 @@ jacobi_update_kernel(const SvdProblem* __restrict__ probs, int round, const int*
                         base[(size_t)colo[j][q] * nrows + row] = make_double2(p1[j][q] - p2[j][q], p3[j][q] - p1[j][q] - p2[j][q]);
         }
     }
+    trace_end(3, trace_t0);
 }
 
 __global__ void set_int_kernel(int* p, int n, int v) {
@@ -810,12 +844,29 @@ static int work_reserve(size_t bytes, size_t hbytes) {
 
 // Sub-batch streams: independent groups of matrices run their rounds concurrently (created once, never destroyed).
 constexpr int kMaxGroups = 4;
-static cudaStream_t g_sub[kMaxGroups] = {nullptr, nullptr, nullptr, nullptr};
+static cudaStream_t g_sub[kMaxGroups] = {nullptr, nullptr, nullptr, nullptr};    // Gram / update kernels of a sub-batch
+static cudaStream_t g_subE[kMaxGroups] = {nullptr, nullptr, nullptr, nullptr};   // its eigensolve kernels (high priority)
+static cudaEvent_t g_evG[kMaxGroups], g_evE[kMaxGroups];
 static cudaEvent_t g_sub_ev = nullptr;
 
+// Every sub-batch has its own stream; its eigensolve runs on a HIGH-priority companion stream, chained by events.
+// Measured with the CTA tracer (tools/jacobi_trace.py): a tensor-pipe kernel in flight fills every SM's register file,
+// so at equal priority the pending eigensolve CTAs of the other sub-batches wait until it drains, after which all
+// eigensolves run together with the tensor pipe idle (26 % of a sweep).  With priority they take the slots the
+// running update kernel frees continuously (tensor pipe idle 18 %).  Two alternatives were measured and dropped:
+// a per-sweep phase skew between the streams (they fall back into lock-step within a millisecond: convoy effect) and
+// an explicit software pipeline with all tensor-pipe kernels on one stream in interleaved sub-batch order (10 %
+// slower: every kernel boundary then exposes its partial last wave, which independent streams back-fill).
 static int sub_streams_init() {
     if (g_sub_ev) return QTN_OK;
-    for (int g = 0; g < kMaxGroups; ++g) CUDA_TRY(cudaStreamCreateWithFlags(&g_sub[g], cudaStreamNonBlocking));
+    int lo = 0, hi = 0;
+    CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));  // lo = least, hi = greatest (numerically lower)
+    for (int g = 0; g < kMaxGroups; ++g) {
+        CUDA_TRY(cudaStreamCreateWithPriority(&g_sub[g], cudaStreamNonBlocking, lo));
+        CUDA_TRY(cudaStreamCreateWithPriority(&g_subE[g], cudaStreamNonBlocking, hi));
+        CUDA_TRY(cudaEventCreateWithFlags(&g_evG[g], cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&g_evE[g], cudaEventDisableTiming));
+    }
     CUDA_TRY(cudaEventCreateWithFlags(&g_sub_ev, cudaEventDisableTiming));
     return QTN_OK;
 }
@@ -890,12 +941,19 @@ int svd_batched_device(int batch, const SvdJob* jobs_in, double er, int64_t maxd
     if (total_work < 4e9) ngroups = 1;  // small problems: launch-latency-bound, one stream
     std::vector<SvdGroup> groups;
     {
+        // cumulative work shares of the sub-batches.  QTN_JACOBI_SKEW=x (default 0 = equal shares) makes them unequal
+        // (share of group g proportional to 1 + x g): equal sub-batches have equal round periods and phase-lock.
+        double skew = 0.0;
+        if (const char* e = getenv("QTN_JACOBI_SKEW")) skew = atof(e);
+        std::vector<double> cum(ngroups + 1, 0.0);
+        for (int g = 0; g < ngroups; ++g) cum[g + 1] = cum[g] + 1.0 + skew * g;
+        for (int g = 0; g <= ngroups; ++g) cum[g] /= cum[ngroups];
         double acc = 0;
         int start = 0;
         for (int b = 0; b < batch; ++b) {
             acc += work[b];
             const int g = (int)groups.size();
-            if (b + 1 == batch || (g + 1 < ngroups && acc >= total_work * (g + 1) / ngroups && batch - (b + 1) >= ngroups - (g + 1))) {
+            if (b + 1 == batch || (g + 1 < ngroups && acc >= total_work * cum[g + 1] && batch - (b + 1) >= ngroups - (g + 1))) {
                 SvdGroup grp;
                 grp.b0 = start;
                 grp.b1 = b + 1;
@@ -924,7 +982,7 @@ int svd_batched_device(int batch, const SvdJob* jobs_in, double er, int64_t maxd
         const long target = std::max<long>(148 * 8 / ngroups, 1);
         const long ggroups = (grp.maxm + 15) / 16, ugroups = (grp.maxm + 7) / 8 + (grp.any_v ? (grp.maxn + 7) / 8 : 0);
         grp.S = (int)std::max<long>(1, std::min<long>((target + units - 1) / units, ggroups / 8));
-        grp.SU = (int)std::max<long>(1, std::min<long>((target + units - 1) / units, ugroups / 16));
+        grp.SU = (int)std::max<long>(1, std::min<long>((target * (256 / JTHREADS) + units - 1) / units, ugroups / (2 * (JTHREADS / 32))));
         if (const char* e = getenv("QTN_JACOBI_S")) grp.S = std::max(1, atoi(e));
         if (const char* e = getenv("QTN_JACOBI_SU")) grp.SU = std::max(1, atoi(e));
         const size_t nb_ = (size_t)(grp.b1 - grp.b0);
@@ -1003,6 +1061,7 @@ int svd_batched_device(int batch, const SvdJob* jobs_in, double er, int64_t maxd
     if (getenv("QTN_JACOBI_STATS")) { cudaMalloc((void**)&dstat, 2 * 64 * sizeof(int)); cudaMemsetAsync(dstat, 0, 2 * 64 * sizeof(int), st); }
     int inner = kInnerSweeps;
     if (const char* e = getenv("QTN_JACOBI_INNER")) inner = std::max(1, atoi(e));
+    const bool eig_priority = [] { const char* e = getenv("QTN_JACOBI_EIGPRIO"); return !(e && atoi(e) == 0); }();  // A/B switch
     const bool use_cross = [] { const char* e = getenv("QTN_JACOBI_CROSS"); return !(e && atoi(e) == 0); }();  // A/B switch
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     if (dstat) { cudaEventCreate(&ev0); cudaEventCreate(&ev1); cudaEventRecord(ev0, st); }
@@ -1012,7 +1071,19 @@ int svd_batched_device(int batch, const SvdJob* jobs_in, double er, int64_t maxd
     int sweeps = 0, stamp = 1;
     const int kMaxSweeps = 60;
     bool any_active = true;
+    const char* trace_file = getenv("QTN_JACOBI_TRACE");
+    int trace_sweep = 3;
+    if (const char* e = getenv("QTN_JACOBI_TRACE_SWEEP")) trace_sweep = atoi(e);
+    unsigned long long* trace_dev = nullptr;
+    const unsigned trace_cap = 1u << 20;
     for (; sweeps < kMaxSweeps && any_active; ++sweeps) {
+        if (trace_file && sweeps == trace_sweep) {  // record this sweep only
+            const unsigned zero = 0;
+            CUDA_TRY(cudaMalloc((void**)&trace_dev, (size_t)trace_cap * 24));
+            CUDA_TRY(cudaMemcpyToSymbol(d_trace_cap, &trace_cap, sizeof(unsigned)));
+            CUDA_TRY(cudaMemcpyToSymbol(d_trace_cnt, &zero, sizeof(unsigned)));
+            CUDA_TRY(cudaMemcpyToSymbol(d_trace_buf, &trace_dev, sizeof(void*)));
+        }
         // flags: 0 = no rotation yet this sweep, 1 = rotated, -1 = converged (its CTAs exit at once)
         int max_rounds = 0;
         for (int g = 0; g < ngroups; ++g) {
@@ -1047,9 +1118,12 @@ int svd_batched_device(int batch, const SvdJob* jobs_in, double er, int64_t maxd
                 else
                     jacobi_gram_kernel<<<dim3((unsigned)(grp.maxpairs * grp.S), nb_), GRAM_THREADS, 0, g_sub[g]>>>(
                         dp + grp.b0, round, drot + grp.b0, grp.S, grp.maxpairs, (double2*)(base + grp.offG));
-                jacobi_eig_kernel<<<dim3((unsigned)grp.maxpairs, nb_), ETHREADS, 0, g_sub[g]>>>(
+                cudaStream_t se = eig_priority ? g_subE[g] : g_sub[g];
+                if (eig_priority) { CUDA_TRY(cudaEventRecord(g_evG[g], g_sub[g])); CUDA_TRY(cudaStreamWaitEvent(se, g_evG[g], 0)); }
+                jacobi_eig_kernel<<<dim3((unsigned)grp.maxpairs, nb_), ETHREADS, 0, se>>>(
                     dp + grp.b0, round, tol, drot + grp.b0, (const double*)dfro + grp.b0, inner, st_ptr, stamp, grp.S, grp.maxpairs,
                     (const double2*)(base + grp.offG), (double2*)(base + grp.offW), (int*)(base + grp.offF), cross, dact + grp.b0);
+                if (eig_priority) { CUDA_TRY(cudaEventRecord(g_evE[g], se)); CUDA_TRY(cudaStreamWaitEvent(g_sub[g], g_evE[g], 0)); }
                 jacobi_update_kernel<<<dim3((unsigned)(grp.maxpairs * grp.SU), nb_), JTHREADS, 0, g_sub[g]>>>(
                     dp + grp.b0, round, drot + grp.b0, grp.SU, grp.maxpairs, (const double2*)(base + grp.offW), (const int*)(base + grp.offF));
                 count_launch(3);
@@ -1062,11 +1136,25 @@ int svd_batched_device(int batch, const SvdJob* jobs_in, double er, int64_t maxd
             CUDA_TRY(cudaMemcpyAsync(hrot + grp.b0, drot + grp.b0, (size_t)(grp.b1 - grp.b0) * 4, cudaMemcpyDeviceToHost, g_sub[g]));
             CUDA_TRY(cudaMemcpyAsync(hact + grp.b0, dact + grp.b0, (size_t)(grp.b1 - grp.b0) * 4, cudaMemcpyDeviceToHost, g_sub[g]));
         }
+        for (int g = 0; g < ngroups; ++g)
+            if (groups[g].active) CUDA_TRY(cudaStreamSynchronize(g_sub[g]));
         any_active = false;
+        if (trace_dev) {  // dump: n records of (kind | smid << 8 | problem << 24, t0, t1) in ns
+            unsigned n = 0;
+            unsigned long long* nul = nullptr;
+            CUDA_TRY(cudaMemcpyFromSymbol(&n, d_trace_cnt, sizeof(unsigned)));
+            CUDA_TRY(cudaMemcpyToSymbol(d_trace_buf, &nul, sizeof(void*)));
+            n = std::min(n, trace_cap);
+            std::vector<unsigned long long> rec((size_t)n * 3);
+            CUDA_TRY(cudaMemcpy(rec.data(), trace_dev, (size_t)n * 24, cudaMemcpyDeviceToHost));
+            if (FILE* f = fopen(trace_file, "wb")) { fwrite(rec.data(), 24, n, f); fclose(f); }
+            cudaFree(trace_dev);
+            trace_dev = nullptr;
+            trace_file = nullptr;
+        }
         for (int g = 0; g < ngroups; ++g) {
             SvdGroup& grp = groups[g];
             if (!grp.active) continue;
-            CUDA_TRY(cudaStreamSynchronize(g_sub[g]));
             bool any = false;
             grp.prev_active = 0;
             for (int b = grp.b0; b < grp.b1; ++b) {

@@ -196,8 +196,15 @@ def test_random_general_networks_plan_parity(q):
         want_shape = tuple(dims[l] for l in sorted((l for lab in il for l in lab if l < 0), reverse=True))
         assert plan.out_dims == want_shape
         lim = max(int(np.log2(max(mx, 2))) - 2, 1)
-        S = q.choose_slices(shapes, il, None, lim, 2)
+        S = q.choose_slices(shapes, il, None, lim, 2, allow_partial=True)
         assert S == oplan.choose_slice_labels(nodes, steps, dims, lim, 2)
+        _, _, mx_after, _ = oplan.tree_cost(nodes, steps, dims, S)
+        nsl = int(np.prod([dims[l] for l in S])) if S else 1
+        if mx_after > 2 ** lim or nsl < 2:   # an unreachable target is reported, not silently ignored
+            with pytest.raises(q.QtnError, match="qtn_choose_slices"):
+                q.choose_slices(shapes, il, None, lim, 2)
+        else:
+            assert S == q.choose_slices(shapes, il, None, lim, 2)
         if S:
             sp = q.ContractionPlan(shapes, il, None, S)
             f2, b2, mx2, _ = oplan.tree_cost(nodes, steps, dims, S)
@@ -310,7 +317,7 @@ def test_order_search_random_general_networks_vs_oracle(q):
         order2, info2 = q.search_order(shapes, il, 24, trial, lim)
         nodes2, steps2 = oplan.contraction_tree(il, order2)
         S = oplan.choose_slice_labels(nodes2, steps2, dims, lim, 1)
-        assert S == q.choose_slices(shapes, il, order2, lim, 1)
+        assert S == q.choose_slices(shapes, il, order2, lim, 1, allow_partial=True)   # open legs may keep a tensor above the target
         f2, _, _, _ = oplan.tree_cost(nodes2, steps2, dims, S)
         nsl = int(np.prod([dims[l] for l in S])) if S else 1
         assert (info2["flops_per_slice"], info2["nslices"]) == (f2, float(nsl))

@@ -283,6 +283,12 @@ int qtn_mps_expect_mpo(const qtn_mps* mps, const void* const* host_mpo_sites, co
  * fallback (n < 128, a failed orthogonality check, or QTN_ORTH=jacobi in the environment).          */
 int qtn_orth_columns(const void* host_a, int64_t m, int64_t n, void* host_q, int32_t* method_out);
 
+/* Diagnostics of the grow-only device workspace pool that serves the transient buffers of the SVD /
+ * MPS / MPO / permutedims entry points (where the reference lets Julia's GC own the temporaries of
+ * `svd` / `permutedims`, src/svd.jl:22-27): out = { cudaMalloc calls so far, cache hits, bytes owned,
+ * blocks currently handed out }.  A steady-state caller sees out[0] stop growing.                    */
+int qtn_pool_stats(int64_t out[4]);
+
 #ifdef __cplusplus
 }
 #endif

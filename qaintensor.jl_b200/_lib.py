@@ -85,6 +85,7 @@ _SIGS = {
     "qtn_mps_apply_mpo": [vp, P(vp), P(i64), P(i64), f64, i64, P(f64)],
     "qtn_mps_expect_mpo": [vp, P(vp), P(i64), P(i64), P(f64)],
     "qtn_orth_columns": [vp, i64, i64, vp, P(i32)],
+    "qtn_pool_stats": [P(i64)],
     "qtn_net_create": [i32, P(vp), P(i32), P(P(i64)), i32, P(i32), i32, P(i32), P(vp)],
     "qtn_net_destroy": [vp],
     "qtn_net_sizes": [vp, P(i32)],
@@ -131,6 +132,13 @@ def dmma_peak_tflops():
     v = f64(0.0)
     check(lib.qtn_bench_dmma_peak(C.byref(v)))
     return float(v.value)
+
+
+def pool_stats():
+    """Workspace pool counters: (cudaMalloc calls, cache hits, bytes owned, blocks handed out)."""
+    out = (i64 * 4)()
+    check(lib.qtn_pool_stats(out))
+    return tuple(int(x) for x in out)
 
 
 def stream_ptr():

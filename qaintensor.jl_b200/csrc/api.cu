@@ -262,9 +262,9 @@ int qtn_permutedims(const void* host_in, int32_t rank, const int64_t* dims, cons
     if (rc) return rc;
     int64_t n = 1;
     for (int i = 0; i < rank; ++i) n *= dims[i];
-    double2 *din = nullptr, *dout = nullptr;
-    CUDA_TRY(cudaMalloc((void**)&din, (size_t)n * 16 + 256));
-    CUDA_TRY(cudaMalloc((void**)&dout, (size_t)n * 16 + 256));
+    PoolBuf bin, bout;   // workspace pool (pool.cu)
+    if (bin.alloc((size_t)n * 16 + 256) || bout.alloc((size_t)n * 16 + 256)) return QTN_ENOMEM;
+    double2 *din = (double2*)bin.p, *dout = (double2*)bout.p;
     cudaMemcpyAsync(din, host_in, (size_t)n * 16, cudaMemcpyHostToDevice, stream());
     rc = permutedims_device(din, rank, dims, perm, dout);
     if (!rc) {
@@ -272,8 +272,6 @@ int qtn_permutedims(const void* host_in, int32_t rank, const int64_t* dims, cons
         cudaError_t e = cudaStreamSynchronize(stream());
         if (e != cudaSuccess) rc = fail(QTN_ECUDA, "qtn_permutedims: %s", cudaGetErrorString(e));
     }
-    cudaFree(din);
-    cudaFree(dout);
     return rc;
 }
 

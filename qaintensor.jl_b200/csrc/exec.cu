@@ -61,7 +61,7 @@ int device_init(int device) {
         return fail(QTN_ENODEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
     CUDA_TRY(cudaSetDevice(device));
     if (g_inited && g_device == device) return QTN_OK;
-    if (g_stream) { cudaStreamDestroy(g_stream); g_stream = nullptr; }
+    if (g_stream) { cudaStreamSynchronize(g_stream); pool_trim(); cudaStreamDestroy(g_stream); g_stream = nullptr; }  // cached workspace belongs to the old device
     CUDA_TRY(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
     g_device = device;
     g_inited = true;
@@ -69,7 +69,7 @@ int device_init(int device) {
 }
 
 int device_shutdown() {
-    if (g_stream) { cudaStreamSynchronize(g_stream); cudaStreamDestroy(g_stream); g_stream = nullptr; }
+    if (g_stream) { cudaStreamSynchronize(g_stream); pool_trim(); cudaStreamDestroy(g_stream); g_stream = nullptr; }
     g_inited = false;
     g_device = -1;
     return QTN_OK;

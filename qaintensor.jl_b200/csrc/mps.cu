@@ -109,11 +109,8 @@ static int scale_copy(const double2* in, int64_t ldi, double2* out, int64_t ldo,
     return cudaGetLastError() == cudaSuccess ? QTN_OK : fail(QTN_ECUDA, "scale_copy launch failed");
 }
 
-struct DevBuf {
-    void* p = nullptr;
-    int alloc(size_t bytes) { return cudaMalloc(&p, std::max<size_t>(bytes, 256)) == cudaSuccess ? QTN_OK : fail(QTN_ENOMEM, "cudaMalloc(%zu) failed", bytes); }
-    ~DevBuf() { if (p) cudaFree(p); }
-};
+// transient device buffers come from the grow-only workspace pool (pool.cu): no cudaMalloc / cudaFree per call
+using DevBuf = PoolBuf;
 
 
 // M (mm x nn, mm >= nn, device) <- an orthonormal basis Q of its columns; keep <- the original M;

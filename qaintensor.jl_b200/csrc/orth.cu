@@ -157,11 +157,7 @@ __global__ void residual_kernel(const double2* __restrict__ A, const double2* __
 
 int grid_for(int64_t work) { return (int)std::max<int64_t>(1, std::min<int64_t>((work + 255) / 256, 148 * 8)); }
 
-struct Scratch {
-    void* p = nullptr;
-    int alloc(size_t bytes) { return cudaMalloc(&p, std::max<size_t>(bytes, 256)) == cudaSuccess ? QTN_OK : fail(QTN_ENOMEM, "cudaMalloc(%zu) failed", bytes); }
-    ~Scratch() { if (p) cudaFree(p); }
-};
+using Scratch = PoolBuf;   // workspace pool (pool.cu)
 
 // G (n x n, ld n) <- upper Cholesky factor in its upper block rows (strictly lower blocks are left stale);
 // dinv / ndinv <- +-R_jj^-1 per diagonal block; work = 2 * 64 * n elements.

@@ -130,6 +130,27 @@ int zgemm_dense(char opa, char opb, int64_t m, int64_t n, int64_t k, const void*
 // when M is too ill-conditioned for it: callers fall back to the Jacobi SVD.  Synchronises the library stream.
 int orth_cholqr2(void* dev_m, const void* dev_keep, void* dev_c, int64_t m, int64_t n, bool* ok);
 
+// ---- pool.cu -------------------------------------------------------------------
+// Grow-only, size-cached device workspace (stream-ordered on the library stream; not re-entrant).
+void* pool_alloc(size_t bytes);   // nullptr (and the error message set) when the device is out of memory
+void pool_free(void* p);          // back to the cache; never cudaFree
+void pool_trim();                 // release every cached block to the driver
+void pool_stats(int64_t out[4]);  // cudaMalloc calls, cache hits, bytes owned, blocks handed out
+// RAII block of the pool.
+struct PoolBuf {
+    void* p = nullptr;
+    PoolBuf() = default;
+    PoolBuf(const PoolBuf&) = delete;
+    PoolBuf& operator=(const PoolBuf&) = delete;
+    PoolBuf(PoolBuf&& o) noexcept : p(o.p) { o.p = nullptr; }
+    int alloc(size_t bytes) {
+        if (p) { pool_free(p); p = nullptr; }
+        p = pool_alloc(bytes < 256 ? 256 : bytes);
+        return p ? QTN_OK : QTN_ENOMEM;
+    }
+    ~PoolBuf() { if (p) pool_free(p); }
+};
+
 // ---- exec.cu -------------------------------------------------------------------
 int device_ready();  // QTN_OK or QTN_ENODEVICE (with message)
 int plan_device_init(Plan* p);

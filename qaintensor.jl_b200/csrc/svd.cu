@@ -777,12 +777,9 @@ __global__ void store_conj_rows_kernel(const double2* __restrict__ D, int64_t le
 static int complete_null_vectors(const SvdJob& job, bool transposed, int dead) {
     cudaStream_t st = stream();
     const int64_t r = std::min(job.m0, job.n0), len = transposed ? job.n0 : job.m0, g = r - dead, d = dead;
-    struct Buf {
-        void* p = nullptr;
-        ~Buf() { if (p) cudaFree(p); }
-    } D, keep, P, C;
-    if (cudaMalloc(&D.p, (size_t)len * d * 16) != cudaSuccess || cudaMalloc(&keep.p, (size_t)len * d * 16) != cudaSuccess ||
-        cudaMalloc(&P.p, (size_t)std::max<int64_t>(g, 1) * d * 16) != cudaSuccess || cudaMalloc(&C.p, (size_t)d * d * 16) != cudaSuccess)
+    PoolBuf D, keep, P, C;
+    if (D.alloc((size_t)len * d * 16) || keep.alloc((size_t)len * d * 16) || P.alloc((size_t)std::max<int64_t>(g, 1) * d * 16) ||
+        C.alloc((size_t)d * d * 16))
         return fail(QTN_ENOMEM, "svd: null-space completion workspace");
     auto grid = [](int64_t n) { return (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, 148 * 8)); };
     fill_random_kernel<<<grid(len * d), 256, 0, st>>>((double2*)D.p, len * d);
@@ -1247,8 +1244,9 @@ int qtn_svd_trunc_batched(int32_t batch, const void* const* host_a, const int64_
         oS[b] = al((size_t)r * 8);
         oV[b] = al((size_t)r * n[b] * 16);
     }
-    char* buf = nullptr;
-    if (cudaMalloc((void**)&buf, total) != cudaSuccess) return fail(QTN_ENOMEM, "qtn_svd_trunc: cudaMalloc(%zu) failed", total);
+    PoolBuf pool_buf;   // workspace pool: no cudaMalloc / cudaFree (and no implicit device sync) per call
+    if (pool_buf.alloc(total)) return QTN_ENOMEM;
+    char* buf = (char*)pool_buf.p;
     std::vector<SvdJob> jobs(batch);
     for (int b = 0; b < batch; ++b) {
         cudaMemcpyAsync(buf + oA[b], host_a[b], (size_t)m[b] * n[b] * 16, cudaMemcpyHostToDevice, st);
@@ -1265,7 +1263,6 @@ int qtn_svd_trunc_batched(int32_t batch, const void* const* host_a, const int64_
         cudaError_t e = cudaStreamSynchronize(st);
         if (e != cudaSuccess) rc = fail(QTN_ECUDA, "qtn_svd_trunc: %s", cudaGetErrorString(e));
     }
-    cudaFree(buf);
     return rc;
 }
 

@@ -266,6 +266,36 @@ int qtn_mps_overlap(const qtn_mps* a, const qtn_mps* b, double out[2]);
  * host_sites[i] receives site i: first (2, b1), middle (b_{i-1}, 2, b_i), last (b_{n-1}, 2), column-major;
  * bonds_out[i] (nsites-1 entries) = b_{i+1}.  Buffers must hold min(2^i, 2^(n-i)) bonds.          */
 int qtn_mps_from_vector(const void* host_psi, int32_t nsites, void* const* host_sites, int64_t* bonds_out);
+/* Replaces the arithmetic of `MPO(m::AbstractMatrix)` (src/mpo.jl:27-90): host_m is the
+ * 2^M x 2^M operator (column-major, M = nqubits >= 2).  reshape to fill(2, 2M), permutedims
+ * (1, M+1, 2, M+2, ...) (src/mpo.jl:45-50), then the left-to-right chain of un-truncated SVDs
+ * (src/mpo.jl:53-66) with the running `diagm(S) * V'` kept on the device.  host_sites[i] receives
+ * tensor i+1: (2, 2, b_1), (b_i, 2, 2, b_{i+1}), ..., (b_{M-1}, 2, 2), column-major, with
+ * b_i = min(4 b_{i-1}, 4^(M-i)); bonds_out[i] (M-1 entries) = b_{i+1}.  The Summation / openidx
+ * bookkeeping (src/mpo.jl:56,67,72-82) stays with the caller.                                      */
+int qtn_mpo_from_matrix(const void* host_m, int32_t nqubits, void* const* host_sites, int64_t* bonds_out);
+/* Replaces the arithmetic of `decompose!(cg)` (src/decompose.jl:6-52), which is the chain of MPO(m)
+ * on the gate matrix; nqubits < 2 fails with the reference's message (src/decompose.jl:7).  The
+ * (t, c, w) wire bookkeeping stays with the caller.                                                  */
+int qtn_decompose(const void* host_m, int32_t nqubits, void* const* host_sites, int64_t* bonds_out);
+/* Replaces `contract_svd_mps(tn; er)` (src/mps.jl:190-201): tcontract = T_1, then
+ * tcontract = contract_svd(tcontract, T_j, (ndims(tcontract), 1); er) for j = 2..n.  The contracted legs
+ * are the last / first ones, so no permute is needed; every T_j is uploaded once and the running
+ * tensor never leaves the device.  numel[j] = length(T_j), first[j] / last[j] = size(T_j, 1) /
+ * size(T_j, ndims).  host_out receives numel_out = prod of the open extents elements, column-major
+ * in the order size(T_1)[1:end-1] ++ size(T_2)[2:end-1] ++ ... ++ size(T_n)[2:end].  er < 0:
+ * QTN_EDOMAIN "Error must be positive" (src/mps.jl:192).  The periodic-boundary check
+ * (src/mps.jl:195) stays with the caller, which sees the Summations.                                 */
+int qtn_contract_svd_fold(int32_t ntensors, const void* const* host_t, const int64_t* numel,
+                          const int64_t* first, const int64_t* last, double er, void* host_out,
+                          int64_t numel_out);
+/* Replaces the arithmetic of `switch!(mps, i)` (src/switch.jl:18-56) in one call: contract_svd of the
+ * two neighbours with er = 0 (:26), exchange of the two physical legs (:28-36), svd (:39),
+ * T1' = U, T2' = diagm(S) * V' (:41-52).  T1 is (l1, 2, b) -- or (2, b) when l1 == 0 (first tensor
+ * of an MPS with two legs); T2 is (b, 2, r2) -- or (b, 2) when r2 == 0.  host_u receives
+ * (l1, 2, bond) [(2, bond)], host_v (bond, 2, r2) [(bond, 2)], *bond_out = min(2 max(l1,1), 2 max(r2,1)). */
+int qtn_mps_switch_adjacent(const void* host_t1, int64_t l1, int64_t b, const void* host_t2, int64_t r2,
+                            void* host_u, void* host_v, int64_t* bond_out);
 /* EXTENSION (SURVEY 8a iii/iv): site-tensor MPO with the layout of src/mpo.jl:66,
  * W_i = (bond_in, out, in, bond_out) = (dl[i], 2, 2, dr[i]), dl[0] = dr[n-1] = 1.
  * qtn_mps_apply_mpo: |psi> <- compress(MPO |psi>): site-wise apply (bonds multiply), a

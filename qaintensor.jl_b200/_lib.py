@@ -82,6 +82,10 @@ _SIGS = {
     "qtn_mps_apply_layer": [vp, i32, P(i32), vp, f64, i64, P(f64)],
     "qtn_mps_overlap": [vp, vp, P(f64)],
     "qtn_mps_from_vector": [vp, i32, P(vp), P(i64)],
+    "qtn_mpo_from_matrix": [vp, i32, P(vp), P(i64)],
+    "qtn_decompose": [vp, i32, P(vp), P(i64)],
+    "qtn_contract_svd_fold": [i32, P(vp), P(i64), P(i64), P(i64), f64, vp, i64],
+    "qtn_mps_switch_adjacent": [vp, i64, i64, vp, i64, vp, vp, P(i64)],
     "qtn_mps_apply_mpo": [vp, P(vp), P(i64), P(i64), f64, i64, P(f64)],
     "qtn_mps_expect_mpo": [vp, P(vp), P(i64), P(i64), P(f64)],
     "qtn_orth_columns": [vp, i64, i64, vp, P(i32)],

@@ -137,6 +137,83 @@ static int orth_columns(void* M, void* keep, void* carry, int64_t mm, int64_t nn
     return zgemm_dense('C', 'N', nn, nn, mm, M, mm, keep, mm, carry, nn, false);
 }
 
+
+// The arithmetic of contract_svd (src/svd.jl:22-35) on device-resident, already permuted operands:
+// a1 (m1 x D) and a2 (D x m2), column-major, both OVERWRITTEN (the Jacobi works in place);
+// out (m1 x m2) <- U1[:, :k1] diag(S1) V1h[:k1, :] U2[:, :k2] diag(S2) V2h[:k2, :] with the tail-norm cutoff `er`.
+// The two SVDs run as one batch.  Work on the library stream; returns after the SVD's host synchronisation,
+// the closing GEMMs may still be in flight.
+int contract_svd_device(void* a1, int64_t m1, void* a2, int64_t m2, int64_t D, double er, void* out) {
+    int rc;
+    const int64_t r1 = std::min(m1, D), r2 = std::min(D, m2);
+    DevBuf u1, u2, v1, v2, s1, s2, x1, x2, y, z;
+    if ((rc = u1.alloc(m1 * r1 * 16)) || (rc = v1.alloc(r1 * D * 16)) || (rc = s1.alloc(r1 * 8)) ||
+        (rc = u2.alloc(D * r2 * 16)) || (rc = v2.alloc(r2 * m2 * 16)) || (rc = s2.alloc(r2 * 8)))
+        return rc;
+    SvdJob jobs[2] = {{(double2*)a1, m1, D, (double2*)u1.p, (double*)s1.p, (double2*)v1.p},
+                      {(double2*)a2, D, m2, (double2*)u2.p, (double*)s2.p, (double2*)v2.p}};
+    int64_t k[2] = {0, 0};
+    if ((rc = svd_batched_device(2, jobs, er, 0, k, nullptr, nullptr))) return rc;
+    if (k[0] == 0 || k[1] == 0)
+        return fail(QTN_EDOMAIN, "contract_svd: the cutoff removes every singular value (the reference's findfirst returns nothing)");
+    const int64_t k1 = k[0], k2 = k[1];
+    if ((rc = x1.alloc(m1 * k1 * 16)) || (rc = x2.alloc(k2 * m2 * 16)) || (rc = y.alloc(k1 * k2 * 16))) return rc;
+    if ((rc = scale_copy((double2*)u1.p, m1, (double2*)x1.p, m1, m1, k1, (double*)s1.p, 1))) return rc;
+    if ((rc = scale_copy((double2*)v2.p, r2, (double2*)x2.p, k2, k2, m2, (double*)s2.p, 0))) return rc;
+    if ((rc = qtn_zgemm_device('N', 'N', k1, k2, D, v1.p, r1, u2.p, D, y.p, k1))) return rc;
+    if (m1 * k1 * k2 + m1 * k2 * m2 <= k1 * k2 * m2 + m1 * k1 * m2) {
+        if ((rc = z.alloc(m1 * k2 * 16))) return rc;
+        if ((rc = qtn_zgemm_device('N', 'N', m1, k2, k1, x1.p, m1, y.p, k1, z.p, m1))) return rc;
+        if ((rc = qtn_zgemm_device('N', 'N', m1, m2, k2, z.p, m1, x2.p, k2, out, m1))) return rc;
+    } else {
+        if ((rc = z.alloc(k1 * m2 * 16))) return rc;
+        if ((rc = qtn_zgemm_device('N', 'N', k1, m2, k2, y.p, k1, x2.p, k2, z.p, k1))) return rc;
+        if ((rc = qtn_zgemm_device('N', 'N', m1, m2, k1, x1.p, m1, z.p, k1, out, m1))) return rc;
+    }
+    return QTN_OK;
+}
+
+// Sequential-SVD chain shared by MPS(psi) (src/mps.jl:55-89, d = 2), MPO(m) (src/mpo.jl:40-75, d = 4) and
+// decompose! (src/decompose.jl:17-48, d = 4): rest (d x cols, device, overwritten) is split site by site,
+//   rest -> reshape(lbond * d, :) -> svd -> site_i = U, rest = diag(S) V',
+// the running `rest` never leaves the device; every site is copied to its host buffer as it is produced.
+// tmp: scratch of the size of rest.  bonds_out[nsites - 1].
+int svd_chain_device(void* rest, void* tmp, int64_t total, int64_t d, int nsites, void* const* host_sites, int64_t* bonds_out) {
+    cudaStream_t st = stream();
+    int rc;
+    int64_t lbond = 1, cols = total;
+    // the factors of the largest step bound every step's: allocate once
+    int64_t maxU = 0, maxV = 0, maxS = 0;
+    {
+        int64_t lb = 1, c = total;
+        for (int i = 1; i < nsites; ++i) {
+            const int64_t m = lb * d;
+            c /= d;
+            const int64_t r = std::min(m, c);
+            maxU = std::max(maxU, m * r); maxV = std::max(maxV, r * c); maxS = std::max(maxS, r);
+            lb = r;
+        }
+    }
+    DevBuf u, s, v;
+    if ((rc = u.alloc(maxU * 16)) || (rc = s.alloc(maxS * 8)) || (rc = v.alloc(maxV * 16))) return rc;
+    for (int i = 1; i < nsites; ++i) {
+        const int64_t m = lbond * d;
+        cols /= d;
+        const int64_t r = std::min(m, cols);
+        SvdJob job{(double2*)rest, m, cols, (double2*)u.p, (double*)s.p, (double2*)v.p};
+        int64_t k = 0;
+        if ((rc = svd_batched_device(1, &job, -1.0, 0, &k, nullptr, nullptr))) return rc;
+        CUDA_TRY(cudaMemcpyAsync(host_sites[i - 1], u.p, (size_t)m * r * 16, cudaMemcpyDeviceToHost, st));
+        if ((rc = scale_copy((double2*)v.p, r, (double2*)tmp, r, r, cols, (double*)s.p, 0))) return rc;
+        std::swap(rest, tmp);
+        bonds_out[i - 1] = r;
+        lbond = r;
+    }
+    CUDA_TRY(cudaMemcpyAsync(host_sites[nsites - 1], rest, (size_t)lbond * d * 16, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return QTN_OK;
+}
+
 }  // namespace qtn
 
 using namespace qtn;
@@ -172,11 +249,9 @@ int qtn_contract_svd(const void* host_t1, int32_t rank1, const int64_t* dims1, i
     for (int i = 0; i < rank2; ++i) n2 *= dims2[i];
     const int64_t D = D1, m1 = n1 / D, m2 = n2 / D;
     if (n1 == 0 || n2 == 0) return fail(QTN_EINVAL, "qtn_contract_svd: empty tensor");
-    const int64_t r1 = std::min(m1, D), r2 = std::min(D, m2);
-    DevBuf t1, t2, p1, p2, u1, u2, v1, v2, s1, s2, x1, x2, y, z, out;
+    DevBuf t1, t2, p1, p2, out;
     if ((rc = t1.alloc(n1 * 16)) || (rc = t2.alloc(n2 * 16)) || (rc = p1.alloc(n1 * 16)) || (rc = p2.alloc(n2 * 16)) ||
-        (rc = u1.alloc(m1 * r1 * 16)) || (rc = v1.alloc(r1 * D * 16)) || (rc = s1.alloc(r1 * 8)) ||
-        (rc = u2.alloc(D * r2 * 16)) || (rc = v2.alloc(r2 * m2 * 16)) || (rc = s2.alloc(r2 * 8)))
+        (rc = out.alloc(m1 * m2 * 16)))
         return rc;
     CUDA_TRY(cudaMemcpyAsync(t1.p, host_t1, n1 * 16, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(t2.p, host_t2, n2 * 16, cudaMemcpyHostToDevice, st));
@@ -188,27 +263,7 @@ int qtn_contract_svd(const void* host_t1, int32_t rank1, const int64_t* dims1, i
     for (int a = 1; a <= rank2; ++a) if (a != i2) perm2.push_back(a);
     if ((rc = permutedims_device(t1.p, rank1, dims1, perm1.data(), p1.p))) return rc;
     if ((rc = permutedims_device(t2.p, rank2, dims2, perm2.data(), p2.p))) return rc;
-    SvdJob jobs[2] = {{(double2*)p1.p, m1, D, (double2*)u1.p, (double*)s1.p, (double2*)v1.p},
-                      {(double2*)p2.p, D, m2, (double2*)u2.p, (double*)s2.p, (double2*)v2.p}};
-    int64_t k[2] = {0, 0};
-    if ((rc = svd_batched_device(2, jobs, er, 0, k, nullptr, nullptr))) return rc;
-    if (k[0] == 0 || k[1] == 0)
-        return fail(QTN_EDOMAIN, "contract_svd: the cutoff removes every singular value (the reference's findfirst returns nothing)");
-    const int64_t k1 = k[0], k2 = k[1];
-    // T = U1[:, :k1] diag(S1) V1h[:k1, :] U2[:, :k2] diag(S2) V2h[:k2, :]   (src/svd.jl:35)
-    if ((rc = x1.alloc(m1 * k1 * 16)) || (rc = x2.alloc(k2 * m2 * 16)) || (rc = y.alloc(k1 * k2 * 16)) || (rc = out.alloc(m1 * m2 * 16))) return rc;
-    if ((rc = scale_copy((double2*)u1.p, m1, (double2*)x1.p, m1, m1, k1, (double*)s1.p, 1))) return rc;
-    if ((rc = scale_copy((double2*)v2.p, r2, (double2*)x2.p, k2, k2, m2, (double*)s2.p, 0))) return rc;
-    if ((rc = qtn_zgemm_device('N', 'N', k1, k2, D, v1.p, r1, u2.p, D, y.p, k1))) return rc;
-    if (m1 * k1 * k2 + m1 * k2 * m2 <= k1 * k2 * m2 + m1 * k1 * m2) {
-        if ((rc = z.alloc(m1 * k2 * 16))) return rc;
-        if ((rc = qtn_zgemm_device('N', 'N', m1, k2, k1, x1.p, m1, y.p, k1, z.p, m1))) return rc;
-        if ((rc = qtn_zgemm_device('N', 'N', m1, m2, k2, z.p, m1, x2.p, k2, out.p, m1))) return rc;
-    } else {
-        if ((rc = z.alloc(k1 * m2 * 16))) return rc;
-        if ((rc = qtn_zgemm_device('N', 'N', k1, m2, k2, y.p, k1, x2.p, k2, z.p, k1))) return rc;
-        if ((rc = qtn_zgemm_device('N', 'N', m1, m2, k1, x1.p, m1, z.p, k1, out.p, m1))) return rc;
-    }
+    if ((rc = contract_svd_device(p1.p, m1, p2.p, m2, D, er, out.p))) return rc;
     CUDA_TRY(cudaMemcpyAsync(host_out, out.p, m1 * m2 * 16, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     return QTN_OK;
@@ -385,31 +440,123 @@ int qtn_mps_from_vector(const void* host_psi, int32_t nsites, void* const* host_
     if (nsites < 2 || nsites > 30) return fail(QTN_EINVAL, "qtn_mps_from_vector: nsites must be in 2..30");
     int rc = device_ready();
     if (rc) return rc;
-    cudaStream_t st = stream();
     const int64_t n = (int64_t)1 << nsites;
-    DevBuf rest, U, S, Vh, tmp;
+    DevBuf rest, tmp;
     if ((rc = rest.alloc(n * 16)) || (rc = tmp.alloc(n * 16))) return rc;
-    CUDA_TRY(cudaMemcpyAsync(rest.p, host_psi, n * 16, cudaMemcpyHostToDevice, st));
-    int64_t lbond = 1, cols = n;
-    for (int bit = 1; bit < nsites; ++bit) {
-        // rest is (lbond*2) x (cols/2): U -> site `bit`, diag(S) V' -> next rest      (src/mps.jl:62-76)
-        const int64_t m = lbond * 2;
-        cols /= 2;
-        const int64_t r = std::min(m, cols);
-        DevBuf u, s, v;
-        if ((rc = u.alloc(m * r * 16)) || (rc = s.alloc(r * 8)) || (rc = v.alloc(r * cols * 16))) return rc;
-        SvdJob job{(double2*)rest.p, m, cols, (double2*)u.p, (double*)s.p, (double2*)v.p};
-        int64_t k = 0;
-        if ((rc = svd_batched_device(1, &job, -1.0, 0, &k, nullptr, nullptr))) return rc;
-        CUDA_TRY(cudaMemcpyAsync(host_sites[bit - 1], u.p, (size_t)m * r * 16, cudaMemcpyDeviceToHost, st));
-        if ((rc = scale_copy((double2*)v.p, r, (double2*)tmp.p, r, r, cols, (double*)s.p, 0))) return rc;
-        CUDA_TRY(cudaMemcpyAsync(rest.p, tmp.p, (size_t)r * cols * 16, cudaMemcpyDeviceToDevice, st));
-        CUDA_TRY(cudaStreamSynchronize(st));  // u/s/v are freed at the end of the iteration
-        bonds_out[bit - 1] = r;
-        lbond = r;
+    CUDA_TRY(cudaMemcpyAsync(rest.p, host_psi, n * 16, cudaMemcpyHostToDevice, stream()));
+    return svd_chain_device(rest.p, tmp.p, n, 2, nsites, host_sites, bonds_out);
+}
+
+// ---------------- MPO(m) / decompose! on the device (src/mpo.jl:27-90, src/decompose.jl:6-52) ---------------
+// host_m: 2^M x 2^M operator, column-major.  reshape(m, fill(2, 2M)) -> permutedims (1, M+1, 2, M+2, ...) ->
+// the sequential-SVD chain with physical dimension 4.  host_sites[i] receives site i+1: (bond_i, 2, 2, bond_{i+1})
+// with bond_0 = 1 (the first site is (2, 2, bond_1), the last (bond_{M-1}, 2, 2)); the svd is not truncated, so
+// bond_i = min(4 bond_{i-1}, 4^(M-i)) is known to the caller, who sizes the buffers.  bonds_out[M - 1].
+int qtn_mpo_from_matrix(const void* host_m, int32_t nqubits, void* const* host_sites, int64_t* bonds_out) {
+    if (!host_m || !host_sites || !bonds_out) return fail(QTN_EINVAL, "qtn_mpo_from_matrix: null argument");
+    if (nqubits < 2) return fail(QTN_EDOMAIN, "Need at least two qubits to split (a one-qubit operator is its own MPO)");
+    if (nqubits > 15) return fail(QTN_EINVAL, "qtn_mpo_from_matrix: nqubits must be in 2..15");
+    int rc = device_ready();
+    if (rc) return rc;
+    const int M = nqubits;
+    const int64_t n = (int64_t)1 << (2 * M);
+    DevBuf in, rest;
+    if ((rc = in.alloc(n * 16)) || (rc = rest.alloc(n * 16))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(in.p, host_m, n * 16, cudaMemcpyHostToDevice, stream()));
+    std::vector<int64_t> dims(2 * M, 2);
+    std::vector<int32_t> perm;
+    for (int i = 1; i <= M; ++i) { perm.push_back(i); perm.push_back(i + M); }   // src/mpo.jl:45-50, src/decompose.jl:19-23
+    if ((rc = permutedims_device(in.p, 2 * M, dims.data(), perm.data(), rest.p))) return rc;
+    return svd_chain_device(rest.p, in.p, n, 4, M, host_sites, bonds_out);
+}
+
+// decompose!(cg) (src/decompose.jl:6-52) performs exactly the chain of MPO(m) on the gate's matrix; the wire /
+// bond bookkeeping (t, c, w) stays with the caller.
+int qtn_decompose(const void* host_m, int32_t nqubits, void* const* host_sites, int64_t* bonds_out) {
+    if (nqubits < 2) return fail(QTN_EDOMAIN, "Only decompose Circuit Gates that apply to multiple wires");
+    return qtn_mpo_from_matrix(host_m, nqubits, host_sites, bonds_out);
+}
+
+// contract_svd_mps (src/mps.jl:190-201): tcontract = T_1; tcontract = contract_svd(tcontract, T_j, (ndims, 1); er)
+// for j = 2..n.  The contracted legs are already the last / the first, so the fold needs no permute: every T_j is
+// uploaded once, the running tensor stays on the device, one download at the end.
+// numel[j] = elements of T_j, first[j] / last[j] = its first / last extent.  host_out: numel_out elements
+// (= prod of all open extents; the caller knows the shape: dims(T_1)[:-1] ++ dims(T_2)[2:-1] ++ ... ++ dims(T_n)[2:]).
+int qtn_contract_svd_fold(int32_t ntensors, const void* const* host_t, const int64_t* numel, const int64_t* first,
+                          const int64_t* last, double er, void* host_out, int64_t numel_out) {
+    if (!(er >= 0)) return fail(QTN_EDOMAIN, "Error must be positive");
+    if (ntensors < 1 || !host_t || !numel || !first || !last || !host_out) return fail(QTN_EINVAL, "qtn_contract_svd_fold: null argument");
+    int64_t tot = 0;     // elements of the running tensor
+    int64_t peak = 0;
+    for (int j = 0; j < ntensors; ++j) {
+        if (!host_t[j] || numel[j] < 1 || first[j] < 1 || last[j] < 1 || numel[j] % first[j] || numel[j] % last[j])
+            return fail(QTN_EINVAL, "qtn_contract_svd_fold: tensor %d has an inconsistent shape", j + 1);
+        if (j == 0) tot = numel[0];
+        else {
+            if (first[j] != last[j - 1]) return fail(QTN_EDOMAIN, "Dimensions of contraction legs do not match");
+            tot = tot / last[j - 1] * (numel[j] / first[j]);
+        }
+        peak = std::max(peak, tot);
+        if (peak > ((int64_t)1 << 33)) return fail(QTN_EINVAL, "qtn_contract_svd_fold: the running tensor exceeds 2^33 elements");
     }
-    CUDA_TRY(cudaMemcpyAsync(host_sites[nsites - 1], rest.p, (size_t)lbond * 2 * 16, cudaMemcpyDeviceToHost, st));
+    if (tot != numel_out) return fail(QTN_EINVAL, "qtn_contract_svd_fold: output has %lld elements, expected %lld", (long long)numel_out, (long long)tot);
+    int rc = device_ready();
+    if (rc) return rc;
+    cudaStream_t st = stream();
+    DevBuf acc, nxt, tj;
+    int64_t maxt = 0;
+    for (int j = 1; j < ntensors; ++j) maxt = std::max(maxt, numel[j]);
+    if ((rc = acc.alloc(peak * 16)) || (rc = nxt.alloc(peak * 16)) || (rc = tj.alloc(std::max<int64_t>(maxt, 1) * 16))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(acc.p, host_t[0], (size_t)numel[0] * 16, cudaMemcpyHostToDevice, st));
+    void *a = acc.p, *b = nxt.p;
+    int64_t cur = numel[0];   // elements of the running tensor
+    for (int j = 1; j < ntensors; ++j) {
+        // running tensor as (m1 x D), T_j as (D x m2)
+        const int64_t D = first[j], m1 = cur / D, m2 = numel[j] / D;
+        CUDA_TRY(cudaMemcpyAsync(tj.p, host_t[j], (size_t)numel[j] * 16, cudaMemcpyHostToDevice, st));
+        if ((rc = contract_svd_device(a, m1, tj.p, m2, D, er, b))) return rc;
+        std::swap(a, b);
+        cur = m1 * m2;
+    }
+    CUDA_TRY(cudaMemcpyAsync(host_out, a, (size_t)numel_out * 16, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
+    return QTN_OK;
+}
+
+// switch!(mps, i) (src/switch.jl:18-56) in one call: T = contract_svd(T1, T2, (ndims(T1), 1)) with er = 0, the two
+// physical legs exchanged by permutedims, svd, T1' = U, T2' = diag(S) V'.  T1: (l1, 2, b) or (2, b) when l1 == 0;
+// T2: (b, 2, r2) or (b, 2) when r2 == 0 (the boundary tensors of an MPS with two legs).
+// host_u receives (l1, 2, bond) [(2, bond)], host_v (bond, 2, r2) [(bond, 2)]; *bond_out = min(2 l1, 2 r2).
+int qtn_mps_switch_adjacent(const void* host_t1, int64_t l1, int64_t b, const void* host_t2, int64_t r2, void* host_u,
+                            void* host_v, int64_t* bond_out) {
+    if (!host_t1 || !host_t2 || !host_u || !host_v || !bond_out) return fail(QTN_EINVAL, "qtn_mps_switch_adjacent: null argument");
+    if (l1 < 0 || r2 < 0 || b < 1) return fail(QTN_EINVAL, "qtn_mps_switch_adjacent: bad extents");
+    int rc = device_ready();
+    if (rc) return rc;
+    cudaStream_t st = stream();
+    const int64_t L = std::max<int64_t>(l1, 1), R = std::max<int64_t>(r2, 1);
+    const int64_t m1 = L * 2, m2 = 2 * R;
+    DevBuf t1, t2, T, P, u, s, v, sv;
+    const int64_t r = std::min(m1, m2);
+    if ((rc = t1.alloc(m1 * b * 16)) || (rc = t2.alloc(b * m2 * 16)) || (rc = T.alloc(m1 * m2 * 16)) || (rc = P.alloc(m1 * m2 * 16)) ||
+        (rc = u.alloc(m1 * r * 16)) || (rc = s.alloc(r * 8)) || (rc = v.alloc(r * m2 * 16)) || (rc = sv.alloc(r * m2 * 16)))
+        return rc;
+    CUDA_TRY(cudaMemcpyAsync(t1.p, host_t1, (size_t)m1 * b * 16, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(t2.p, host_t2, (size_t)b * m2 * 16, cudaMemcpyHostToDevice, st));
+    if ((rc = contract_svd_device(t1.p, m1, t2.p, m2, b, 0.0, T.p))) return rc;   // src/switch.jl:26
+    // T is (L, 2, 2, R): exchange the physical legs (src/switch.jl:28-36: [2,1,3] / [1,3,2] / [1,3,2,4] are this
+    // permutation with the absent boundary legs dropped)
+    const int64_t dims4[4] = {L, 2, 2, R};
+    const int32_t perm4[4] = {1, 3, 2, 4};
+    if ((rc = permutedims_device(T.p, 4, dims4, perm4, P.p))) return rc;
+    SvdJob job{(double2*)P.p, m1, m2, (double2*)u.p, (double*)s.p, (double2*)v.p};
+    int64_t k = 0;
+    if ((rc = svd_batched_device(1, &job, -1.0, 0, &k, nullptr, nullptr))) return rc;   // src/switch.jl:39
+    if ((rc = scale_copy((double2*)v.p, r, (double2*)sv.p, r, r, m2, (double*)s.p, 0))) return rc;   // src/switch.jl:41
+    CUDA_TRY(cudaMemcpyAsync(host_u, u.p, (size_t)m1 * r * 16, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(host_v, sv.p, (size_t)r * m2 * 16, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    *bond_out = r;
     return QTN_OK;
 }
 

@@ -3,7 +3,7 @@ host; the operator-splitting SVDs run on the GPU."""
 import numpy as np
 
 from .gates import CircuitGate
-from .svd import svd
+from .svd import operator_chain
 from .tensor_network import GeneralTensorNetwork, Summation, Tensor, TensorNetwork, shift_pair, shift_summation
 
 
@@ -24,16 +24,11 @@ class MPO(TensorNetwork):
             self.tensors.append(Tensor(np.reshape(m, (2, 2), order="F")))
             self.openidx = [(1, 2), (1, 1)]
             return
-        rest = np.transpose(np.reshape(m, (2,) * (2 * M), order="F"), [a for i in range(M) for a in (i, i + M)])
-        bond = 1
-        for i in range(1, M):
-            U, S, Vh = svd(np.reshape(rest, (bond * 4, -1), order="F"))
-            nb = len(S)
-            self.tensors.append(Tensor(np.reshape(U, (2, 2, nb) if i == 1 else (bond, 2, 2, nb), order="F")))
-            self.contractions.append(Summation([(i, 3 if i == 1 else 4), (i + 1, 1)]))
-            rest = S[:, None] * Vh
-            bond = nb
-        self.tensors.append(Tensor(np.reshape(rest, (bond, 2, 2), order="F")))
+        # src/mpo.jl:40-70: the whole reshape / permutedims / sequential-SVD chain is one device call
+        for i, site in enumerate(operator_chain(np.reshape(m, (2 ** M, 2 ** M), order="F"), M), 1):
+            self.tensors.append(Tensor(site))
+            if i < M:
+                self.contractions.append(Summation([(i, 3 if i == 1 else 4), (i + 1, 1)]))
         self.openidx = [(M - i + 1, 2) for i in range(1, M)] + [(1, 1)] + [(M - i + 1, 3) for i in range(1, M)] + [(1, 2)]
 
     def isapprox(self, other):

@@ -130,10 +130,24 @@ def contract_svd_mps(tn, er=0.0):  # src/mps.jl:190-201
     periodic = (Summation([(n, 3), (1, 1)]), Summation([(1, 1), (n, 3)]))
     if any(s in periodic for s in tn.contractions):
         raise ValueError("Function doesn't support periodic boundary conditions for now")
-    acc = tn.tensors[0]
+    # the fold tcontract = contract_svd(tcontract, T_j, (ndims, 1); er) in one library call (qtn_contract_svd_fold):
+    # the running tensor stays on the device
+    import ctypes as C
+    from . import _lib
+    _lib.require_device()
+    arrs = [_lib.as_c128(t.data) for t in tn.tensors]
+    for a, b in zip(arrs[:-1], arrs[1:]):
+        if a.shape[-1] != b.shape[0]:
+            raise ValueError("Dimensions of contraction legs do not match")
+    shape = arrs[0].shape[:-1] if n > 1 else arrs[0].shape
     for j in range(1, n):
-        acc = contract_svd(acc, tn.tensors[j], (acc.ndims(), 1), er=er)
-    return acc.data
+        shape = shape + (arrs[j].shape[1:-1] if j < n - 1 else arrs[j].shape[1:])
+    out = np.zeros(shape, dtype=np.complex128, order="F")
+    ptrs = (C.c_void_p * n)(*[a.ctypes.data for a in arrs])
+    _lib.check(_lib.lib.qtn_contract_svd_fold(n, ptrs, _lib.arr_i64([a.size for a in arrs]), _lib.arr_i64([a.shape[0] for a in arrs]),
+                                              _lib.arr_i64([a.shape[-1] for a in arrs]), float(er),
+                                              out.ctypes.data_as(C.c_void_p), out.size))
+    return out
 
 
 # ---- src/switch.jl ---------------------------------------------------------------------
@@ -143,24 +157,24 @@ def _switch_adjacent(mps, i):  # switch!(mps, i) src/switch.jl:18-56
         raise IndexError("BoundsError: attempt to access %d-element MPS at index %d" % (len(mps.tensors), i + 1))
     T1, T2 = mps.tensors[i - 1], mps.tensors[i]
     d1, d2 = T1.size(), T2.size()
-    T = contract_svd(T1, T2, (T1.ndims(), 1)).data
-    if T1.ndims() == 2:
-        T = np.reshape(permutedims(T, [2, 1, 3]), (2, 2 * d2[-1]), order="F")
-    elif T2.ndims() == 2:
-        T = np.reshape(permutedims(T, [1, 3, 2]), (2 * d1[0], 2), order="F")
-    else:
-        T = np.reshape(permutedims(T, [1, 3, 2, 4]), (2 * d1[0], 2 * d2[-1]), order="F")
-    U, S, Vh = svd(T)
-    bond = len(S)
-    V = S[:, None] * Vh
-    if T1.ndims() == 2:
-        U = np.reshape(U, (2, bond), order="F")
-        V = np.reshape(V, (bond, 2, d2[-1]), order="F")
-    elif T2.ndims() == 2:
-        U = np.reshape(U, (d1[0], 2, bond), order="F")
-    else:
-        U = np.reshape(U, (d1[0], 2, bond), order="F")
-        V = np.reshape(V, (bond, 2, d2[-1]), order="F")
+    if T1.ndims() == 2 and T2.ndims() == 2:   # the reference's permutedims(T, [2,1,3]) of a 2-leg T throws as well
+        raise ValueError("switch! of a two-tensor MPS: the contracted pair has no third leg to permute")
+    # src/switch.jl:26-52 in one library call (contract_svd, leg exchange, svd, diagm(S) * V' on the device)
+    import ctypes as C
+    from . import _lib
+    _lib.require_device()
+    a, b = _lib.as_c128(T1.data), _lib.as_c128(T2.data)
+    if d1[-1] != d2[0]:
+        raise ValueError("Dimensions of contraction legs do not match")
+    l1 = d1[0] if T1.ndims() == 3 else 0
+    r2 = d2[-1] if T2.ndims() == 3 else 0
+    bond = min(2 * max(l1, 1), 2 * max(r2, 1))
+    U = np.zeros((2, bond) if l1 == 0 else (l1, 2, bond), dtype=np.complex128, order="F")
+    V = np.zeros((bond, 2) if r2 == 0 else (bond, 2, r2), dtype=np.complex128, order="F")
+    kb = C.c_int64(0)
+    _lib.check(_lib.lib.qtn_mps_switch_adjacent(a.ctypes.data_as(C.c_void_p), l1, d1[-1], b.ctypes.data_as(C.c_void_p), r2,
+                                                U.ctypes.data_as(C.c_void_p), V.ctypes.data_as(C.c_void_p), C.byref(kb)))
+    assert kb.value == bond
     mps.tensors[i - 1] = Tensor(U)
     mps.tensors[i] = Tensor(V)
 

@@ -66,3 +66,24 @@ def orth_columns(A):
     method = C.c_int32(0)
     check(lib.qtn_orth_columns(A.ctypes.data_as(C.c_void_p), m, n, Q.ctypes.data_as(C.c_void_p), C.byref(method)))
     return Q, int(method.value)
+
+
+def operator_chain(m, M, entry="qtn_mpo_from_matrix"):
+    """The SVD chain of ``MPO(m)`` (src/mpo.jl:40-75) / ``decompose!`` (src/decompose.jl:17-48) in ONE library
+    call: reshape, permutedims and the left-to-right un-truncated SVDs run on the device, the running
+    ``diagm(S) * V'`` never returns to the host.  Returns the M site arrays: (2, 2, b1), (b_i, 2, 2, b_{i+1}), ...,
+    (b_{M-1}, 2, 2)."""
+    _lib.require_device()
+    m = as_c128(m)
+    caps, b = [], 1
+    for i in range(1, M):
+        b = min(4 * b, 4 ** (M - i))
+        caps.append(b)
+    shapes = [(2, 2, caps[0])] + [(caps[i - 1], 2, 2, caps[i]) for i in range(1, M - 1)] + [(caps[-1], 2, 2)]
+    bufs = [np.zeros(int(np.prod(sh)), dtype=np.complex128) for sh in shapes]
+    ptrs = (C.c_void_p * M)(*[x.ctypes.data for x in bufs])
+    bonds = (C.c_int64 * max(M - 1, 1))()
+    check(getattr(lib, entry)(m.ctypes.data_as(C.c_void_p), M, ptrs, bonds))
+    bd = [int(bonds[i]) for i in range(M - 1)]
+    assert bd == caps, (bd, caps)
+    return [np.reshape(x, sh, order="F") for x, sh in zip(bufs, shapes)]

@@ -4,7 +4,7 @@ symbolic network growth on the host; the small gate-splitting SVDs go through
 import numpy as np
 
 from .gates import CircuitGate
-from .svd import svd
+from .svd import operator_chain
 from .tensor_network import Summation, Tensor
 
 
@@ -13,23 +13,11 @@ def decompose(cg):
     M = len(cg.iwire)
     if not M > 1:
         raise ValueError("Only decompose Circuit Gates that apply to multiple wires")
-    m = np.reshape(np.array(cg.matrix), (2,) * (2 * M), order="F")
-    m = np.transpose(m, [a for i in range(M) for a in (i, i + M)])
-    tensors, wires, bonds = [], [], [0, 3]
-    bond = 1
-    for i in range(1, M):
-        m = np.reshape(m, (bond * 4, -1), order="F")
-        U, S, Vh = svd(m)
-        nb = len(S)
-        m = S[:, None] * Vh
-        shape = (2, 2, nb) if i == 1 else (bond, 2, 2, nb)
-        tensors.append(Tensor(np.reshape(U, shape, order="F")))
-        wires.append(cg.iwire[i - 1])
-        if i > 1:
-            bonds.append(4)
-        bond = nb
-    tensors.append(Tensor(np.reshape(m, (bond, 2, 2), order="F")))
-    wires.append(cg.iwire[M - 1])
+    # src/decompose.jl:17-48: one device call for the reshape / permutedims / sequential-SVD chain
+    sites = operator_chain(np.array(cg.matrix), M, entry="qtn_decompose")
+    tensors = [Tensor(t) for t in sites]
+    wires = [cg.iwire[i] for i in range(M)]
+    bonds = [0, 3] + [4] * (M - 2)
     return tensors, bonds, wires
 
 

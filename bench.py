@@ -57,6 +57,7 @@ def parse():
                     help="reference = optimize_contraction_order! (treewidth heuristic, the default and the named config); "
                          "search = EXTENSION qtn_order_search (randomised greedy + annealing), reported separately")
     ap.add_argument("--search-trials", type=int, default=512)
+    ap.add_argument("--no-parity-check", action="store_true", help="skip the cfg2 sliced parity check before timing (ncu launch windows)")
     ap.add_argument("--dump-steps", default=None, help="write the per-step (M, N, K, ms) table of one slice to this file")
     ap.add_argument("--precision", default="c128", choices=["c128", "c64"], help="c64 = optional ComplexF32 mode (cfg2/cfg3)")
     args = ap.parse_args()
@@ -612,7 +613,7 @@ def main():
             plan.close()
             S, plan = make_plan(level)
     sps = args.slices_per_step if plan.nslices > 1 else 1
-    parity = multi_rank_parity_check(q, rank, world) if args.workload == "cfg3" and args.open_wires == 0 else None
+    parity = multi_rank_parity_check(q, rank, world) if args.workload == "cfg3" and args.open_wires == 0 and not args.no_parity_check else None
     plan.upload(arrays)
     out = torch.zeros(2 * plan.out_numel, dtype=torch.float64 if args.precision == "c128" else torch.float32, device="cuda")
 
@@ -677,12 +678,19 @@ def main():
                                                                 16.0 * (M_ * K_ + K_ * N_ + M_ * N_) / max(t_, 1e-6) / 1e6))
         # dominant kernel = the tile variant (flags bits 4-7) with the largest summed time over the slice-dependent
         # pairwise steps; its longest launch carries the roofline
+        # (kernel class: the persistent streaming kernel takes the tall-skinny steps, csrc/exec.cu:launch_gemm)
+        def kclass(st):
+            M_, N_, K_, fl_ = st
+            if (args.precision == "c128" and os.environ.get("QTN_STREAM", "1") != "0" and (fl_ >> 4) & 15 != 2 and (fl_ >> 8) == 1
+                    and M_ >= 16384 and K_ <= 32 and N_ <= 128):
+                return "stream"
+            return (fl_ >> 4) & 15
         by_variant = {}
         for i, st in enumerate(steps):
             if not (st[3] & 1) and (st[3] >> 1) & 7 == 0:
-                by_variant[(st[3] >> 4) & 15] = by_variant.get((st[3] >> 4) & 15, 0.0) + step_ms[i]
+                by_variant[kclass(st)] = by_variant.get(kclass(st), 0.0) + step_ms[i]
         top_variant = max(by_variant, key=by_variant.get) if by_variant else 0
-        cand = [i for i, st in enumerate(steps) if not (st[3] & 1) and (st[3] >> 1) & 7 == 0 and (st[3] >> 4) & 15 == top_variant]
+        cand = [i for i, st in enumerate(steps) if not (st[3] & 1) and (st[3] >> 1) & 7 == 0 and kclass(st) == top_variant]
         dom = max(cand or range(len(steps)), key=lambda i: step_ms[i])
         M, N, K, _ = steps[dom]
         dom_flops = 8.0 * M * N * K
@@ -712,11 +720,18 @@ def main():
         else:
             roof = {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
                     "traffic": traffic, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if pk else "fallback 6650 GB/s"}
-        roof.update({"kernel": "zgemm_gather_kernel", "kernel_tile_variant": top_variant,
+        roof.update({"kernel": "zgemm_stream_kernel" if top_variant == "stream" else "zgemm_gather_kernel", "kernel_tile_variant": top_variant,
                      "kernel_share_of_slice": by_variant.get(top_variant, 0.0) / max(sum(by_variant.values()), 1e-9),
                      "step_MNK": [M, N, K], "step_ms": step_ms[dom],
                      "step_share_of_slice": step_ms[dom] / max(sum(ms_ for ms_, st in zip(step_ms, steps) if not (st[3] & 1)), 1e-9),
                      "whole_slice_tflops": plan.flops_per_slice / (ms * 1e-3 / (args.steps * sps)) / 1e12})
+        # the class's longest HBM-bound launch as well (the searched order is mostly such launches)
+        hb = [i for i in cand if 8.0 * steps[i][0] * steps[i][1] * steps[i][2] / (16.0 * (steps[i][0] * steps[i][2] + steps[i][2] * steps[i][1] + steps[i][0] * steps[i][1])) < ridge]
+        if hb and tensor_bound:
+            j = max(hb, key=lambda i: step_ms[i])
+            bj = 16.0 * (steps[j][0] * steps[j][2] + steps[j][2] * steps[j][1] + steps[j][0] * steps[j][1])
+            roof["hbm_bound_launch"] = {"step_MNK": list(steps[j][:3]), "step_ms": step_ms[j], "achieved": bj / (step_ms[j] * 1e-3) / 1e9,
+                                        "peak": hbm_peak, "unit": "GB/s", "frac": bj / (step_ms[j] * 1e-3) / 1e9 / hbm_peak}
         cpu = None
         if not args.no_cpu_baseline and world == 1:
             if args.workload == "cfg3" and args.open_wires == 0:

@@ -2,6 +2,7 @@
 #include <cuda_profiler_api.h>
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -111,8 +112,61 @@ static int launch_gemm_t(GemmArgs& g, int split_k, cudaStream_t st) {
     return QTN_OK;
 }
 
+// Persistent streaming kernel for the HBM-bound tall-skinny steps (kernels.cuh: zgemm_stream_kernel).
+static const int64_t kNumSMs = 148;
+template <int MI, int NI, int KP, int MAXW>
+static int launch_stream_t(GemmArgs& g, cudaStream_t st) {
+    static bool attr_done = false;
+    static int max_smem = 0;
+    auto kern = zgemm_stream_kernel<MI, NI, KP, MAXW>;
+    if (!attr_done) {
+        int dev = 0;
+        CUDA_TRY(cudaGetDevice(&dev));
+        CUDA_TRY(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        attr_done = true;
+    }
+    const int64_t ncb = (g.N + NI * 8 - 1) / (NI * 8);
+    const size_t fixed = (size_t)KP * (ncb * NI * 8 + 2) * 16 + (size_t)KP * 8;
+    const size_t stage = (size_t)KP * (MI * 8 + 2) * 16;
+    static int s_env = -1, w_env = -1;
+    if (s_env < 0) { const char* e = getenv("QTN_STREAM_STAGES"); s_env = e ? atoi(e) : 0; }
+    if (w_env < 0) { const char* e = getenv("QTN_STREAM_WARPS"); w_env = e ? atoi(e) : 0; }
+    int S = s_env >= 2 && s_env <= 4 ? s_env : 3;
+    int NW = w_env >= 1 && w_env <= MAXW ? w_env : MAXW;
+    // shared memory: warps (latency hiding of the issue stream) before ring depth
+    while (S > 2 && fixed + (size_t)NW * S * stage > (size_t)max_smem) --S;
+    while (NW > 1 && fixed + (size_t)NW * S * stage > (size_t)max_smem) --NW;
+    const size_t smem = fixed + (size_t)NW * S * stage;
+    if (smem > (size_t)max_smem) return fail(QTN_EINVAL, "stream GEMM: tile does not fit shared memory");
+    const int64_t ntiles = (g.M + MI * 8 - 1) / (MI * 8);
+    const unsigned grid = (unsigned)std::min<int64_t>(kNumSMs, (ntiles + NW - 1) / NW);
+    kern<<<grid, NW * 32, smem, st>>>(g, S);
+    CUDA_TRY(cudaGetLastError());
+    count_launch(1);
+    return QTN_OK;
+}
+
+template <int MI, int NI, int MAXW>
+static int launch_stream_k(GemmArgs& g, cudaStream_t st) {
+    if (g.K <= 8) return launch_stream_t<MI, NI, 8, MAXW>(g, st);
+    if (g.K <= 16) return launch_stream_t<MI, NI, 16, MAXW>(g, st);
+    return launch_stream_t<MI, NI, 32, MAXW>(g, st);
+}
+
 int launch_gemm(GemmArgs& g, int variant, int split_k, cudaStream_t st) {
     if (g.M <= 0 || g.N <= 0) return QTN_OK;
+    {
+        // QTN_STREAM=0 restores the tile kernels for A/B runs
+        static int stream_on = -1;
+        if (stream_on < 0) { const char* e = getenv("QTN_STREAM"); stream_on = e ? atoi(e) : 1; }
+        if (stream_on && variant != 2 && split_k == 1 && g.M >= 16384 && g.K <= 32 && g.N <= 128) {
+            // HBM-bound shapes: small tiles, 16 warps; tensor-bound shapes (N > 16): 8 warps with wide column blocks
+            if (g.N <= 8) return g.K <= 8 ? launch_stream_t<4, 1, 8, 16>(g, st) : launch_stream_k<2, 1, 16>(g, st);
+            if (g.N <= 16) return launch_stream_k<2, 2, 16>(g, st);
+            return launch_stream_k<2, 4, 8>(g, st);   // column blocks of 32
+        }
+    }
     if (variant == 2) {
         int blocks = (int)std::min<int64_t>(2 * 148, (g.K + 255) / 256);
         if (blocks < 1) blocks = 1;

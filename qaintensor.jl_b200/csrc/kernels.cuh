@@ -298,6 +298,190 @@ zgemm_gather_kernel(const __grid_constant__ GemmArgs g) {
         }
 }
 
+// K2s: persistent streaming kernel for the tall-skinny steps with a short contraction (N <= 128, K <= 32: "a small
+// operator applied to a huge tensor", what a searched / state-vector-like order consists of; HBM-bound for N <= 16).
+//   * One CTA per SM, NW independent warps; a warp owns (8 MI)-row tiles  tile = wglobal + i * (gridDim.x * NW)  and
+//     its own ring of S stages in shared memory (a stage = one whole A tile, 8 MI rows x KP): loads of the tiles
+//     i+1..i+S-1 are in flight (cp.async, 16 B, gathered through the row / k offset tables like the tile kernel) while
+//     tile i runs on the FP64 tensor pipe and its C rows are stored straight from the accumulators.  No CTA barrier in
+//     the loop (cp.async.wait_group + __syncwarp only): the warps drift apart and load / DMMA / store phases overlap.
+//   * B (K x N, at most 64 KB) is staged once per CTA; A is read exactly once, C written exactly once.  N is covered in
+//     column blocks of 8 NI (the A fragments are re-read from shared memory per block).
+//   * The loop is instruction-lean on purpose (the first version ran 1078 warp instructions per 16 KB tile and was
+//     issue-latency-bound at 8 warps per SM): KP is a template parameter so the stage loads unroll with the k offsets
+//     pre-scaled to bytes, the dense / full-tile epilogue has no predicates, and small tiles leave room for 16 warps.
+//   conj_a is folded into the staging of B and the epilogue: conj(A) B = conj(A conj(B)).
+template <int MI, int NI, int KP, int MAXW>
+__global__ void __launch_bounds__(MAXW * 32, 1)
+zgemm_stream_kernel(const __grid_constant__ GemmArgs g, int S) {
+    constexpr int TR = MI * 8, PA = TR + 2, CB = NI * 8, NK4 = KP / 4;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int NW = blockDim.x >> 5;
+    const int K = (int)g.K, N = (int)g.N;
+    const int ncb = (N + CB - 1) / CB, PB = ncb * CB + 2;
+    double2* sB = reinterpret_cast<double2*>(smem_raw);                 // [KP][PB]
+    i64* sKa = reinterpret_cast<i64*>(sB + KP * PB);                     // [KP]  k offsets of A in bytes (-1: padding)
+    double2* sA = reinterpret_cast<double2*>(sKa + KP);                  // [NW][S][KP][PA]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, gq = lane >> 2, t = lane & 3;
+    const char* A = reinterpret_cast<const char*>(static_cast<const double2*>(g.A) + (g.a_soff ? *g.a_soff : 0));
+    const double2* B = static_cast<const double2*>(g.B) + (g.b_soff ? *g.b_soff : 0);
+    double2* const Cbase = static_cast<double2*>(g.C);
+    const bool flip_b = (g.conj_b != 0) != (g.conj_a != 0);
+    for (int e = tid; e < KP * ncb * CB; e += blockDim.x) {
+        // consecutive threads walk B's contiguous direction
+        const int k = g.b_kmajor ? e % KP : e / (ncb * CB), n = g.b_kmajor ? e / KP : e % (ncb * CB);
+        double2 v = make_double2(0.0, 0.0);
+        if (k < K && n < N) {
+            v = __ldg(B + tab_off(g.b_k, k) + tab_off(g.b_col, n));
+            if (flip_b) v.y = -v.y;
+        }
+        sB[k * PB + n] = v;
+    }
+    for (int k = tid; k < KP; k += blockDim.x) sKa[k] = k < K ? tab_off(g.a_k, k) * 16 : -1;
+    __syncthreads();
+    const i64 M = g.M;
+    const i64 ntiles = (M + TR - 1) / TR;
+    const i64 wstride = (i64)gridDim.x * NW;
+    const i64 w0 = (i64)blockIdx.x * NW + warp;
+    const unsigned ring_s = (unsigned)__cvta_generic_to_shared(sA + (size_t)warp * S * KP * PA);
+    constexpr unsigned STAGE_BYTES = KP * PA * 16;
+    // stage loads: lane -> (row, k) with rows fastest, or k fastest when the operand's contiguous direction is k
+    constexpr int KPI = 32 / TR;   // k rows per load instruction (rows fastest)
+    const int lrow = lane % TR, lksub = lane / TR;
+    const unsigned ldst = (unsigned)((lksub * PA + lrow) * 16);
+    constexpr int KSH = KP >= 32 ? 5 : (KP >= 16 ? 4 : 3);
+    const int kk = lane & (KP - 1), rsub = lane >> KSH;   // (k fastest; KP = 32 -> one row per instruction)
+    constexpr int RPER = 32 >> KSH;
+    auto issue = [&](i64 tile, int stage) {
+        const unsigned dst = ring_s + (unsigned)stage * STAGE_BYTES;
+        const i64 r = tile * TR + lrow;
+        const i64 ro = (tile < ntiles && r < M) ? tab_off(g.a_row, r) * 16 : -1;   // lanes >= TR duplicate (TR = 16)
+        if (!g.a_kmajor) {
+            const char* src = A + ro;
+#pragma unroll
+            for (int k = 0; k < KP; k += KPI) {
+                const i64 ka = sKa[k + lksub];
+                const int sz = (ro | ka) >= 0 ? 16 : 0;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst + ldst + (unsigned)(k * PA * 16)), "l"(sz ? src + ka : A), "r"(sz));
+            }
+        } else {
+            const i64 ka = sKa[kk];
+#pragma unroll
+            for (int r0 = 0; r0 < TR; r0 += RPER) {
+                const i64 rr = __shfl_sync(0xffffffffu, ro, r0 + rsub);
+                const int sz = (rr | ka) >= 0 ? 16 : 0;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst + (unsigned)((kk * PA + r0 + rsub) * 16)), "l"(sz ? A + rr + ka : A), "r"(sz));
+            }
+        }
+    };
+    for (int s = 0; s < S - 1; ++s) {
+        issue(w0 + (i64)s * wstride, s);
+        cp_async_commit();
+    }
+    const bool fast_cols = g.c_dense && g.mode == 0 && N == ncb * CB;
+    int stage = 0;
+    for (i64 tile = w0; tile < ntiles; tile += wstride) {
+        // S - 2 groups may stay pending: the oldest (this tile's) has landed for this thread; __syncwarp makes the
+        // other lanes' copies visible and guarantees every lane is done reading the stage overwritten next
+        if (S >= 4) cp_async_wait<2>(); else if (S == 3) cp_async_wait<1>(); else cp_async_wait<0>();
+        __syncwarp();
+        {
+            int ns = stage + S - 1;
+            if (ns >= S) ns -= S;
+            issue(tile + (i64)(S - 1) * wstride, ns);
+            cp_async_commit();
+        }
+        const double2* a_s = sA + ((size_t)warp * S + stage) * (KP * PA) + gq;
+        const i64 rbase = tile * TR + gq;
+        const bool fast = fast_cols && (tile + 1) * TR <= M;
+        for (int cb = 0; cb < ncb; ++cb) {
+            const double2* b_s = sB + cb * CB + gq;
+            double cr[MI][NI][2], ci[MI][NI][2];
+#pragma unroll
+            for (int i = 0; i < MI; ++i)
+#pragma unroll
+                for (int j = 0; j < NI; ++j) cr[i][j][0] = cr[i][j][1] = ci[i][j][0] = ci[i][j][1] = 0.0;
+            double2 af0[MI], bf0[NI], af1[MI], bf1[NI];   // two statically named fragment buffers (no local-memory indexing)
+            auto load_frags = [&](double2 (&af)[MI], double2 (&bf)[NI], int k4) {
+                const int kr = k4 * 4 + t;
+#pragma unroll
+                for (int i = 0; i < MI; ++i) af[i] = a_s[kr * PA + i * 8];
+#pragma unroll
+                for (int j = 0; j < NI; ++j) bf[j] = b_s[kr * PB + j * 8];
+            };
+            auto mma = [&](const double2 (&af)[MI], const double2 (&bf)[NI]) {
+#pragma unroll
+                for (int i = 0; i < MI; ++i)
+#pragma unroll
+                    for (int j = 0; j < NI; ++j) dmma884(cr[i][j][0], cr[i][j][1], af[i].x, bf[j].x);
+#pragma unroll
+                for (int i = 0; i < MI; ++i)
+#pragma unroll
+                    for (int j = 0; j < NI; ++j) dmma884(ci[i][j][0], ci[i][j][1], af[i].x, bf[j].y);
+                double nby[NI];
+#pragma unroll
+                for (int j = 0; j < NI; ++j) nby[j] = -bf[j].y;
+#pragma unroll
+                for (int i = 0; i < MI; ++i)
+#pragma unroll
+                    for (int j = 0; j < NI; ++j) dmma884(cr[i][j][0], cr[i][j][1], af[i].y, nby[j]);
+#pragma unroll
+                for (int i = 0; i < MI; ++i)
+#pragma unroll
+                    for (int j = 0; j < NI; ++j) dmma884(ci[i][j][0], ci[i][j][1], af[i].y, bf[j].x);
+            };
+            load_frags(af0, bf0, 0);
+#pragma unroll
+            for (int k4 = 0; k4 < NK4; k4 += 2) {   // the LDS.128 of the next k4 fly under the DMMAs of the current one
+                load_frags(af1, bf1, k4 + 1);
+                mma(af0, bf0);
+                if (k4 + 2 < NK4) load_frags(af0, bf0, k4 + 2);
+                mma(af1, bf1);
+            }
+            if (g.conj_a) {
+#pragma unroll
+                for (int i = 0; i < MI; ++i)
+#pragma unroll
+                    for (int j = 0; j < NI; ++j) { ci[i][j][0] = -ci[i][j][0]; ci[i][j][1] = -ci[i][j][1]; }
+            }
+            // epilogue: straight from the accumulators (8 consecutive rows per column = one full 128-byte line per store)
+            if (fast) {
+                double2* cp = Cbase + rbase + (i64)(cb * CB + 2 * t) * M;
+#pragma unroll
+                for (int j = 0; j < NI; ++j) {
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+#pragma unroll
+                        for (int i = 0; i < MI; ++i) cp[i * 8] = make_double2(cr[i][j][q], ci[i][j][q]);
+                        cp += M;
+                    }
+                    cp += 6 * M;
+                }
+            } else {
+                i64 crow[MI];
+#pragma unroll
+                for (int i = 0; i < MI; ++i) {
+                    const i64 r = rbase + i * 8;
+                    crow[i] = (r < M) ? (g.c_dense ? r : tab_off(g.c_row, r)) : -1;
+                }
+#pragma unroll
+                for (int j = 0; j < NI; ++j)
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        const int c = cb * CB + j * 8 + 2 * t + q;
+                        if (c >= N) continue;
+                        const i64 co = g.c_dense ? (i64)c * M : tab_off(g.c_col, c);
+#pragma unroll
+                        for (int i = 0; i < MI; ++i)
+                            if (crow[i] >= 0) store_c(Cbase + crow[i] + co, cr[i][j][q], ci[i][j][q], g.mode);
+                    }
+            }
+        }
+        if (++stage == S) stage = 0;
+    }
+    cp_async_wait<0>();
+}
+
 // K3: ComplexF32 mode on the FP32 pipes (optional precision; tensor cores would need TF32, whose
 // 10-bit mantissa misses the 1e-4 amplitude bar).  Same gather/scatter addressing as the FP64
 // kernel; 64x64 CTA tile, 256 threads, 4x4 complex outputs per thread, BK = 16, 2-stage cp.async (8 B).

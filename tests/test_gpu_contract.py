@@ -333,3 +333,14 @@ def test_sliced_self_contraction_is_the_trace(gpu):  # a sliced labe
         assert plan.nslices == int(np.prod([{1: 3, 2: 2, 3: 4}[l] for l in S]))
         assert abs(complex(plan.execute(ts)) - want) < TOL * abs(want)
         assert abs(complex(oplan.contract_sliced(ts, il, None, S)) - want) < 1e-12 * abs(want)
+
+
+def test_stream_kernel_parity(gpu):  # persistent streaming kernel of the tall-skinny steps (M >= 16384, N <= 32, K <= 32)
+    import os
+    import sys
+    from conftest import ROOT
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import stream_check
+    before = gpu.launch_count()
+    assert stream_check.run() < 1e-12
+    assert gpu.launch_count() > before

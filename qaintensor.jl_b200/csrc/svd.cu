@@ -58,6 +58,7 @@ struct SvdProblem {
     int* last_mod;  // [nblocks]  launch stamp of the last rotation that touched a column block
     int* last_ok;   // [nblocks * nblocks] launch stamp at which a block pair was last found converged
     double2* D;     // [nblocks][16 x 16] Gram of each column block (row-major), kept current by the eigensolve kernel
+    int* ver;       // [nblocks]  dataflow kernel: number of rounds of the current sweep this block has been through
 };
 
 __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
@@ -596,6 +597,514 @@ jacobi_update_kernel(const SvdProblem* __restrict__ probs, int round, const int*
     trace_end(3, trace_t0);
 }
 
+// =============================================================================================================
+// Dataflow sweep kernel (batches with enough block pairs per round to fill the machine).
+//
+// The three-kernel round above synchronises ALL block pairs of a sub-batch at every phase boundary, 63 times per
+// sweep: the latency-bound eigensolves leave the tensor pipe idle, every kernel has a partial last wave, and the
+// phases of different sub-batches only overlap by luck.  But a block pair (I, J) of round r+1 depends on exactly two
+// pairs of round r -- the ones that held I and J.  This kernel expresses that directly:
+//   * the (matrix, round, pair) visits of a sweep form a task list sorted by round; persistent CTAs (4 per SM) draw
+//     tasks from an atomic counter;
+//   * a task waits until both its blocks carry version == round (ld.acquire spin by one thread), runs
+//     Gram -> eigensolve -> update for its pair entirely inside the CTA (G and W never leave shared memory; no partial
+//     Grams, no W buffer, no apply flags in global memory), then publishes version = round + 1 for both blocks
+//     (__threadfence + st.release);
+//   * CTAs of one SM are in different phases at any time, so the tensor pipe sees the Gram / update DMMAs of some
+//     tasks while others sit in their eigensolve -- without any barrier wider than a CTA.
+// Tasks are drawn in list order, so a task's producers (previous round) were drawn earlier by CTAs that are running:
+// no deadlock, no co-residency requirement.  Everything a task reads that another CTA may have written (A, V, D,
+// stamps, versions) is read with ld.cg / ld.acquire (L1 is not coherent across SMs).
+// FULL = true: full 32 x 32 Gram (round 0 of a sweep, polishing sweeps); false: cross block only + cached diagonal blocks.
+// =============================================================================================================
+__device__ __forceinline__ int ld_acquire(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(int* p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ int ldcg_int(const int* p) { return __ldcg(p); }
+
+constexpr int FLOW_THREADS = 128;
+constexpr int FSP = JP + 4;  // pitch of the re + im plane of W (conflict-free LDS.64 for the B fragments)
+
+// Shared-memory arena of one CTA (dynamic): [ W | Wsum ][ G ][ extra ].  During the Gram main loop the WHOLE arena is a
+// ring of per-thread cp.async slots; the update phase uses [ G | extra ] the same way (G is dead after the eigensolve).
+constexpr int FLOW_W_ELEMS = JP * JPITCH + JP * FSP / 2;   // W (double2) + Wsum (double) in double2 units
+constexpr int FLOW_G_ELEMS = JP * JPITCH;
+template <int MINB> struct FlowCfg {
+    static constexpr int EXTRA = MINB >= 4 ? 0 : (MINB == 3 ? 1536 : 4096);                    // extra ring space, double2 units
+    static constexpr int ARENA = FLOW_W_ELEMS + FLOW_G_ELEMS + EXTRA;
+    static constexpr int DG = ARENA / (4 * FLOW_THREADS);                                      // Gram ring depth (4-row chunks)
+    static constexpr int DU = (FLOW_G_ELEMS + EXTRA) / (8 * FLOW_THREADS);                     // update ring depth (8-row groups)
+    static constexpr size_t SMEM = (size_t)ARENA * sizeof(double2);
+};
+
+template <bool FULL, int MINB>
+__global__ void __launch_bounds__(FLOW_THREADS, MINB)
+jacobi_flow_kernel(const SvdProblem* __restrict__ probs, const uint2* __restrict__ tasks, int ntasks, int* __restrict__ counter,
+                   double tol, int* __restrict__ rotated, const double* __restrict__ fro2, int inner_sweeps, int* __restrict__ stat,
+                   int stamp_base, int* __restrict__ nactive) {
+    typedef FlowCfg<MINB> Cfg;
+    extern __shared__ __align__(16) unsigned char flow_smem[];
+    double2* const arena = reinterpret_cast<double2*>(flow_smem);
+    double2* const W = arena;
+    double* const Wsum = reinterpret_cast<double*>(arena + JP * JPITCH);
+    double2* const G = arena + FLOW_W_ELEMS;
+    __shared__ double2 rot[JB], rph[JB];
+    __shared__ int s_pq[2 * JB];
+    __shared__ int s_any, s_sweep_any, s_rot, s_task;
+    __shared__ int s_cols[JP];
+    static_assert(sizeof(double2) * FLOW_W_ELEMS >= sizeof(double) * 2 * 40 * 32, "reduction scratch");
+    static_assert(Cfg::DG >= 2 && Cfg::DU >= 1, "ring depths");
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+    for (;;) {
+        __syncthreads();  // every thread is done with the previous task's shared state (incl. s_task)
+        if (tid == 0) s_task = atomicAdd(counter, 1);
+        __syncthreads();
+        const int task = s_task;
+        if (task >= ntasks) return;
+        const uint2 tk = __ldg(tasks + task);
+        const int b = (int)tk.x, round = (int)(tk.y >> 16), pair = (int)(tk.y & 0xffffu);
+        const SvdProblem* __restrict__ prp = probs + b;   // fields are re-read where needed (registers are the scarce resource here)
+        const int nb = prp->nblocks, pn = prp->n;
+        int bi, bj;  // every block is in exactly one pair per round (nb is even): versions advance even for padding / idle pairs
+        if (pair == 0) { bi = nb - 1; bj = round; }
+        else { bi = (round + pair) % (nb - 1); bj = (round - pair + (nb - 1)) % (nb - 1); }
+        if (bi > bj) { const int tt = bi; bi = bj; bj = tt; }
+        if (tid == 0) {
+            unsigned ns = 32;
+            while (ld_acquire(prp->ver + bi) < round || ld_acquire(prp->ver + bj) < round) { __nanosleep(ns); if (ns < 1024) ns *= 2; }
+        }
+        __syncthreads();
+        const bool live = __ldcg(rotated + b) >= 0 && bi * JB < pn;
+        const bool idle = live && max(ldcg_int(prp->last_mod + bi), ldcg_int(prp->last_mod + bj)) < ldcg_int(prp->last_ok + bi * nb + bj);
+        if (!live || idle) {
+            if (tid == 0) {
+                if (live && stat) atomicAdd(&stat[0], 1);
+                st_release(prp->ver + bi, round + 1);
+                st_release(prp->ver + bj, round + 1);
+            }
+            continue;
+        }
+        const int m = prp->m;
+        const int stamp = stamp_base + round;
+        // ------------------------------------------------ Gram of the panel -> G ------------------------------
+        unsigned long long trace_t0 = d_trace_buf ? trace_now() : 0ull;
+        {
+            const double2* cp[4];
+            bool cv[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int col = panel_col(i * 8 + g, bi, bj, pn);
+                cv[i] = col >= 0;
+                cp[i] = prp->A + (size_t)(col >= 0 ? col : 0) * m;
+            }
+            const int ngroups = (m + 15) >> 4;
+            constexpr int NWP = FLOW_THREADS / 32;
+            double* red = reinterpret_cast<double*>(W);  // [2][NB4][32]
+            if constexpr (FULL) {
+                double gr[10][2], gi[10][2];
+#pragma unroll
+                for (int k = 0; k < 10; ++k) gr[k][0] = gr[k][1] = gi[k][0] = gi[k][1] = 0.0;
+                for (int grp = warp; grp < ngroups; grp += NWP) {
+                    double2 f[4][4];
+                    const int r = grp * 16 + t;
+#pragma unroll
+                    for (int s = 0; s < 4; ++s)
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const int row = r + 4 * s;
+                            f[s][i] = (cv[i] && row < m) ? __ldcg(cp[i] + row) : make_double2(0.0, 0.0);
+                        }
+#pragma unroll
+                    for (int s = 0; s < 4; ++s) {
+                        int k = 0;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+#pragma unroll
+                            for (int j = i; j < 4; ++j, ++k) {
+                                dmma(gr[k][0], gr[k][1], f[s][i].x, f[s][j].x);
+                                dmma(gr[k][0], gr[k][1], f[s][i].y, f[s][j].y);
+                                dmma(gi[k][0], gi[k][1], f[s][i].x, f[s][j].y);
+                                dmma(gi[k][0], gi[k][1], -f[s][i].y, f[s][j].x);
+                            }
+                    }
+                }
+#pragma unroll
+                for (int stage = 0; stage < 2; ++stage) {  // fixed-order tree over the 4 warps (deterministic)
+                    const int half = stage == 0 ? 2 : 1;
+                    if (warp >= half && warp < 2 * half) {
+#pragma unroll
+                        for (int k = 0; k < 10; ++k) {
+                            red[((warp - half) * 40 + 4 * k + 0) * 32 + lane] = gr[k][0];
+                            red[((warp - half) * 40 + 4 * k + 1) * 32 + lane] = gr[k][1];
+                            red[((warp - half) * 40 + 4 * k + 2) * 32 + lane] = gi[k][0];
+                            red[((warp - half) * 40 + 4 * k + 3) * 32 + lane] = gi[k][1];
+                        }
+                    }
+                    __syncthreads();
+                    if (warp < half) {
+#pragma unroll
+                        for (int k = 0; k < 10; ++k) {
+                            gr[k][0] += red[(warp * 40 + 4 * k + 0) * 32 + lane];
+                            gr[k][1] += red[(warp * 40 + 4 * k + 1) * 32 + lane];
+                            gi[k][0] += red[(warp * 40 + 4 * k + 2) * 32 + lane];
+                            gi[k][1] += red[(warp * 40 + 4 * k + 3) * 32 + lane];
+                        }
+                    }
+                    __syncthreads();
+                }
+                if (warp == 0) {  // upper block triangle: block k = (i, j >= i), lane (g, t) owns row g, columns 2t, 2t+1
+                    int k = 0;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int j = i; j < 4; ++j, ++k) {
+                            G[(i * 8 + g) * JPITCH + j * 8 + 2 * t] = make_double2(gr[k][0], gi[k][0]);
+                            G[(i * 8 + g) * JPITCH + j * 8 + 2 * t + 1] = make_double2(gr[k][1], gi[k][1]);
+                        }
+                }
+            } else {
+                double m1[4][2], m2[4][2], m3[4][2];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) m1[k][0] = m1[k][1] = m2[k][0] = m2[k][1] = m3[k][0] = m3[k][1] = 0.0;
+                // 4-row chunks (one k-step of the DMMA) through a DG-deep ring of per-thread cp.async slots spanning the whole
+                // arena: a thread reads back exactly the four fragments it fetched itself, so the ring needs no barrier.
+                // (ncu: with one chunk of register prefetch this phase was 21 % of the kernel's time, all long-scoreboard,
+                // for 6 us of tensor-pipe work: only ~2 CTAs of an SM are in a tensor phase at any time.)
+                const int nch = (m + 3) >> 2;
+                const int nk = nch > warp ? (nch - warp + NWP - 1) / NWP : 0;   // this warp's chunks: warp + NWP * k
+                double2* const gslot = arena + tid;                             // [slot][i][FLOW_THREADS]
+                auto fetch = [&](int kq) {
+                    if (kq < nk) {
+                        const int row = (warp + NWP * kq) * 4 + t;
+                        double2* dst = gslot + (size_t)(kq % Cfg::DG) * (4 * FLOW_THREADS);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const bool ok = cv[i] && row < m;
+                            cp_async16(dst + i * FLOW_THREADS, ok ? (const void*)(cp[i] + row) : (const void*)cp[i], ok);
+                        }
+                    }
+                    cp_async_commit();
+                };
+                for (int kq = 0; kq < Cfg::DG - 1; ++kq) fetch(kq);
+                for (int kq = 0; kq < nk; ++kq) {
+                    fetch(kq + Cfg::DG - 1);          // overwrites the slot read in iteration kq - 1
+                    cp_async_wait<Cfg::DG - 1>();     // group kq has landed
+                    const double2* src = gslot + (size_t)(kq % Cfg::DG) * (4 * FLOW_THREADS);
+                    double2 f[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) f[i] = src[i * FLOW_THREADS];
+                    asm volatile("" ::: "memory");
+                    const double sa0 = f[0].x + f[0].y, sa1 = f[1].x + f[1].y;
+                    const double db2 = f[2].x - f[2].y, db3 = f[3].x - f[3].y;
+#pragma unroll
+                    for (int i = 0; i < 2; ++i)
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) {
+                            const int kk = 2 * i + j;
+                            dmma(m1[kk][0], m1[kk][1], f[i].x, f[2 + j].x);
+                            dmma(m2[kk][0], m2[kk][1], f[i].y, f[2 + j].y);
+                            dmma(m3[kk][0], m3[kk][1], i ? sa1 : sa0, j ? db3 : db2);
+                        }
+                }
+                cp_async_wait<0>();
+                __syncthreads();   // every warp is done with its ring slots: the reduction scratch and G overlay them
+                double gr[4][2], gi[4][2];
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) { gr[k][q] = m1[k][q] + m2[k][q]; gi[k][q] = m1[k][q] - m2[k][q] - m3[k][q]; }
+#pragma unroll
+                for (int stage = 0; stage < 2; ++stage) {
+                    const int half = stage == 0 ? 2 : 1;
+                    if (warp >= half && warp < 2 * half) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            red[((warp - half) * 16 + 4 * k + 0) * 32 + lane] = gr[k][0];
+                            red[((warp - half) * 16 + 4 * k + 1) * 32 + lane] = gr[k][1];
+                            red[((warp - half) * 16 + 4 * k + 2) * 32 + lane] = gi[k][0];
+                            red[((warp - half) * 16 + 4 * k + 3) * 32 + lane] = gi[k][1];
+                        }
+                    }
+                    __syncthreads();
+                    if (warp < half) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            gr[k][0] += red[(warp * 16 + 4 * k + 0) * 32 + lane];
+                            gr[k][1] += red[(warp * 16 + 4 * k + 1) * 32 + lane];
+                            gi[k][0] += red[(warp * 16 + 4 * k + 2) * 32 + lane];
+                            gi[k][1] += red[(warp * 16 + 4 * k + 3) * 32 + lane];
+                        }
+                    }
+                    __syncthreads();
+                }
+                if (warp == 0) {  // block k = 2 i + j' is block (i, 2 + j') of the panel Gram
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int i = k >> 1, j = 2 + (k & 1);
+                        G[(i * 8 + g) * JPITCH + j * 8 + 2 * t] = make_double2(gr[k][0], gi[k][0]);
+                        G[(i * 8 + g) * JPITCH + j * 8 + 2 * t + 1] = make_double2(gr[k][1], gi[k][1]);
+                    }
+                }
+            }
+        }
+        trace_end(FULL ? 0 : 1, trace_t0);
+        trace_t0 = d_trace_buf ? trace_now() : 0ull;
+        // ------------------------------------------------ eigensolve of G, rotations accumulated in W ---------
+        const double dthr = 1e-30 * fro2[b];
+        double2* DI = prp->D + (size_t)bi * (JB * JB);
+        double2* DJ = prp->D + (size_t)bj * (JB * JB);
+        if (tid < JP) s_cols[tid] = panel_col(tid, bi, bj, pn);
+        if (tid == 0) { s_any = 0; s_rot = 0; }
+        if (!FULL)  // diagonal blocks from the cache
+            for (int e = tid; e < 2 * JB * JB; e += FLOW_THREADS) {
+                const int h = e >> 8, r = (e >> 4) & 15, c = e & 15;
+                G[(h * JB + r) * JPITCH + h * JB + c] = __ldcg((h ? DJ : DI) + (e & 255));
+            }
+        __syncthreads();  // (also: the reduction scratch in W / Wsum is dead from here on)
+        for (int e = tid; e < JP * JP; e += FLOW_THREADS) {  // mirror the strictly-lower block triangle, W = I
+            const int r = e / JP, c = e % JP;
+            if (!FULL ? (r >= JB && c < JB) : ((r >> 3) > (c >> 3))) { const double2 v = G[c * JPITCH + r]; G[r * JPITCH + c] = make_double2(v.x, -v.y); }
+            W[r * JPITCH + c] = make_double2(r == c ? 1.0 : 0.0, 0.0);
+        }
+        __syncthreads();
+        for (int sweep = 0; sweep < inner_sweeps; ++sweep) {
+            if (tid == 0) s_sweep_any = 0;
+            __syncthreads();
+            for (int step = 0; step < JP - 1; ++step) {
+                if (tid < JB) {
+                    int p, q;
+                    if (tid == 0) { p = JP - 1; q = step; }
+                    else { p = (step + tid) % (JP - 1); q = (step - tid + (JP - 1)) % (JP - 1); }
+                    if (p > q) { int tt = p; p = q; q = tt; }
+                    const double alpha = G[p * JPITCH + p].x, beta = G[q * JPITCH + q].x;
+                    const double2 gg = G[p * JPITCH + q];
+                    const double ag2 = gg.x * gg.x + gg.y * gg.y;
+                    double c = 1.0, s = 0.0;
+                    double2 ph = make_double2(1.0, 0.0);
+                    const bool real_cols = s_cols[p] >= 0 && s_cols[q] >= 0;  // never touch padding slots
+                    if (!real_cols) {
+                        // identity
+                    } else if (ag2 > tol * tol * fabs(alpha) * fabs(beta) && ag2 > 0.0 && alpha > dthr && beta > dthr) {
+                        const double a = 0.5 * (beta - alpha);
+                        const double rg = rsqrt(ag2), rr = rsqrt(a * a + ag2);
+                        ph = make_double2(gg.x * rg, gg.y * rg);
+                        const double c2 = 0.5 + 0.5 * fabs(a) * rr;
+                        const double rc = rsqrt(c2);
+                        c = c2 * rc;
+                        s = 0.5 * (ag2 * rg) * rr * rc;
+                        if (a < 0) s = -s;
+                        const double t_ag = (s * rc) * (ag2 * rg);
+                        if (alpha - t_ag < beta + t_ag) { const double cc = s, ss = -c; c = cc; s = ss; }
+                        s_sweep_any = 1;
+                        s_rot = 1;
+                    } else if (alpha < beta && beta > dthr) {
+                        c = 0.0; s = -1.0;
+                        s_sweep_any = 1;
+                    }
+                    rot[tid] = make_double2(c, s);
+                    rph[tid] = make_double2(s * ph.x, s * ph.y);   // S = s e^{i phi}: the phase is folded into the sine once
+                    s_pq[2 * tid] = p;
+                    s_pq[2 * tid + 1] = q;
+                }
+                __syncthreads();
+                {
+                    // u' = c u - S v  and  v' = conj(S) u + c v  (rows; columns take conj(S) / S): 6 FP64 instructions per
+                    // complex output instead of 8 -- the eigensolve's DFMAs queue behind the DMMAs of the other CTAs
+                    auto lin_m = [](double c, double2 u, double2 S, double2 v) {   // c u - S v
+                        return make_double2(fma(-S.x, v.x, fma(S.y, v.y, c * u.x)), fma(-S.x, v.y, fma(-S.y, v.x, c * u.y)));
+                    };
+                    auto lin_mc = [](double c, double2 u, double2 S, double2 v) {  // c u - conj(S) v
+                        return make_double2(fma(-S.x, v.x, fma(-S.y, v.y, c * u.x)), fma(-S.x, v.y, fma(S.y, v.x, c * u.y)));
+                    };
+                    auto lin_p = [](double c, double2 u, double2 S, double2 v) {   // c u + S v
+                        return make_double2(fma(S.x, v.x, fma(-S.y, v.y, c * u.x)), fma(S.x, v.y, fma(S.y, v.x, c * u.y)));
+                    };
+                    auto lin_pc = [](double c, double2 u, double2 S, double2 v) {  // c u + conj(S) v
+                        return make_double2(fma(S.x, v.x, fma(S.y, v.y, c * u.x)), fma(S.x, v.y, fma(-S.y, v.x, c * u.y)));
+                    };
+                    const int k2 = tid & 15;
+                    const double c2 = rot[k2].x;
+                    const double2 S2 = rph[k2];
+                    const bool id2 = (c2 == 1.0 && rot[k2].y == 0.0);
+                    const int p2 = s_pq[2 * k2], q2 = s_pq[2 * k2 + 1];
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh) {
+                        const int k1 = (tid >> 4) + 8 * hh;
+                        const double c1 = rot[k1].x;
+                        const bool id1 = (c1 == 1.0 && rot[k1].y == 0.0);
+                        if (id1 && id2) continue;
+                        const double2 S1 = rph[k1];
+                        const int p1 = s_pq[2 * k1], q1 = s_pq[2 * k1 + 1];
+                        double2 g00 = G[p1 * JPITCH + p2], g01 = G[p1 * JPITCH + q2];
+                        double2 g10 = G[q1 * JPITCH + p2], g11 = G[q1 * JPITCH + q2];
+                        if (!id1) {  // rows: y_p' = c y_p - S y_q ; y_q' = conj(S) y_p + c y_q
+                            const double2 n00 = lin_m(c1, g00, S1, g10), n01 = lin_m(c1, g01, S1, g11);
+                            const double2 n10 = lin_pc(c1, g10, S1, g00), n11 = lin_pc(c1, g11, S1, g01);
+                            g00 = n00; g01 = n01; g10 = n10; g11 = n11;
+                        }
+                        if (!id2) {  // columns: x_p' = c x_p - conj(S) x_q ; x_q' = S x_p + c x_q
+                            const double2 n00 = lin_mc(c2, g00, S2, g01), n10 = lin_mc(c2, g10, S2, g11);
+                            const double2 n01 = lin_p(c2, g01, S2, g00), n11 = lin_p(c2, g11, S2, g10);
+                            g00 = n00; g01 = n01; g10 = n10; g11 = n11;
+                        }
+                        G[p1 * JPITCH + p2] = g00; G[p1 * JPITCH + q2] = g01;
+                        G[q1 * JPITCH + p2] = g10; G[q1 * JPITCH + q2] = g11;
+                    }
+                    if (!id2) {  // W <- W J (columns), rows (tid >> 4) + 8 h for pair k2
+#pragma unroll
+                        for (int h = 0; h < 4; ++h) {
+                            const int r = (tid >> 4) + 8 * h;
+                            const double2 xp = W[r * JPITCH + p2], xq = W[r * JPITCH + q2];
+                            W[r * JPITCH + p2] = lin_mc(c2, xp, S2, xq);
+                            W[r * JPITCH + q2] = lin_p(c2, xq, S2, xp);
+                        }
+                    }
+                }
+                __syncthreads();
+            }
+            const int any_now = s_sweep_any;
+            if (any_now && tid == 0) s_any = 1;
+            __syncthreads();
+            if (!any_now) break;
+        }
+        const int any = s_any;
+        if (tid == 0) {
+            if (stat) atomicAdd(&stat[any ? 1 : 0], 1);
+            if (any) { prp->last_mod[bi] = stamp; prp->last_mod[bj] = stamp; }
+            else prp->last_ok[bi * nb + bj] = stamp;
+            if (any && s_rot) rotated[b] = 1;
+            if (any) atomicAdd(&nactive[b], 1);
+        }
+        if (any || FULL)
+            for (int e = tid; e < 2 * JB * JB; e += FLOW_THREADS) {
+                const int h = e >> 8, r = (e >> 4) & 15, c = e & 15;
+                (h ? DJ : DI)[e & 255] = G[(h * JB + r) * JPITCH + h * JB + c];
+            }
+        trace_end(2, trace_t0);
+        // ------------------------------------------------ update  P <- P W  (A panel, then V panel) -----------
+        if (any) {
+            trace_t0 = d_trace_buf ? trace_now() : 0ull;
+            for (int e = tid; e < JP * JP; e += FLOW_THREADS) {
+                const double2 wv = W[(e >> 5) * JPITCH + (e & 31)];
+                Wsum[(e >> 5) * FSP + (e & 31)] = wv.x + wv.y;
+            }
+            __syncthreads();   // Wsum is complete; every thread has read its D write-back values out of G
+            // Software pipeline: the 8 fragments of the next DU row groups are fetched by cp.async into per-thread slots of
+            // [ G | extra ] (G is dead after the eigensolve) while the 96 DMMAs of the current group run; every thread reads
+            // back exactly what it fetched itself.  The W fragments of k4 + 1 are loaded under the DMMAs of k4.  All column
+            // addressing is hoisted out of the row loop (a warp holds one DMMA issue slot in four: every other instruction
+            // of the loop is time the tensor pipe is not fed -- tools/micro/dmma_warp.cu).
+            double2* const slot = G + tid;   // [slot][k4][FLOW_THREADS]
+            constexpr int NWP = FLOW_THREADS / 32;
+            constexpr int NJ = MINB >= 4 ? 2 : 4;   // column blocks per pass (3 NJ accumulator pairs)
+            auto run_panel = [&](double2* __restrict__ base, const int nrows) {
+                const int ngr = (nrows + 7) >> 3;
+                const int ngw = ngr > warp ? (ngr - warp + NWP - 1) / NWP : 0;   // this warp's row groups: warp + NWP * k
+                const double2* src_col[8];   // fragment slot k4 of this lane: column k4 * 4 + t, row g of the group
+                unsigned src_ok = 0;
+#pragma unroll
+                for (int k4 = 0; k4 < 8; ++k4) {
+                    const int col = panel_col(k4 * 4 + t, bi, bj, pn);
+                    src_col[k4] = base + (size_t)(col >= 0 ? col : 0) * nrows + g;
+                    src_ok |= (col >= 0 ? 1u : 0u) << k4;
+                }
+                auto fetch_rows = [&](int kq) {
+                    if (kq < ngw) {
+                        const int r0 = (warp + NWP * kq) * 8;
+                        const bool rok = r0 + g < nrows;
+                        const unsigned dst = (unsigned)__cvta_generic_to_shared(slot + (size_t)(kq % Cfg::DU) * (8 * FLOW_THREADS));
+#pragma unroll
+                        for (int k4 = 0; k4 < 8; ++k4) {
+                            const int sz = (rok && ((src_ok >> k4) & 1u)) ? 16 : 0;
+                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst + (unsigned)(k4 * FLOW_THREADS * 16)),
+                                         "l"(sz ? src_col[k4] + r0 : src_col[k4]), "r"(sz));
+                        }
+                    }
+                    cp_async_commit();
+                };
+                for (int kq = 0; kq < Cfg::DU; ++kq) fetch_rows(kq);
+                for (int kq = 0; kq < ngw; ++kq) {
+                    double2 a[8];
+                    cp_async_wait<Cfg::DU - 1>();   // group kq has landed
+                    const double2* src = slot + (size_t)(kq % Cfg::DU) * (8 * FLOW_THREADS);
+#pragma unroll
+                    for (int k4 = 0; k4 < 8; ++k4) a[k4] = src[k4 * FLOW_THREADS];
+                    asm volatile("" ::: "memory");   // the slot is re-filled only after it has been read
+                    fetch_rows(kq + Cfg::DU);
+                    const int row = (warp + NWP * kq) * 8 + g;
+                    const bool rok = row < nrows;
+#pragma unroll 1
+                    for (int jh = 0; jh < 4 / NJ; ++jh) {
+                        double p1[NJ][2], p2[NJ][2], p3[NJ][2];
+#pragma unroll
+                        for (int j = 0; j < NJ; ++j) p1[j][0] = p1[j][1] = p2[j][0] = p2[j][1] = p3[j][0] = p3[j][1] = 0.0;
+                        const double2* wp = W + t * JPITCH + (NJ * jh) * 8 + g;
+                        const double* sp = Wsum + t * FSP + (NJ * jh) * 8 + g;
+                        double2 b0[NJ], b1[NJ];
+                        double s0[NJ], s1[NJ];
+#pragma unroll
+                        for (int j = 0; j < NJ; ++j) { b0[j] = wp[j * 8]; s0[j] = sp[j * 8]; }
+#pragma unroll
+                        for (int k4 = 0; k4 < 8; k4 += 2) {
+#pragma unroll
+                            for (int j = 0; j < NJ; ++j) { b1[j] = wp[(k4 + 1) * 4 * JPITCH + j * 8]; s1[j] = sp[(k4 + 1) * 4 * FSP + j * 8]; }
+                            {
+                                const double asum = a[k4].x + a[k4].y;
+#pragma unroll
+                                for (int j = 0; j < NJ; ++j) dmma(p1[j][0], p1[j][1], a[k4].x, b0[j].x);
+#pragma unroll
+                                for (int j = 0; j < NJ; ++j) dmma(p2[j][0], p2[j][1], a[k4].y, b0[j].y);
+#pragma unroll
+                                for (int j = 0; j < NJ; ++j) dmma(p3[j][0], p3[j][1], asum, s0[j]);
+                            }
+                            if (k4 + 2 < 8) {
+#pragma unroll
+                                for (int j = 0; j < NJ; ++j) { b0[j] = wp[(k4 + 2) * 4 * JPITCH + j * 8]; s0[j] = sp[(k4 + 2) * 4 * FSP + j * 8]; }
+                            }
+                            {
+                                const double asum = a[k4 + 1].x + a[k4 + 1].y;
+#pragma unroll
+                                for (int j = 0; j < NJ; ++j) dmma(p1[j][0], p1[j][1], a[k4 + 1].x, b1[j].x);
+#pragma unroll
+                                for (int j = 0; j < NJ; ++j) dmma(p2[j][0], p2[j][1], a[k4 + 1].y, b1[j].y);
+#pragma unroll
+                                for (int j = 0; j < NJ; ++j) dmma(p3[j][0], p3[j][1], asum, s1[j]);
+                            }
+                        }
+                        if (rok) {
+                            // output slot (j, q) of this lane: column (NJ jh + j) * 8 + 2 t + q.  Columns 2t, 2t+1 are neighbours
+                            // of one block (JB is even), so one panel_col per j locates both.
+#pragma unroll
+                            for (int j = 0; j < NJ; ++j) {
+                                const int col = panel_col((NJ * jh + j) * 8 + 2 * t, bi, bj, pn);
+                                if (col >= 0) {
+                                    double2* o = base + (size_t)col * nrows + row;
+                                    o[0] = make_double2(p1[j][0] - p2[j][0], p3[j][0] - p1[j][0] - p2[j][0]);
+                                    if (col + 1 < pn) o[nrows] = make_double2(p1[j][1] - p2[j][1], p3[j][1] - p1[j][1] - p2[j][1]);
+                                }
+                            }
+                        }
+                    }
+                }
+                cp_async_wait<0>();
+            };
+            run_panel(prp->A, m);
+            if (prp->V) run_panel(prp->V, pn);
+            trace_end(3, trace_t0);
+        }
+        // publish: every thread's stores (A, V, D, stamps) are fenced before the versions move
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) {
+            st_release(prp->ver + bi, round + 1);
+            st_release(prp->ver + bj, round + 1);
+        }
+    }
+}
+
 __global__ void set_int_kernel(int* p, int n, int v) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
@@ -915,6 +1424,9 @@ int svd_batched_device(int batch, const SvdJob* jobs_in, double er, int64_t maxd
     auto al = [&](size_t bytes) { size_t o = dev_bytes; dev_bytes += (bytes + 255) / 256 * 256; return o; };
     std::vector<size_t> offAt(batch), offV(batch), offSig(batch), offRank(batch), offStamp(batch), offD(batch);
     std::vector<double> work(batch);
+    std::vector<size_t> ver_off(batch);
+    size_t ver_ints = 0;
+    long pairs_per_round = 0;
     int maxn = 0, maxm = 0;
     double total_work = 0;
     for (int b = 0; b < batch; ++b) {
@@ -927,15 +1439,38 @@ int svd_batched_device(int batch, const SvdJob* jobs_in, double er, int64_t maxd
         if (nbk & 1) ++nbk;
         offStamp[b] = al((size_t)(nbk + (size_t)nbk * nbk) * 4);
         offD[b] = al((size_t)nbk * JB * JB * 16);
+        ver_off[b] = ver_ints;
+        ver_ints += (size_t)nbk;
+        pairs_per_round += nbk / 2;
         maxn = std::max<int>(maxn, (int)n);
         maxm = std::max<int>(maxm, (int)m);
         work[b] = (double)(m + ((jobs[b].need_v || tr[b]) ? n : 0)) * n * n;  // ~ flops of one sweep
         total_work += work[b];
     }
+    // ---- dataflow mode: enough block pairs per round to keep 4 CTAs on every SM busy ----------------------------
+    bool flow = pairs_per_round >= 2 * 148 && maxn > 2 * JB;
+    if (const char* e = getenv("QTN_JACOBI_FLOW")) { if (atoi(e) == 0) flow = false; else if (atoi(e) == 2) flow = maxn > 2 * JB; }
+    const size_t offVer = al((ver_ints + 16) * 4);   // block versions of all problems, then the two task counters
+    std::vector<uint2> tasks;
+    int ntasks0 = 0;   // tasks of round 0
+    if (flow) {
+        int max_nb_all = 2;
+        for (int b = 0; b < batch; ++b) { int nbk = (int)((cols(perm[b]) + JB - 1) / JB); if (nbk & 1) ++nbk; max_nb_all = std::max(max_nb_all, nbk); }
+        for (int round = 0; round < max_nb_all - 1; ++round) {
+            for (int b = 0; b < batch; ++b) {
+                int nbk = (int)((cols(perm[b]) + JB - 1) / JB);
+                if (nbk & 1) ++nbk;
+                if (nbk < 2 || round >= nbk - 1) continue;
+                for (int pair = 0; pair < nbk / 2; ++pair) tasks.push_back(make_uint2((unsigned)b, ((unsigned)round << 16) | (unsigned)pair));
+            }
+            if (round == 0) ntasks0 = (int)tasks.size();
+        }
+    }
+    const size_t offTasks = al(tasks.size() * sizeof(uint2) + 16);
     // ---- sub-batches: contiguous in the sorted order, about equal work each -----------------------------------
-    int ngroups = std::min(batch, kMaxGroups);
+    int ngroups = flow ? 1 : std::min(batch, kMaxGroups);
     if (const char* e = getenv("QTN_JACOBI_GROUPS")) ngroups = std::max(1, std::min(std::min(batch, kMaxGroups), atoi(e)));
-    if (total_work < 4e9) ngroups = 1;  // small problems: launch-latency-bound, one stream
+    if (total_work < 4e9 || flow) ngroups = 1;  // small problems: launch-latency-bound, one stream
     std::vector<SvdGroup> groups;
     {
         // cumulative work shares of the sub-batches.  QTN_JACOBI_SKEW=x (default 0 = equal shares) makes them unequal
@@ -1020,6 +1555,7 @@ int svd_batched_device(int batch, const SvdJob* jobs_in, double er, int64_t maxd
         hp[b].last_mod = (int*)(base + offStamp[b]);
         hp[b].last_ok = hp[b].last_mod + nbk;
         hp[b].D = (double2*)(base + offD[b]);
+        hp[b].ver = (int*)(base + offVer) + ver_off[b];
         // last_mod = 1, last_ok = 0: every pair starts "modified after its last check"
         CUDA_TRY(cudaMemsetAsync(hp[b].last_ok, 0, (size_t)nbk * nbk * 4, st));
         set_int_kernel<<<(nbk + 255) / 256, 256, 0, st>>>(hp[b].last_mod, nbk, 1);
@@ -1037,6 +1573,20 @@ int svd_batched_device(int batch, const SvdJob* jobs_in, double er, int64_t maxd
     }
     CUDA_TRY(cudaMemcpyAsync(dtab, h, tab_bytes - 1024, cudaMemcpyHostToDevice, st));
     const SvdProblem* dp = (const SvdProblem*)dtab;
+    int* dcounter = (int*)(base + offVer) + ver_ints;
+    const uint2* dtasks = (const uint2*)(base + offTasks);
+    if (flow) {
+        CUDA_TRY(cudaMemcpyAsync(base + offTasks, tasks.data(), tasks.size() * sizeof(uint2), cudaMemcpyHostToDevice, st));
+        static bool carve_done = false;
+        if (!carve_done) {  // dynamic shared-memory arenas (45 - 110 KB per CTA)
+            CUDA_TRY(cudaFuncSetAttribute(jacobi_flow_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FlowCfg<4>::SMEM));
+            CUDA_TRY(cudaFuncSetAttribute(jacobi_flow_kernel<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FlowCfg<3>::SMEM));
+            CUDA_TRY(cudaFuncSetAttribute(jacobi_flow_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FlowCfg<2>::SMEM));
+            CUDA_TRY(cudaFuncSetAttribute(jacobi_flow_kernel<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FlowCfg<3>::SMEM));
+            CUDA_TRY(cudaFuncSetAttribute(jacobi_flow_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FlowCfg<2>::SMEM));
+            carve_done = true;
+        }
+    }
     const FinishArgs* df = (const FinishArgs*)dptr(hf);
     double* const* dsig = (double* const*)dptr(hsig);
     int* const* drank = (int* const*)dptr(hrank);
@@ -1102,6 +1652,33 @@ int svd_batched_device(int batch, const SvdJob* jobs_in, double er, int64_t maxd
             max_rounds = std::max(max_rounds, grp.max_nb - 1);
         }
         int* st_ptr = dstat ? dstat + 2 * std::min(sweeps, 63) : (int*)nullptr;
+        if (flow) {
+            // one task-queue kernel per sweep (two when round 0 computes full Grams and the rest take cached diagonals)
+            const SvdGroup& grp = groups[0];
+            cudaStream_t fs = g_sub[0];
+            CUDA_TRY(cudaMemsetAsync(base + offVer, 0, (ver_ints + 16) * 4, fs));
+            const int nt = (int)tasks.size();
+            static int flow_ctas = -1;   // CTAs per SM of the cross-Gram kernel (QTN_JACOBI_FLOW_CTAS = 2 / 3 / 4)
+            if (flow_ctas < 0) { const char* e = getenv("QTN_JACOBI_FLOW_CTAS"); flow_ctas = e ? std::max(2, std::min(4, atoi(e))) : 3; }
+            auto launch = [&](bool full, int t0, int t1, int* counter) {
+                if (t1 <= t0) return;
+                const int per_sm = full ? std::min(flow_ctas, 3) : flow_ctas;
+                const int ctas = std::min(t1 - t0, 148 * per_sm);
+#define QTN_FLOW_LAUNCH(F, B)                                                                                                   \
+    jacobi_flow_kernel<F, B><<<ctas, FLOW_THREADS, FlowCfg<B>::SMEM, fs>>>(dp, dtasks + t0, t1 - t0, counter, tol, drot,          \
+                                                                           (const double*)dfro, inner, st_ptr, stamp + 1, dact)
+                if (full) { if (per_sm == 3) QTN_FLOW_LAUNCH(true, 3); else QTN_FLOW_LAUNCH(true, 2); }
+                else if (per_sm == 4) QTN_FLOW_LAUNCH(false, 4);
+                else if (per_sm == 3) QTN_FLOW_LAUNCH(false, 3);
+                else QTN_FLOW_LAUNCH(false, 2);
+#undef QTN_FLOW_LAUNCH
+                count_launch(1);
+            };
+            if (grp.cross) { launch(true, 0, ntasks0, dcounter); launch(false, ntasks0, nt, dcounter + 1); }
+            else launch(true, 0, nt, dcounter);
+            stamp += max_rounds;
+            max_rounds = 0;
+        }
         for (int round = 0; round < max_rounds; ++round) {
             ++stamp;
             for (int g = 0; g < ngroups; ++g) {  // round-robin over the streams: none is starved by the enqueue order

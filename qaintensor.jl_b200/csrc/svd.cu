@@ -644,7 +644,7 @@ template <bool FULL, int MINB>
 __global__ void __launch_bounds__(FLOW_THREADS, MINB)
 jacobi_flow_kernel(const SvdProblem* __restrict__ probs, const uint2* __restrict__ tasks, int ntasks, int* __restrict__ counter,
                    double tol, int* __restrict__ rotated, const double* __restrict__ fro2, int inner_sweeps, int* __restrict__ stat,
-                   int stamp_base, int* __restrict__ nactive) {
+                   int stamp_base, int* __restrict__ nactive, int* __restrict__ errflag) {
     typedef FlowCfg<MINB> Cfg;
     extern __shared__ __align__(16) unsigned char flow_smem[];
     double2* const arena = reinterpret_cast<double2*>(flow_smem);
@@ -673,8 +673,14 @@ jacobi_flow_kernel(const SvdProblem* __restrict__ probs, const uint2* __restrict
         else { bi = (round + pair) % (nb - 1); bj = (round - pair + (nb - 1)) % (nb - 1); }
         if (bi > bj) { const int tt = bi; bi = bj; bj = tt; }
         if (tid == 0) {
-            unsigned ns = 32;
-            while (ld_acquire(prp->ver + bi) < round || ld_acquire(prp->ver + bj) < round) { __nanosleep(ns); if (ns < 1024) ns *= 2; }
+            unsigned ns = 32, polls = 0;
+            while (ld_acquire(prp->ver + bi) < round || ld_acquire(prp->ver + bj) < round) {
+                __nanosleep(ns);
+                if (ns < 1024) ns *= 2;
+                // watchdog (~1 s): a producer that never publishes is a bug, not a reason to hang the device; the host
+                // reports QTN_ECUDA when the flag is set
+                if (++polls > (1u << 20)) { atomicExch(errflag, 1); break; }
+            }
         }
         __syncthreads();
         const bool live = __ldcg(rotated + b) >= 0 && bi * JB < pn;
@@ -1574,6 +1580,8 @@ int svd_batched_device(int batch, const SvdJob* jobs_in, double er, int64_t maxd
     CUDA_TRY(cudaMemcpyAsync(dtab, h, tab_bytes - 1024, cudaMemcpyHostToDevice, st));
     const SvdProblem* dp = (const SvdProblem*)dtab;
     int* dcounter = (int*)(base + offVer) + ver_ints;
+    int* dflow_err = dcounter + 12;
+    if (flow) CUDA_TRY(cudaMemsetAsync(dflow_err, 0, 4, st));
     const uint2* dtasks = (const uint2*)(base + offTasks);
     if (flow) {
         CUDA_TRY(cudaMemcpyAsync(base + offTasks, tasks.data(), tasks.size() * sizeof(uint2), cudaMemcpyHostToDevice, st));
@@ -1656,7 +1664,7 @@ int svd_batched_device(int batch, const SvdJob* jobs_in, double er, int64_t maxd
             // one task-queue kernel per sweep (two when round 0 computes full Grams and the rest take cached diagonals)
             const SvdGroup& grp = groups[0];
             cudaStream_t fs = g_sub[0];
-            CUDA_TRY(cudaMemsetAsync(base + offVer, 0, (ver_ints + 16) * 4, fs));
+            CUDA_TRY(cudaMemsetAsync(base + offVer, 0, (ver_ints + 8) * 4, fs));   // versions + task counters (not the error flag)
             const int nt = (int)tasks.size();
             static int flow_ctas = -1;   // CTAs per SM of the cross-Gram kernel (QTN_JACOBI_FLOW_CTAS = 2 / 3 / 4)
             if (flow_ctas < 0) { const char* e = getenv("QTN_JACOBI_FLOW_CTAS"); flow_ctas = e ? std::max(2, std::min(4, atoi(e))) : 3; }
@@ -1666,7 +1674,7 @@ int svd_batched_device(int batch, const SvdJob* jobs_in, double er, int64_t maxd
                 const int ctas = std::min(t1 - t0, 148 * per_sm);
 #define QTN_FLOW_LAUNCH(F, B)                                                                                                   \
     jacobi_flow_kernel<F, B><<<ctas, FLOW_THREADS, FlowCfg<B>::SMEM, fs>>>(dp, dtasks + t0, t1 - t0, counter, tol, drot,          \
-                                                                           (const double*)dfro, inner, st_ptr, stamp + 1, dact)
+                                                                           (const double*)dfro, inner, st_ptr, stamp + 1, dact, dflow_err)
                 if (full) { if (per_sm == 3) QTN_FLOW_LAUNCH(true, 3); else QTN_FLOW_LAUNCH(true, 2); }
                 else if (per_sm == 4) QTN_FLOW_LAUNCH(false, 4);
                 else if (per_sm == 3) QTN_FLOW_LAUNCH(false, 3);
@@ -1760,6 +1768,11 @@ int svd_batched_device(int batch, const SvdJob* jobs_in, double er, int64_t maxd
         for (int i = 0; i < sweeps && i < 64; ++i) fprintf(stderr, " (%d,%d)", hs[2 * i], hs[2 * i + 1]);
         fprintf(stderr, "\n");
         cudaFree(dstat);
+    }
+    if (flow) {
+        int herr = 0;
+        CUDA_TRY(cudaMemcpy(&herr, dflow_err, 4, cudaMemcpyDeviceToHost));
+        if (herr) return fail(QTN_ECUDA, "Jacobi dataflow kernel: a block-pair task waited for its producers for more than a second (watchdog)");
     }
     // every sub-stream was synchronised by the host above: the library stream continues with the finalisation
     column_norms_kernel<<<dim3(std::min(148 * 2, (maxn + 7) / 8), batch), 256, 0, st>>>(dp, dsig);

@@ -21,7 +21,8 @@
  *   - there is NO CPU fallback: compute entry points fail with QTN_ENODEVICE
  *     when no sm_100 device is usable.  Host-only entry points (ordering,
  *     planning, cost queries) work without a GPU;
- *   - not re-entrant: call from one host thread at a time.
+ *   - not re-entrant: call from one host thread at a time.  A second thread entering a device entry point
+ *     while another one is inside fails with QTN_EBUSY instead of corrupting the shared stream / workspace state.
  */
 #ifndef QAINTENSOR_CUDA_H
 #define QAINTENSOR_CUDA_H
@@ -39,6 +40,7 @@ extern "C" {
 #define QTN_ENOMEM (-4)    /* device arena exhausted                   */
 #define QTN_ENCCL (-5)     /* NCCL unavailable or failed               */
 #define QTN_EDOMAIN (-6)   /* reference error() condition (see message) */
+#define QTN_EBUSY (-7)     /* another host thread is inside a device entry point (not re-entrant) */
 
 typedef struct qtn_plan qtn_plan;       /* contraction plan (opaque)          */
 typedef struct qtn_mps qtn_mps;         /* device-resident MPS (opaque)       */

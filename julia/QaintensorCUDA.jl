@@ -8,6 +8,7 @@ module QaintensorCUDA
 const LIB = get(ENV, "QAINTENSOR_CUDA_LIB", "libqaintensor_cuda")
 const QTN_C128 = Cint(0)
 const QTN_EDOMAIN = Cint(-6)
+const QTN_EBUSY = Cint(-7)   # a second host thread entered a device entry point (the library is not re-entrant)
 
 struct QtnError <: Exception
     code::Cint

@@ -16,6 +16,7 @@ QTN_C128 = 0
 QTN_C64 = 1
 QTN_ENODEVICE = -2
 QTN_EDOMAIN = -6
+QTN_EBUSY = -7
 
 
 class QtnError(RuntimeError):

@@ -49,6 +49,7 @@ int qtn_device_count(int* count) {
 void* qtn_stream(void) { return (void*)stream(); }
 int64_t qtn_launch_count(int reset) { return launch_count(reset); }
 int qtn_bench_dmma_peak(double* tflops_out) {
+    QTN_API_GUARD();
     if (!tflops_out) return fail(QTN_EINVAL, "null argument");
     return bench_dmma_peak(tflops_out);
 }
@@ -77,6 +78,7 @@ int qtn_plan_create(int32_t nt, const int32_t* ranks, const int64_t* const* dims
     return QTN_OK;
 }
 int qtn_plan_destroy(qtn_plan* plan) {
+    QTN_API_GUARD();
     if (!plan) return QTN_OK;
     plan_device_free(plan->p);
     delete plan->p;
@@ -128,10 +130,12 @@ int qtn_plan_steps(const qtn_plan* plan, int64_t* mnk, int32_t* flags) {
     return QTN_OK;
 }
 int qtn_plan_upload(qtn_plan* plan, const void* const* host_data) {
+    QTN_API_GUARD();
     if (!plan || !host_data) return fail(QTN_EINVAL, "qtn_plan_upload: null argument");
     return plan_upload(plan->p, host_data);
 }
 int qtn_plan_execute(qtn_plan* plan, int64_t slice_begin, int64_t slice_end, void* dev_out) {
+    QTN_API_GUARD();
     if (!plan) return fail(QTN_EINVAL, "null plan");
     return plan_execute(plan->p, slice_begin, slice_end, dev_out);
 }
@@ -139,10 +143,12 @@ int qtn_plan_execute(qtn_plan* plan, int64_t slice_begin, int64_t slice_end, voi
 static int exec_host(Plan* p, const void* const* host_data, int64_t s0, int64_t s1, void* host_out, bool allreduce);
 
 int qtn_plan_execute_host(qtn_plan* plan, const void* const* host_data, int64_t slice_begin, int64_t slice_end, void* host_out) {
+    QTN_API_GUARD();
     if (!plan || !host_out) return fail(QTN_EINVAL, "qtn_plan_execute_host: null argument");
     return exec_host(plan->p, host_data, slice_begin, slice_end, host_out, false);
 }
 int qtn_plan_time_steps(qtn_plan* plan, int64_t slice_id, float* ms) {
+    QTN_API_GUARD();
     if (!plan || !ms) return fail(QTN_EINVAL, "qtn_plan_time_steps: null argument");
     return plan_time_steps(plan->p, slice_id, ms);
 }
@@ -150,6 +156,7 @@ int qtn_plan_time_steps(qtn_plan* plan, int64_t slice_id, float* ms) {
 int qtn_contract(int32_t nt, const void* const* host_data, const int32_t* ranks, const int64_t* const* dims,
                  const int32_t* const* labels, const int32_t* order, int32_t norder, int32_t dtype, void* host_out,
                  int32_t* out_rank, int64_t* out_dims) {
+    QTN_API_GUARD();
     if (!host_data || !host_out) return fail(QTN_EINVAL, "qtn_contract: null argument");
     int rc = device_ready();
     if (rc) return rc;
@@ -236,6 +243,7 @@ static int exec_host(Plan* p, const void* const* host_data, int64_t s0, int64_t 
 
 int qtn_contract_sliced_range(qtn_plan* plan, const void* const* host_data, int64_t first_slice, int64_t nslices,
                               int32_t rank, int32_t nranks, void* host_out) {
+    QTN_API_GUARD();
     if (!plan || !host_out) return fail(QTN_EINVAL, "qtn_contract_sliced: null argument");
     if (nranks < 1 || rank < 0 || rank >= nranks) return fail(QTN_EINVAL, "qtn_contract_sliced: bad rank %d of %d", rank, nranks);
     if (first_slice < 0 || nslices < 0 || first_slice + nslices > plan->p->nslices)
@@ -244,6 +252,7 @@ int qtn_contract_sliced_range(qtn_plan* plan, const void* const* host_data, int6
     return exec_host(plan->p, host_data, s0, s1, host_out, nranks > 1);
 }
 int qtn_contract_sliced(qtn_plan* plan, const void* const* host_data, int32_t rank, int32_t nranks, void* host_out) {
+    QTN_API_GUARD();
     if (!plan) return fail(QTN_EINVAL, "qtn_contract_sliced: null argument");
     return qtn_contract_sliced_range(plan, host_data, 0, plan->p->nslices, rank, nranks, host_out);
 }
@@ -251,12 +260,14 @@ int qtn_contract_sliced(qtn_plan* plan, const void* const* host_data, int32_t ra
 // ---- permutedims ---------------------------------------------------------------------
 int qtn_permutedims_device(const void* dev_in, int32_t rank, const int64_t* dims, const int32_t* perm, int32_t dtype,
                            void* dev_out) {
+    QTN_API_GUARD();
     if (dtype != QTN_C128) return fail(QTN_EINVAL, "only QTN_C128 is implemented");
     int rc = device_ready();
     if (rc) return rc;
     return permutedims_device(dev_in, rank, dims, perm, dev_out);
 }
 int qtn_permutedims(const void* host_in, int32_t rank, const int64_t* dims, const int32_t* perm, int32_t dtype, void* host_out) {
+    QTN_API_GUARD();
     if (dtype != QTN_C128) return fail(QTN_EINVAL, "only QTN_C128 is implemented");
     int rc = device_ready();
     if (rc) return rc;
@@ -313,6 +324,7 @@ int zgemm_dense(char opa, char opb, int64_t m, int64_t n, int64_t k, const void*
 extern "C" {
 int qtn_zgemm_device(char opa, char opb, int64_t m, int64_t n, int64_t k, const void* dev_a, int64_t lda,
                      const void* dev_b, int64_t ldb, void* dev_c, int64_t ldc) {
+    QTN_API_GUARD();
     int rc = device_ready();
     if (rc) return rc;
     return zgemm_dense(opa, opb, m, n, k, dev_a, lda, dev_b, ldb, dev_c, ldc, false);

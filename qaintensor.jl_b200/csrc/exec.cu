@@ -7,6 +7,8 @@
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <mutex>
+#include <thread>
 
 #define QTN_KERNELS_IMPL
 #include "kernels.cuh"
@@ -27,6 +29,22 @@ int fail(int code, const char* fmt, ...) {
     return code;
 }
 const char* last_error_text() { return g_err; }
+
+static std::mutex g_api_mutex;
+static std::thread::id g_api_owner;
+static int g_api_depth = 0;
+ApiGuard::ApiGuard() {
+    std::lock_guard<std::mutex> lk(g_api_mutex);
+    const std::thread::id me = std::this_thread::get_id();
+    if (g_api_depth == 0) { g_api_owner = me; g_api_depth = 1; ok = true; }
+    else if (g_api_owner == me) { ++g_api_depth; ok = true; }
+    else ok = false;
+}
+ApiGuard::~ApiGuard() {
+    if (!ok) return;
+    std::lock_guard<std::mutex> lk(g_api_mutex);
+    --g_api_depth;
+}
 
 static bool g_inited = false;
 static int g_device = -1;

@@ -235,6 +235,7 @@ extern "C" {
 
 int qtn_contract_svd(const void* host_t1, int32_t rank1, const int64_t* dims1, int32_t i1, const void* host_t2,
                      int32_t rank2, const int64_t* dims2, int32_t i2, double er, void* host_out) {
+    QTN_API_GUARD();
     if (!(er >= 0)) return fail(QTN_EDOMAIN, "Error must be positive");
     if (!host_t1 || !host_t2 || !host_out || !dims1 || !dims2) return fail(QTN_EINVAL, "qtn_contract_svd: null argument");
     if (i1 < 1 || i2 < 1) return fail(QTN_EINVAL, "qtn_contract_svd: leg index must be >= 1");
@@ -272,6 +273,7 @@ int qtn_contract_svd(const void* host_t1, int32_t rank1, const int64_t* dims1, i
 // ---------------- device-resident MPS (EXTENSION) -------------------------------------------------
 int qtn_mps_create(int32_t nsites, const void* const* host_sites, const int64_t* lbond, const int64_t* rbond,
                    int64_t maxdim_capacity, qtn_mps** mps_out) {
+    QTN_API_GUARD();
     if (nsites < 2 || !host_sites || !lbond || !rbond || !mps_out || maxdim_capacity < 1) return fail(QTN_EINVAL, "qtn_mps_create: bad argument");
     int rc = device_ready();
     if (rc) return rc;
@@ -302,6 +304,7 @@ int qtn_mps_create(int32_t nsites, const void* const* host_sites, const int64_t*
 }
 
 int qtn_mps_destroy(qtn_mps* m) {
+    QTN_API_GUARD();
     if (!m) return QTN_OK;
     if (stream()) cudaStreamSynchronize(stream());
     for (auto p : m->site) if (p) cudaFree(p);
@@ -321,6 +324,7 @@ int qtn_mps_bonds(const qtn_mps* m, int64_t* lbond, int64_t* rbond) {
 }
 
 int qtn_mps_download(const qtn_mps* m, void* const* host_sites) {
+    QTN_API_GUARD();
     if (!m || !host_sites) return fail(QTN_EINVAL, "null argument");
     for (int i = 0; i < m->n; ++i)
         CUDA_TRY(cudaMemcpyAsync(host_sites[i], m->site[i], (size_t)m->lb[i] * 2 * m->rb[i] * 16, cudaMemcpyDeviceToHost, stream()));
@@ -350,6 +354,7 @@ static int mps_scratch(qtn_mps* m, int bonds) {
 
 int qtn_mps_apply_layer(qtn_mps* m, int32_t ngates, const int32_t* sites, const void* host_gates, double er, int64_t maxdim,
                         double* disc_out) {
+    QTN_API_GUARD();
     if (!m || !sites || !host_gates || ngates < 0) return fail(QTN_EINVAL, "qtn_mps_apply_layer: null argument");
     if (ngates == 0) return QTN_OK;
     if (maxdim <= 0 || maxdim > m->cap) maxdim = m->cap;
@@ -403,10 +408,12 @@ int qtn_mps_apply_layer(qtn_mps* m, int32_t ngates, const int32_t* sites, const 
 }
 
 int qtn_mps_apply_gate2(qtn_mps* m, int32_t site, const void* host_gate, double er, int64_t maxdim, double* disc_out) {
+    QTN_API_GUARD();
     return qtn_mps_apply_layer(m, 1, &site, host_gate, er, maxdim, disc_out);
 }
 
 int qtn_mps_overlap(const qtn_mps* a, const qtn_mps* b, double out[2]) {
+    QTN_API_GUARD();
     if (!a || !b || !out) return fail(QTN_EINVAL, "null argument");
     if (a->n != b->n) return fail(QTN_EINVAL, "qtn_mps_overlap: different lengths");
     if (a->lb[0] != 1 || b->lb[0] != 1 || a->rb[a->n - 1] != 1 || b->rb[b->n - 1] != 1)
@@ -436,6 +443,7 @@ int qtn_mps_overlap(const qtn_mps* a, const qtn_mps* b, double out[2]) {
 
 // ---------------- MPS(psi) on the device (src/mps.jl:55-89) ----------------------------------------------
 int qtn_mps_from_vector(const void* host_psi, int32_t nsites, void* const* host_sites, int64_t* bonds_out) {
+    QTN_API_GUARD();
     if (!host_psi || !host_sites || !bonds_out) return fail(QTN_EINVAL, "qtn_mps_from_vector: null argument");
     if (nsites < 2 || nsites > 30) return fail(QTN_EINVAL, "qtn_mps_from_vector: nsites must be in 2..30");
     int rc = device_ready();
@@ -453,6 +461,7 @@ int qtn_mps_from_vector(const void* host_psi, int32_t nsites, void* const* host_
 // with bond_0 = 1 (the first site is (2, 2, bond_1), the last (bond_{M-1}, 2, 2)); the svd is not truncated, so
 // bond_i = min(4 bond_{i-1}, 4^(M-i)) is known to the caller, who sizes the buffers.  bonds_out[M - 1].
 int qtn_mpo_from_matrix(const void* host_m, int32_t nqubits, void* const* host_sites, int64_t* bonds_out) {
+    QTN_API_GUARD();
     if (!host_m || !host_sites || !bonds_out) return fail(QTN_EINVAL, "qtn_mpo_from_matrix: null argument");
     if (nqubits < 2) return fail(QTN_EDOMAIN, "Need at least two qubits to split (a one-qubit operator is its own MPO)");
     if (nqubits > 15) return fail(QTN_EINVAL, "qtn_mpo_from_matrix: nqubits must be in 2..15");
@@ -473,6 +482,7 @@ int qtn_mpo_from_matrix(const void* host_m, int32_t nqubits, void* const* host_s
 // decompose!(cg) (src/decompose.jl:6-52) performs exactly the chain of MPO(m) on the gate's matrix; the wire /
 // bond bookkeeping (t, c, w) stays with the caller.
 int qtn_decompose(const void* host_m, int32_t nqubits, void* const* host_sites, int64_t* bonds_out) {
+    QTN_API_GUARD();
     if (nqubits < 2) return fail(QTN_EDOMAIN, "Only decompose Circuit Gates that apply to multiple wires");
     return qtn_mpo_from_matrix(host_m, nqubits, host_sites, bonds_out);
 }
@@ -484,6 +494,7 @@ int qtn_decompose(const void* host_m, int32_t nqubits, void* const* host_sites, 
 // (= prod of all open extents; the caller knows the shape: dims(T_1)[:-1] ++ dims(T_2)[2:-1] ++ ... ++ dims(T_n)[2:]).
 int qtn_contract_svd_fold(int32_t ntensors, const void* const* host_t, const int64_t* numel, const int64_t* first,
                           const int64_t* last, double er, void* host_out, int64_t numel_out) {
+    QTN_API_GUARD();
     if (!(er >= 0)) return fail(QTN_EDOMAIN, "Error must be positive");
     if (ntensors < 1 || !host_t || !numel || !first || !last || !host_out) return fail(QTN_EINVAL, "qtn_contract_svd_fold: null argument");
     int64_t tot = 0;     // elements of the running tensor
@@ -529,6 +540,7 @@ int qtn_contract_svd_fold(int32_t ntensors, const void* const* host_t, const int
 // host_u receives (l1, 2, bond) [(2, bond)], host_v (bond, 2, r2) [(bond, 2)]; *bond_out = min(2 l1, 2 r2).
 int qtn_mps_switch_adjacent(const void* host_t1, int64_t l1, int64_t b, const void* host_t2, int64_t r2, void* host_u,
                             void* host_v, int64_t* bond_out) {
+    QTN_API_GUARD();
     if (!host_t1 || !host_t2 || !host_u || !host_v || !bond_out) return fail(QTN_EINVAL, "qtn_mps_switch_adjacent: null argument");
     if (l1 < 0 || r2 < 0 || b < 1) return fail(QTN_EINVAL, "qtn_mps_switch_adjacent: bad extents");
     int rc = device_ready();
@@ -573,6 +585,7 @@ static int check_mpo(const qtn_mps* m, const void* const* sites, const int64_t* 
 
 int qtn_mps_apply_mpo(qtn_mps* m, const void* const* host_mpo_sites, const int64_t* dl, const int64_t* dr, double er,
                       int64_t maxdim, double* disc_out) {
+    QTN_API_GUARD();
     int rc = check_mpo(m, host_mpo_sites, dl, dr);
     if (rc) return rc;
     if ((rc = device_ready())) return rc;
@@ -665,6 +678,7 @@ int qtn_mps_apply_mpo(qtn_mps* m, const void* const* host_mpo_sites, const int64
 
 // EXTENSION: orthonormal basis of the columns of a host matrix (m >= n); the gauge step of qtn_mps_apply_mpo.
 int qtn_orth_columns(const void* host_a, int64_t m, int64_t n, void* host_q, int32_t* method_out) {
+    QTN_API_GUARD();
     if (!host_a || !host_q) return fail(QTN_EINVAL, "qtn_orth_columns: null argument");
     if (n < 1 || m < n) return fail(QTN_EINVAL, "qtn_orth_columns: needs m >= n >= 1 (got %lld x %lld)", (long long)m, (long long)n);
     int rc = device_ready();
@@ -685,6 +699,7 @@ int qtn_orth_columns(const void* host_a, int64_t m, int64_t n, void* host_q, int
 }
 
 int qtn_mps_expect_mpo(const qtn_mps* m, const void* const* host_mpo_sites, const int64_t* dl, const int64_t* dr, double out[2]) {
+    QTN_API_GUARD();
     int rc = check_mpo(m, host_mpo_sites, dl, dr);
     if (rc) return rc;
     if (!out) return fail(QTN_EINVAL, "null argument");

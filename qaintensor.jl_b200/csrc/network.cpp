@@ -327,6 +327,7 @@ int qtn_net_optimize_order(qtn_net* net, int32_t method, int32_t ntrials, uint64
 // dtype = QTN_C64: the tensors are rounded to ComplexF32 and host_out receives float pairs.
 int qtn_net_contract(const qtn_net* net, int32_t dtype, int32_t max_log2_elems, void* host_out, int32_t* out_rank,
                      int64_t* out_dims) {
+    QTN_API_GUARD();
     if (!net || !host_out) return fail(QTN_EINVAL, "qtn_net_contract: null argument");
     if (net->tensors.empty()) return fail(QTN_EINVAL, "contraction needs at least one tensor");
     Marshal m;

@@ -13,6 +13,19 @@ namespace qtn {
 // Records the message returned by qtn_last_error() and returns `code`.
 int fail(int code, const char* fmt, ...);
 
+// The library keeps one stream, one workspace pool and per-plan graphs: device entry points are not re-entrant.
+// ApiGuard makes a concurrent call from a second host thread fail (QTN_EBUSY) instead of racing on that state;
+// nested calls on the owning thread (entry points built on other entry points) pass.
+struct ApiGuard {
+    bool ok;
+    ApiGuard();
+    ~ApiGuard();
+};
+#define QTN_API_GUARD()                                                                                              \
+    qtn::ApiGuard _qtn_api_guard;                                                                                    \
+    if (!_qtn_api_guard.ok)                                                                                          \
+        return qtn::fail(QTN_EBUSY, "libqaintensor_cuda is not re-entrant: another host thread is inside a device entry point")
+
 // ---- order.cpp ---------------------------------------------------------------
 int order_treewidth(int ntensors, int ncontr, const int32_t* pairs, int32_t* perm_out, int32_t* tw_out);
 int graph_treewidth(int nv, int ne, const int32_t* edges, int32_t* tw_out, int32_t* ordering_out);

@@ -1805,6 +1805,7 @@ extern "C" {
 
 int qtn_svd_trunc_device(void* dev_a, int64_t m, int64_t n, double er, int64_t maxdim, void* dev_u, double* dev_s,
                          void* dev_vh, int64_t* k_out, int32_t* sweeps_out) {
+    QTN_API_GUARD();
     int rc = device_ready();
     if (rc) return rc;
     if (!dev_a || !dev_u || !dev_s || !dev_vh) return fail(QTN_EINVAL, "qtn_svd_trunc_device: null argument");
@@ -1818,6 +1819,7 @@ int qtn_svd_trunc_device(void* dev_a, int64_t m, int64_t n, double er, int64_t m
 int qtn_svd_trunc_batched(int32_t batch, const void* const* host_a, const int64_t* m, const int64_t* n, double er,
                           int64_t maxdim, void* const* host_u, double* const* host_s, void* const* host_vh,
                           int64_t* k_out) {
+    QTN_API_GUARD();
     int rc = device_ready();
     if (rc) return rc;
     if (batch < 0 || !host_a || !m || !n || !host_u || !host_s || !host_vh) return fail(QTN_EINVAL, "qtn_svd_trunc_batched: null argument");
@@ -1858,6 +1860,7 @@ int qtn_svd_trunc_batched(int32_t batch, const void* const* host_a, const int64_
 
 int qtn_svd_trunc(const void* host_a, int64_t m, int64_t n, double er, int64_t maxdim, void* host_u, double* host_s,
                   void* host_vh, int64_t* k_out) {
+    QTN_API_GUARD();
     const void* a[1] = {host_a};
     void* u[1] = {host_u};
     double* s[1] = {host_s};

@@ -95,6 +95,44 @@ def test_svd_batched_ragged(gpu):
         assert np.abs((U * S) @ Vh - A).max() < 1e-11 * Sref[0]
 
 
+def test_svd_dataflow_kernel_forced(gpu, monkeypatch):
+    """The dataflow sweep kernel (jacobi_flow_kernel; default only for batches with >= 296 block pairs per round) forced on
+    awkward batches (QTN_JACOBI_FLOW=2 is read per call): ragged column counts, transposed (m < n) and tall problems in
+    one batch, rank-deficient and graded inputs, truncation -- against LAPACK, same bars as the three-kernel path."""
+    import ctypes as C
+    from qaintensor_b200 import _lib
+    rng = np.random.default_rng(13)
+    monkeypatch.setenv("QTN_JACOBI_FLOW", "2")
+    shapes = [(200, 200), (150, 333), (333, 150), (97, 61), (256, 40), (40, 256), (129, 129)]
+    mats = [np.asfortranarray(crand(rng, *s)) for s in shapes]
+    mats[0][:, 100:] = mats[0][:, :100] @ crand(rng, 100, 100)                    # rank 100 of 200
+    mats[6] = np.asfortranarray(mats[6] * np.exp(-np.arange(129) / 6.0)[None, :])    # graded columns (1 .. 5e-10)
+    Us = [np.zeros((m, min(m, n)), complex, order="F") for m, n in shapes]
+    Ss = [np.zeros(min(m, n)) for m, n in shapes]
+    Vs = [np.zeros((min(m, n), n), complex, order="F") for m, n in shapes]
+    ks = (C.c_int64 * len(shapes))()
+    vp = lambda arrs: (C.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])  # noqa: E731
+    before = gpu.launch_count()
+    _lib.check(_lib.lib.qtn_svd_trunc_batched(len(shapes), vp(mats), _lib.arr_i64([s[0] for s in shapes]),
+                                              _lib.arr_i64([s[1] for s in shapes]), 1e-9, 120, vp(Us), vp(Ss), vp(Vs), ks))
+    flow_launches = gpu.launch_count() - before
+    for A, U, S, Vh, k in zip(mats, Us, Ss, Vs, ks):
+        Sref = osvd.svd(A)[1]
+        r = len(Sref)
+        assert np.abs(S - Sref).max() < 1e-10 * Sref[0]
+        assert k == osvd.truncation_rank(Sref, 1e-9, 120)
+        assert np.abs((U * S) @ Vh - A).max() < 1e-11 * Sref[0] * np.sqrt(r)
+        assert np.abs(U.conj().T @ U - np.eye(r)).max() < 1e-11 and np.abs(Vh @ Vh.conj().T - np.eye(r)).max() < 1e-11
+    # the same batch through the three-kernel path needs many more launches (3 per round)
+    monkeypatch.setenv("QTN_JACOBI_FLOW", "0")
+    before = gpu.launch_count()
+    _lib.check(_lib.lib.qtn_svd_trunc_batched(len(shapes), vp(mats), _lib.arr_i64([s[0] for s in shapes]),
+                                              _lib.arr_i64([s[1] for s in shapes]), 1e-9, 120, vp(Us), vp(Ss), vp(Vs), ks))
+    assert flow_launches < (gpu.launch_count() - before) // 4
+    for A, S in zip(mats, Ss):
+        assert np.abs(S - osvd.svd(A)[1]).max() < 1e-10 * np.linalg.norm(A, 2)
+
+
 def test_svd_1024_chi512_size(gpu):  # BASELINE config 4 SVD size, size-independent properties
     rng = np.random.default_rng(4)
     n = 1024

@@ -200,4 +200,60 @@ function permutedims_gpu(A::Array{ComplexF64}, perm)
     out
 end
 
+# ---- device-resident chains (round 2): one library call each, the running tensor never returns to the host --------
+
+# contract_svd_mps (src/mps.jl:190-201): fold of contract_svd over the tensors of an open-boundary MPS.  `tensors` are the
+# Arrays of mps.tensors in order; the caller keeps the periodic-boundary check of src/mps.jl:195.
+function contract_svd_mps(tensors::Vector{<:Array{ComplexF64}}; er=0.0)
+    n = length(tensors)
+    shape = n > 1 ? collect(size(tensors[1])[1:end-1]) : collect(size(tensors[1]))
+    for j in 2:n
+        sz = size(tensors[j])
+        append!(shape, j < n ? sz[2:end-1] : sz[2:end])
+    end
+    out = Array{ComplexF64}(undef, shape...)
+    ptrs = [pointer(t) for t in tensors]
+    GC.@preserve tensors check(ccall((:qtn_contract_svd_fold, LIB), Cint,
+        (Cint, Ptr{Ptr{Cvoid}}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Cdouble, Ptr{Cvoid}, Int64),
+        n, ptrs, Int64[length(t) for t in tensors], Int64[size(t, 1) for t in tensors],
+        Int64[size(t, ndims(t)) for t in tensors], Float64(er), out, length(out)))
+    out
+end
+
+# arithmetic of switch!(mps, i) (src/switch.jl:18-56): returns the new (T1, T2) data of the two neighbours
+function switch_adjacent(T1::Array{ComplexF64}, T2::Array{ComplexF64})
+    l1 = ndims(T1) == 3 ? size(T1, 1) : 0
+    r2 = ndims(T2) == 3 ? size(T2, 3) : 0
+    b = size(T1, ndims(T1))
+    bond = min(2 * max(l1, 1), 2 * max(r2, 1))
+    U = l1 == 0 ? Array{ComplexF64}(undef, 2, bond) : Array{ComplexF64}(undef, l1, 2, bond)
+    V = r2 == 0 ? Array{ComplexF64}(undef, bond, 2) : Array{ComplexF64}(undef, bond, 2, r2)
+    kb = Ref{Int64}(0)
+    check(ccall((:qtn_mps_switch_adjacent, LIB), Cint,
+        (Ptr{Cvoid}, Int64, Int64, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Ptr{Cvoid}, Ref{Int64}), T1, l1, b, T2, r2, U, V, kb))
+    U, V
+end
+
+# SVD chain of MPO(m) (src/mpo.jl:40-75; entry = :qtn_mpo_from_matrix) and decompose!(cg) (src/decompose.jl:17-48;
+# entry = :qtn_decompose): the M site tensors (2, 2, b1), (b_i, 2, 2, b_{i+1}), ..., (b_{M-1}, 2, 2)
+function operator_chain(m::Matrix{ComplexF64}, M::Integer; entry::Symbol=:qtn_mpo_from_matrix)
+    caps = Int64[]
+    b = 1
+    for i in 1:M-1
+        b = min(4b, 4^(M - i))
+        push!(caps, b)
+    end
+    shapes = [(2, 2, caps[1]); [(caps[i-1], 2, 2, caps[i]) for i in 2:M-1]; (caps[end], 2, 2)]
+    sites = [Array{ComplexF64}(undef, sh...) for sh in shapes]
+    ptrs = [pointer(t) for t in sites]
+    bonds = Vector{Int64}(undef, max(M - 1, 1))
+    GC.@preserve sites begin
+        rc = entry === :qtn_decompose ?
+            ccall((:qtn_decompose, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Ptr{Cvoid}}, Ptr{Int64}), m, M, ptrs, bonds) :
+            ccall((:qtn_mpo_from_matrix, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Ptr{Cvoid}}, Ptr{Int64}), m, M, ptrs, bonds)
+        check(rc)
+    end
+    sites
+end
+
 end # module

@@ -22,6 +22,12 @@
 namespace qtn {
 
 static const int64_t kMaxLo = 4096;
+// QTN_SPLIT_SMALL=0 disables the split-K of small-output mid-size steps (A/B runs)
+static bool split_small() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("QTN_SPLIT_SMALL"); v = e ? atoi(e) : 1; }
+    return v != 0;
+}
 static const int kNumSM = 148;
 
 OffTable make_table(std::vector<int64_t>& tables, const std::vector<int64_t>& extents,
@@ -1043,6 +1049,13 @@ int build_plan(int nt, const int32_t* ranks, const int64_t* const* dims, const i
                 int64_t want = (2 * kNumSM + tiles - 1) / tiles;
                 int64_t maxs = s.K / 64;
                 s.split_k = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(want, maxs), 1024));
+            } else if (tiles < kNumSM / 2 && s.K >= 32 && s.M * s.N <= 65536 && split_small()) {
+                // Mid-size steps of latency-bound plans (cfg 2: 256 x 128 x 128 on 8 tiles took 46 us = 16 dependent
+                // k-iterations of ~3 us on 8 of 148 SMs): one 8-deep k-iteration per CTA; the output is small, so the
+                // atomic epilogue (<= 64 K elements per split) is cheap.
+                int64_t want = (2 * kNumSM + tiles - 1) / tiles;
+                int64_t maxs = s.K / 8;
+                s.split_k = (int)std::max<int64_t>(1, std::min<int64_t>(want, maxs));
             }
             pl.flops += 8.0 * (double)s.M * (double)s.N * (double)s.K;
             pl.bytes += 16.0 * ((double)s.M * s.K + (double)s.K * s.N + (double)s.M * s.N);

@@ -47,7 +47,6 @@ constexpr int JPITCH = JP + 2;
 #define QTN_UPDATE_THREADS 128
 #endif
 constexpr int JTHREADS = QTN_UPDATE_THREADS;  // update kernel: small CTAs pack next to the eigensolve CTAs of other streams
-constexpr int ETHREADS = 128;    // eigensolve kernel: small CTAs that co-reside with the DMMA kernels of another stream
 constexpr int kInnerSweeps = 1;  // one eigen-sweep per Gram visit measured fastest (1: 108 ms, 2: 153, 3: 165, 6: 187 ms for 1024^2)
 
 struct SvdProblem {
@@ -338,7 +337,14 @@ jacobi_gram_cross_kernel(const SvdProblem* __restrict__ probs, int round, const 
 // Rotation of the Hermitian 2x2 pivot [[alpha, g], [conj(g), beta]]: J = [[c, s e^{i phi}], [-s e^{-i phi}, c]].
 struct JRot { double c, s; double2 ph; };
 
-__global__ void __launch_bounds__(ETHREADS, 8)
+// ET threads per CTA.  A tournament step is ~400 instructions per warp at ET = 128 (ncu, uncontended: 6.8 cycles per issued
+// instruction: FP64 chains, shared-memory round trips, two barriers), i.e. latency-bound with one warp per scheduler.
+// Launches that cannot fill the machine anyway (single matrices: cfg 5's truncating sweep, switch!, contract_svd) run
+// ET = 256 -- one 2x2 block of G and two rows of W per thread, two warps per scheduler: 5.12 -> 4.63 ms per sweep of a
+// 1536 x 1024 matrix (ET = 512 with the blocks split over two threads needs a third barrier per step: 4.89).  Batched
+// launches keep ET = 128: small CTAs that co-reside with the DMMA kernels of the other streams.
+template <int ET>
+__global__ void __launch_bounds__(ET, ET == 128 ? 8 : 4)
 jacobi_eig_kernel(const SvdProblem* __restrict__ probs, int round, double tol, int* __restrict__ rotated,
                   const double* __restrict__ fro2, int inner_sweeps, int* __restrict__ stat, int stamp, int S, int maxpairs,
                   const double2* __restrict__ Gpart, double2* __restrict__ Wbuf, int* __restrict__ pflag, int cross,
@@ -368,13 +374,13 @@ jacobi_eig_kernel(const SvdProblem* __restrict__ probs, int round, double tol, i
     __shared__ int s_cols[JP];
     if (tid < JP) s_cols[tid] = panel_col(tid, bi, bj, pr.n);
     if (tid == 0) { s_any = 0; s_rot = 0; }
-    for (int i = tid; i < JP * JPITCH; i += ETHREADS) W[i] = make_double2(0, 0);
+    for (int i = tid; i < JP * JPITCH; i += ET) W[i] = make_double2(0, 0);
     double2* DI = pr.D + (size_t)bi * (JB * JB);
     double2* DJ = pr.D + (size_t)bj * (JB * JB);
     {
         const double2* gp = Gpart + (size_t)((size_t)b * maxpairs + pair) * S * GP_ELEMS;
         const int nel = cross ? 4 * 64 : GP_ELEMS;
-        for (int e = tid; e < nel; e += ETHREADS) {
+        for (int e = tid; e < nel; e += ET) {
             double2 acc = make_double2(0, 0);
             for (int s = 0; s < S; ++s) {  // fixed order: deterministic
                 const double2 v = __ldcg(gp + (size_t)s * GP_ELEMS + e);
@@ -392,13 +398,13 @@ jacobi_eig_kernel(const SvdProblem* __restrict__ probs, int round, double tol, i
             G[(i * 8 + r8) * JPITCH + j * 8 + c8] = acc;
         }
         if (cross)  // diagonal blocks from the cache
-            for (int e = tid; e < 2 * JB * JB; e += ETHREADS) {
+            for (int e = tid; e < 2 * JB * JB; e += ET) {
                 const int h = e >> 8, r = (e >> 4) & 15, c = e & 15;
                 G[(h * JB + r) * JPITCH + h * JB + c] = __ldcg((h ? DJ : DI) + (e & 255));
             }
     }
     __syncthreads();
-    for (int e = tid; e < JP * JP; e += ETHREADS) {  // mirror the strictly-lower block triangle, W = I
+    for (int e = tid; e < JP * JP; e += ET) {  // mirror the strictly-lower block triangle, W = I
         const int r = e / JP, c = e % JP;
         if (cross ? (r >= JB && c < JB) : ((r >> 3) > (c >> 3))) { const double2 v = G[c * JPITCH + r]; G[r * JPITCH + c] = make_double2(v.x, -v.y); }
         if (r == c) W[r * JPITCH + c] = make_double2(1.0, 0.0);
@@ -457,8 +463,10 @@ jacobi_eig_kernel(const SvdProblem* __restrict__ probs, int round, double tol, i
                 const bool id2 = (c2 == 1.0 && s2 == 0.0);
                 const double2 ph2 = rph[k2];
                 const int p2 = s_pq[2 * k2], q2 = s_pq[2 * k2 + 1];
+                // ET = 128: two blocks per thread (k1, k1 + 8); 256: one block
+                constexpr int NH = ET == 128 ? 2 : 1;
 #pragma unroll
-                for (int hh = 0; hh < 2; ++hh) {
+                for (int hh = 0; hh < NH; ++hh) {
                     const int k1 = (tid >> 4) + 8 * hh;
                     const double c1 = rot[k1].x, s1 = rot[k1].y;
                     const bool id1 = (c1 == 1.0 && s1 == 0.0);
@@ -486,10 +494,10 @@ jacobi_eig_kernel(const SvdProblem* __restrict__ probs, int round, double tol, i
                     G[p1 * JPITCH + p2] = g00; G[p1 * JPITCH + q2] = g01;
                     G[q1 * JPITCH + p2] = g10; G[q1 * JPITCH + q2] = g11;
                 }
-                if (!id2) {  // W <- W J (columns), rows (tid >> 4) + 8 h for pair k2
+                if (!id2) {  // W <- W J (columns): rows (tid >> 4) + (ET / 16) h for pair k2
 #pragma unroll
-                    for (int h = 0; h < 4; ++h) {
-                        const int r = (tid >> 4) + 8 * h;
+                    for (int h = 0; h < 512 / ET; ++h) {
+                        const int r = (tid >> 4) + (ET / 16) * h;
                         const double2 xp = W[r * JPITCH + p2], xq = W[r * JPITCH + q2];
                         const double2 eq = mulphc(ph2, xq), ep = mulph(ph2, xp);
                         W[r * JPITCH + p2] = make_double2(c2 * xp.x - s2 * eq.x, c2 * xp.y - s2 * eq.y);
@@ -516,13 +524,13 @@ jacobi_eig_kernel(const SvdProblem* __restrict__ probs, int round, double tol, i
     // the block Grams after this visit: W^H G W restricted to each block (a full-Gram visit refreshes the cache even
     // when nothing was rotated)
     if (any || !cross)
-        for (int e = tid; e < 2 * JB * JB; e += ETHREADS) {
+        for (int e = tid; e < 2 * JB * JB; e += ET) {
             const int h = e >> 8, r = (e >> 4) & 15, c = e & 15;
             (h ? DJ : DI)[e & 255] = G[(h * JB + r) * JPITCH + h * JB + c];
         }
     if (!any) { trace_end(2, trace_t0); return; }
     double2* wout = Wbuf + (size_t)((size_t)b * maxpairs + pair) * (JP * JP);
-    for (int e = tid; e < JP * JP; e += ETHREADS) wout[e] = W[(e >> 5) * JPITCH + (e & 31)];
+    for (int e = tid; e < JP * JP; e += ET) wout[e] = W[(e >> 5) * JPITCH + (e & 31)];
     trace_end(2, trace_t0);
 }
 
@@ -1700,12 +1708,24 @@ int svd_batched_device(int batch, const SvdJob* jobs_in, double er, int64_t maxd
                 else
                     jacobi_gram_kernel<<<dim3((unsigned)(grp.maxpairs * grp.S), nb_), GRAM_THREADS, 0, g_sub[g]>>>(
                         dp + grp.b0, round, drot + grp.b0, grp.S, grp.maxpairs, (double2*)(base + grp.offG));
-                cudaStream_t se = eig_priority ? g_subE[g] : g_sub[g];
-                if (eig_priority) { CUDA_TRY(cudaEventRecord(g_evG[g], g_sub[g])); CUDA_TRY(cudaStreamWaitEvent(se, g_evG[g], 0)); }
-                jacobi_eig_kernel<<<dim3((unsigned)grp.maxpairs, nb_), ETHREADS, 0, se>>>(
+                // (a companion stream only pays when another sub-batch has tensor-pipe work to overlap with)
+                const bool eprio = eig_priority && ngroups > 1;
+                cudaStream_t se = eprio ? g_subE[g] : g_sub[g];
+                if (eprio) { CUDA_TRY(cudaEventRecord(g_evG[g], g_sub[g])); CUDA_TRY(cudaStreamWaitEvent(se, g_evG[g], 0)); }
+                // wide eigensolve CTAs for launches that cannot fill the machine anyway (QTN_JACOBI_ET = 128 / 256 forces one)
+                {
+                    static int et_env = -1;
+                    if (et_env < 0) { const char* e = getenv("QTN_JACOBI_ET"); et_env = e ? atoi(e) : 0; }
+                    const int et = et_env ? et_env : ((long)grp.maxpairs * nb_ <= 148 ? 256 : 128);
+                    const dim3 eg((unsigned)grp.maxpairs, nb_);
+                    if (et == 256) jacobi_eig_kernel<256><<<eg, 256, 0, se>>>(
                     dp + grp.b0, round, tol, drot + grp.b0, (const double*)dfro + grp.b0, inner, st_ptr, stamp, grp.S, grp.maxpairs,
                     (const double2*)(base + grp.offG), (double2*)(base + grp.offW), (int*)(base + grp.offF), cross, dact + grp.b0);
-                if (eig_priority) { CUDA_TRY(cudaEventRecord(g_evE[g], se)); CUDA_TRY(cudaStreamWaitEvent(g_sub[g], g_evE[g], 0)); }
+                    else jacobi_eig_kernel<128><<<eg, 128, 0, se>>>(
+                    dp + grp.b0, round, tol, drot + grp.b0, (const double*)dfro + grp.b0, inner, st_ptr, stamp, grp.S, grp.maxpairs,
+                    (const double2*)(base + grp.offG), (double2*)(base + grp.offW), (int*)(base + grp.offF), cross, dact + grp.b0);
+                }
+                if (eprio) { CUDA_TRY(cudaEventRecord(g_evE[g], se)); CUDA_TRY(cudaStreamWaitEvent(g_sub[g], g_evE[g], 0)); }
                 jacobi_update_kernel<<<dim3((unsigned)(grp.maxpairs * grp.SU), nb_), JTHREADS, 0, g_sub[g]>>>(
                     dp + grp.b0, round, drot + grp.b0, grp.SU, grp.maxpairs, (const double2*)(base + grp.offW), (const int*)(base + grp.offF));
                 count_launch(3);

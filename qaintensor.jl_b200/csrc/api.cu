@@ -317,6 +317,9 @@ int zgemm_dense(char opa, char opb, int64_t m, int64_t n, int64_t k, const void*
     g.conj_b = opb == 'C';
     g.M = m; g.N = n; g.K = k;
     g.mode = accumulate ? 1 : 0;
+    static int pdl = -1;   // QTN_GEMM_PDL=0: plain launches (A/B runs)
+    if (pdl < 0) { const char* e = getenv("QTN_GEMM_PDL"); pdl = e ? atoi(e) : 1; }
+    g.pdl = pdl;
     return launch_gemm(g, n <= 16 ? 1 : 0, 1, stream());
 }
 }  // namespace qtn

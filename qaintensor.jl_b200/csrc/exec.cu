@@ -124,7 +124,21 @@ static int launch_gemm_t(GemmArgs& g, int split_k, cudaStream_t st) {
     g.k_per_split = kps;
     int sy = (int)((g.K + kps - 1) / kps);
     dim3 grid((unsigned)(tm * tn), (unsigned)sy, 1);
-    kern<<<grid, NT, smem, st>>>(g);
+    if (g.pdl) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = grid;
+        cfg.blockDim = dim3(NT);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, g));
+    } else {
+        kern<<<grid, NT, smem, st>>>(g);
+    }
     CUDA_TRY(cudaGetLastError());
     count_launch(1);
     return QTN_OK;

@@ -49,6 +49,7 @@ struct GemmArgs {
     int conj_a, conj_b;  // conjugate the operand on the way into the tensor pipe
     int use_3m;          // contraction plans may use the 3-multiplication complex product (see zgemm_gather_kernel)
     int a_kmajor, b_kmajor;  // operand's contiguous direction is k: consecutive threads of a stage load take consecutive k
+    int pdl;                 // launched with programmatic stream serialization (chains of small dense GEMMs: orth.cu, mps.cu)
 };
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool valid) {
@@ -122,6 +123,8 @@ zgemm_gather_kernel(const __grid_constant__ GemmArgs g) {
     constexpr int A_PER = BM / TPK;
     constexpr int B_PER = (BN + TPK - 1) / TPK;
 
+    // programmatic dependent launch: nothing of the predecessor is touched before this (no-op without the launch attribute)
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double2* sA = reinterpret_cast<double2*>(smem_raw);  // [STAGES][BK][PA]
     double2* sB = sA + STAGES * BK * PA;                 // [STAGES][BK][PB]
@@ -269,6 +272,7 @@ zgemm_gather_kernel(const __grid_constant__ GemmArgs g) {
         }
     }
     cp_async_wait<0>();
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the dependent grid may fill the SMs this grid's tail frees
 
     // epilogue: scatter the accumulators through the C offset tables
     i64 crow[MI];

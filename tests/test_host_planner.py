@@ -321,3 +321,23 @@ def test_order_search_random_general_networks_vs_oracle(q):
         f2, _, _, _ = oplan.tree_cost(nodes2, steps2, dims, S)
         nsl = int(np.prod([dims[l] for l in S])) if S else 1
         assert (info2["flops_per_slice"], info2["nslices"]) == (f2, float(nsl))
+
+
+def test_split_k_rules_of_latency_bound_plans(q):
+    """Kernel selection of the planner (device tuning, not part of the reference's result): split-K only where the tile
+    grid cannot fill the 148 SMs -- K >= 256 steps, and small-output (<= 64 K elements) K >= 32 steps down to one 8-deep
+    k-iteration per CTA; flops / bytes / step shapes of the plan are unaffected (they are compared with the oracle above)."""
+    net, _, _ = q.circuits.cfg2_network()
+    q.optimize_contraction_order(net)
+    il = q.contract_rep(net)
+    plan = q.ContractionPlan([t.data.shape for t in net.tensors], il, None, [])
+    steps = plan.steps()
+    by_shape = {(m, n, k): fl >> 8 for m, n, k, fl in steps if (fl >> 1) & 7 == 0}
+    assert by_shape[(256, 128, 128)] == 16          # 8 tiles, K = 128 -> one k-iteration per CTA
+    assert by_shape[(256, 256, 2048)] == 19         # 16 tiles -> 2 * 148 / 16
+    assert by_shape[(4096, 128, 128)] == 1          # 128 tiles and a 512 K-element output: atomics would cost more
+    assert by_shape[(1024, 512, 32)] == 1
+    for m, n, k, fl in steps:
+        split = fl >> 8
+        assert split >= 1 and (split == 1 or k // split >= 8)
+    plan.close()

@@ -104,3 +104,27 @@ def cfg3_network(rows=6, cols=6, cycles=16, seed=None):
     gates = rqc2d_gates(rows, cols, cycles, rng)
     bits = rng.integers(0, 2, size=rows * cols)
     return amplitude_network(rows * cols, gates, bits), gates, bits
+
+
+def notebook_expectation_network(N=20, seed=None, is_decompose=False, cgc=None):
+    """``expectation_value(cgc)`` of examples/expectation_value_optimization_example.ipynb (cells 2-12): the closed
+    network <random bond-2 MPS| circuit |same MPS> behind the reference's only published timings.  Restated from the
+    notebook's helper cell: ``ClosedMPS`` with *reversed* open legs, ``crand`` uniform in the unit square, the bra =
+    the ket's tensors pushed in reverse site order, bond contractions = the ket's shifted by the tensor count before
+    the push.  Same seeded stream as the product's generator (circuits.py of the package)."""
+    rng = np.random.default_rng(cfg_seed(6) if seed is None else seed)
+
+    def crand(*dims):
+        return rng.random(dims) + 1j * rng.random(dims)
+    t0 = [Tensor(crand(2, 2))] + [Tensor(crand(2, 2, 2)) for _ in range(2, N)] + [Tensor(crand(2, 2))]
+    cons0 = [Summation([(1, 2), (2, 1)])] + [Summation([(i, 3), (i + 1, 1)]) for i in range(2, N)]
+    open0 = list(reversed([(1, 1)] + [(i, 2) for i in range(2, N + 1)]))
+    net = Network(list(t0), list(cons0), list(open0))
+    tensor_circuit(net, qft_circuit(N) if cgc is None else cgc, is_decompose=is_decompose)
+    step = len(net.tensors)
+    net.contractions = net.contractions + [Summation([(t + step, l) for (t, l) in s.idx]) for s in cons0]
+    for i in range(1, N + 1):
+        net.tensors.append(t0[N - i])
+        net.contractions.append(Summation([net.openidx[-1], (len(net.tensors), open0[N - i][1])]))
+        net.openidx.pop()
+    return net

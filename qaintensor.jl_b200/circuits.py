@@ -75,3 +75,31 @@ def cfg3_network(rows=6, cols=6, cycles=16, seed=None):
     gates = rqc2d_gates(rows, cols, cycles, rng)
     bits = rng.integers(0, 2, size=rows * cols)
     return amplitude_network(rows * cols, gates, bits), gates, bits
+
+
+def notebook_expectation_network(N=20, seed=None, is_decompose=False, cgc=None):
+    """The network the reference's only published timings are taken on
+    (``examples/expectation_value_optimization_example.ipynb``, cells 2-12):
+    <random bond-2 MPS| circuit |same MPS> with no open legs, circuit = ``qft_circuit(N)`` unless given.
+
+    Follows the notebook's own helper cell, not src/mps.jl: its ``ClosedMPS`` lists the open legs in reverse
+    (``reverse([1 => 1; [i => 2 for i in 2:l]])``), ``crand`` is uniform on [0, 1) + i [0, 1), the bra re-uses the
+    ket's tensors (no conjugation) appended in reverse site order, and the bra's bond contractions are the ket's
+    shifted by the tensor count *before* the bra tensors are pushed -- so they pair legs of the reversed list
+    (all extents are 2, so the network is valid; it is reproduced as published, not corrected)."""
+    rng = np.random.default_rng(cfg_seed(6) if seed is None else seed)
+
+    def crand(*dims):
+        return np.asfortranarray(rng.random(dims) + 1j * rng.random(dims))
+    t0 = [Tensor(crand(2, 2))] + [Tensor(crand(2, 2, 2)) for _ in range(2, N)] + [Tensor(crand(2, 2))]
+    cons0 = [Summation([(1, 2), (2, 1)])] + [Summation([(i, 3), (i + 1, 1)]) for i in range(2, N)]
+    open0 = list(reversed([(1, 1)] + [(i, 2) for i in range(2, N + 1)]))
+    net = GeneralTensorNetwork(list(t0), list(cons0), list(open0))
+    tensor_circuit(net, qft_circuit(N) if cgc is None else cgc, is_decompose=is_decompose)
+    step = len(net.tensors)
+    net.contractions = net.contractions + [Summation([(t + step, l) for (t, l) in s.idx]) for s in cons0]
+    for i in range(1, N + 1):
+        net.tensors.append(t0[N - i])
+        net.contractions.append(Summation([net.openidx[-1], (len(net.tensors), open0[N - i][1])]))
+        net.openidx.pop()
+    return net

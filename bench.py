@@ -549,7 +549,7 @@ def run_nb(args, q, _lib, torch, ext, variants=("plain", "decomposed"), with_cpu
             "gpu_launches": int(round(head["gpu_launches_per_contract"] * steps)),
             "roofline": {"bound": "hbm", "achieved": d["gbs_algorithmic"], "peak": hbm_peak, "unit": "GB/s", "frac": d["gbs_algorithmic"] / hbm_peak,
                          "traffic": None, "kernel": "zgemm_gather_kernel (skinny tiles)",
-                         "note": "whole default-order contraction (259 steps, 94 % of them K = 4: 1.9 flop/B): algorithmic bytes sum 16(MK+KN+MN) "
+                         "note": "whole default-order contraction (259 steps, 94 %% of them K = 4: 1.9 flop/B): algorithmic bytes sum 16(MK+KN+MN) "
                                  "= %.3g B / device time; the intermediates (<= 16 MB) live in L2, so this is a fraction of the HBM peak the "
                                  "path does not need to touch; the optimized order is launch-latency-bound (%.2f ms for %d launches)"
                                  % (d["bytes"], head["ms_device"], int(head["gpu_launches_per_contract"]))},

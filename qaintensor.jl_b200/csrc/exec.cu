@@ -287,7 +287,10 @@ struct DevPlan {
     bool invariants_done = false;
     int graph_launches = 0;
     std::vector<cudaEvent_t> capture_events;
-    char* host_out = nullptr;  // result buffer of the host-buffer entry points
+    char* host_out = nullptr;  // result buffer of the host-buffer entry points (pool block)
+    char* meta = nullptr;      // one block: offset tables + slice bookkeeping (tables .. stride point into it)
+    size_t meta_bytes = 0;
+    bool inputs_pooled = false, arena_pooled = false, meta_pooled = false;
 };
 
 static TabArg tab_arg(const DevPlan* d, const OffTable& t) {
@@ -300,6 +303,36 @@ static TabArg tab_arg(const DevPlan* d, const OffTable& t) {
     return a;
 }
 
+// Device buffers of a plan.  Up to kPoolMaxBlock they come from the workspace pool (pool.cu), so a one-shot
+// contract(net) -- create, upload, execute, destroy -- pays no cudaMalloc / cudaFree once the pool is warm; the large
+// arenas of sliced contractions are allocated directly and returned to the driver with the plan.
+static const size_t kPoolMaxBlock = (size_t)512 << 20;
+
+static void* dev_alloc(size_t bytes, bool* pooled) {
+    bytes = std::max<size_t>(bytes, 256);
+    if (bytes <= kPoolMaxBlock) { *pooled = true; return pool_alloc(bytes); }
+    *pooled = false;
+    void* ptr = nullptr;
+    cudaError_t e = cudaMalloc(&ptr, bytes);
+    if (e != cudaSuccess) {   // the pool's idle blocks may be what is in the way
+        cudaGetLastError();
+        pool_trim();
+        e = cudaMalloc(&ptr, bytes);
+    }
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        fail(e == cudaErrorMemoryAllocation ? QTN_ENOMEM : QTN_ECUDA, "cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+        return nullptr;
+    }
+    return ptr;
+}
+
+static void dev_free(void* ptr, bool pooled) {
+    if (!ptr) return;
+    if (pooled) pool_free(ptr);
+    else cudaFree(ptr);
+}
+
 int plan_device_init(Plan* p) {
     int rc = device_ready();
     if (rc) return rc;
@@ -309,44 +342,47 @@ int plan_device_init(Plan* p) {
     DevPlan* d = new DevPlan();
     d->es = p->dtype == QTN_C64 ? 8 : 16;
     p->dev = d;
+    // every failure releases the half-built device state (p->dev must never survive without its staging buffer:
+    // plan_upload would take the "already initialised" exit and write through a null pointer)
     auto guard_fail = [&](int code) { plan_device_free(p); return code; };
-    cudaError_t e;
-#define ALLOC(ptr, bytes)                                                                     \
-    if ((e = cudaMalloc((void**)&(ptr), std::max<size_t>((size_t)(bytes), 256))) != cudaSuccess) \
-        return guard_fail(fail(e == cudaErrorMemoryAllocation ? QTN_ENOMEM : QTN_ECUDA,          \
-                               "cudaMalloc(%zu bytes) failed: %s", (size_t)(bytes), cudaGetErrorString(e)));
-    ALLOC(d->inputs, (size_t)p->input_elems * d->es);
-    ALLOC(d->arena, (size_t)p->arena_elems * d->es);
-    ALLOC(d->tables, p->tables.size() * 8);
-    ALLOC(d->sid, 8);
-    ALLOC(d->soff, (size_t)p->nt * 8);
-    ALLOC(d->slice_dims, p->slice_dims.size() * 8 + 8);
+    if (!(d->inputs = (char*)dev_alloc((size_t)p->input_elems * d->es, &d->inputs_pooled))) return guard_fail(QTN_ENOMEM);
+    if (!(d->arena = (char*)dev_alloc((size_t)p->arena_elems * d->es, &d->arena_pooled))) return guard_fail(QTN_ENOMEM);
+    // offset tables and the slice bookkeeping: ONE device block, ONE host image, ONE copy
     std::vector<int> first(p->nt + 1, 0), pos;
     std::vector<i64> stride;
     for (int t = 0; t < p->nt; ++t) {
         for (auto& ps : p->nodes[t].slice_strides) { pos.push_back(ps.first); stride.push_back(ps.second); }
         first[t + 1] = (int)pos.size();
     }
-    ALLOC(d->first, first.size() * 4);
-    ALLOC(d->pos, pos.size() * 4 + 4);
-    ALLOC(d->stride, stride.size() * 8 + 8);
-#undef ALLOC
-    // every failure below releases the half-built device state too (p->dev must never survive without its staging
-    // buffer: plan_upload would take the "already initialised" exit and write through a null pointer)
-#define INIT_TRY(expr)                                                                                        \
-    if ((e = (expr)) != cudaSuccess)                                                                          \
-        return guard_fail(fail(QTN_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e), __FILE__, __LINE__));
-    INIT_TRY(cudaMemcpy(d->tables, p->tables.data(), p->tables.size() * 8, cudaMemcpyHostToDevice));
-    INIT_TRY(cudaMemcpy(d->first, first.data(), first.size() * 4, cudaMemcpyHostToDevice));
-    if (!pos.empty()) {
-        INIT_TRY(cudaMemcpy(d->pos, pos.data(), pos.size() * 4, cudaMemcpyHostToDevice));
-        INIT_TRY(cudaMemcpy(d->stride, stride.data(), stride.size() * 8, cudaMemcpyHostToDevice));
-        INIT_TRY(cudaMemcpy(d->slice_dims, p->slice_dims.data(), p->slice_dims.size() * 8, cudaMemcpyHostToDevice));
-    }
-    INIT_TRY(cudaMemset(d->soff, 0, (size_t)p->nt * 8));
+    size_t off = 0;
+    auto section = [&](size_t bytes) { size_t o = off; off += (std::max<size_t>(bytes, 8) + 255) / 256 * 256; return o; };
+    const size_t o_tables = section(p->tables.size() * 8), o_sid = section(8), o_soff = section((size_t)p->nt * 8),
+                 o_sdims = section(p->slice_dims.size() * 8 + 8), o_first = section(first.size() * 4),
+                 o_pos = section(pos.size() * 4 + 4), o_stride = section(stride.size() * 8 + 8);
+    d->meta_bytes = off;
+    if (!(d->meta = (char*)dev_alloc(off, &d->meta_pooled))) return guard_fail(QTN_ENOMEM);
+    d->tables = (i64*)(d->meta + o_tables);
+    d->sid = (i64*)(d->meta + o_sid);
+    d->soff = (i64*)(d->meta + o_soff);
+    d->slice_dims = (i64*)(d->meta + o_sdims);
+    d->first = (int*)(d->meta + o_first);
+    d->pos = (int*)(d->meta + o_pos);
+    d->stride = (i64*)(d->meta + o_stride);
     d->h_stage_bytes = (size_t)p->input_elems * d->es;
-    INIT_TRY(cudaMallocHost(&d->h_stage, std::max<size_t>(d->h_stage_bytes, 256)));
-#undef INIT_TRY
+    // the page-locked block holds the meta image first (copied once, below) and is then the input staging buffer
+    if (!(d->h_stage = pinned_alloc(std::max(std::max<size_t>(d->h_stage_bytes, off), (size_t)256)))) return guard_fail(QTN_ENOMEM);
+    char* img = (char*)d->h_stage;
+    memset(img, 0, off);   // sid, soff start at zero
+    memcpy(img + o_tables, p->tables.data(), p->tables.size() * 8);
+    memcpy(img + o_first, first.data(), first.size() * 4);
+    if (!pos.empty()) {
+        memcpy(img + o_pos, pos.data(), pos.size() * 4);
+        memcpy(img + o_stride, stride.data(), stride.size() * 8);
+        memcpy(img + o_sdims, p->slice_dims.data(), p->slice_dims.size() * 8);
+    }
+    cudaError_t e = cudaMemcpyAsync(d->meta, img, off, cudaMemcpyHostToDevice, g_stream);
+    if (e != cudaSuccess) return guard_fail(fail(QTN_ECUDA, "plan table upload failed: %s", cudaGetErrorString(e)));
+    // plan_upload synchronises the stream before it re-uses the staging block for the tensors
     return QTN_OK;
 }
 
@@ -355,10 +391,12 @@ void plan_device_free(Plan* p) {
     if (!d) return;
     if (g_stream) cudaStreamSynchronize(g_stream);
     if (d->graph) cudaGraphExecDestroy(d->graph);
-    if (d->host_out) cudaFree(d->host_out);
-    cudaFree(d->inputs); cudaFree(d->arena); cudaFree(d->tables); cudaFree(d->sid); cudaFree(d->soff);
-    cudaFree(d->slice_dims); cudaFree(d->first); cudaFree(d->pos); cudaFree(d->stride);
-    if (d->h_stage) cudaFreeHost(d->h_stage);
+    for (cudaEvent_t ev : d->capture_events) cudaEventDestroy(ev);
+    dev_free(d->host_out, true);
+    dev_free(d->inputs, d->inputs_pooled);
+    dev_free(d->arena, d->arena_pooled);
+    dev_free(d->meta, d->meta_pooled);
+    pinned_free(d->h_stage);
     delete d;
     p->dev = nullptr;
 }
@@ -616,7 +654,7 @@ int plan_result_buffer(Plan* p, void** out) {
     DevPlan* d = (DevPlan*)p->dev;
     if (!d) return fail(QTN_EINVAL, "plan has no device state");
     const size_t bytes = std::max<size_t>((size_t)p->out_numel * d->es, 256);
-    if (!d->host_out) CUDA_TRY(cudaMalloc((void**)&d->host_out, bytes));
+    if (!d->host_out && !(d->host_out = (char*)pool_alloc(bytes))) return QTN_ENOMEM;
     CUDA_TRY(cudaMemsetAsync(d->host_out, 0, bytes, g_stream));
     *out = d->host_out;
     return QTN_OK;

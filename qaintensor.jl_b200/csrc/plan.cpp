@@ -40,21 +40,29 @@ OffTable make_table(std::vector<int64_t>& tables, const std::vector<int64_t>& ex
     t.L = 1;
     while (j < nm && t.L * extents[j] <= max_lo) { t.L *= extents[j]; ++j; }
     if (j == 0 && nm > 0) { t.L = extents[0]; j = 1; }
+    // mixed-radix enumeration by doubling: the table of modes 0..q is e_q shifted copies of the table of modes 0..q-1
+    // (no division / modulo per entry: this loop was 40 ms of a 60 ms one-shot contract on 2^20-row intermediates)
+    auto enumerate = [&](int64_t base, size_t q0, size_t q1) {
+        int64_t len = 1;
+        if ((size_t)base >= tables.size()) return;   // empty section
+        tables[base] = 0;
+        for (size_t q = q0; q < q1; ++q) {
+            for (int64_t d = 1; d < extents[q]; ++d) {
+                const int64_t add = d * strides[q];
+                int64_t* dst = tables.data() + base + d * len;
+                const int64_t* src = tables.data() + base;
+                for (int64_t i = 0; i < len; ++i) dst[i] = src[i] + add;
+            }
+            len *= extents[q];
+        }
+    };
     t.lo = (int64_t)tables.size();
     tables.resize(tables.size() + t.L, 0);
-    for (int64_t i = 0; i < t.L; ++i) {
-        int64_t r = i, off = 0;
-        for (size_t q = 0; q < j; ++q) { off += (r % extents[q]) * strides[q]; r /= extents[q]; }
-        tables[t.lo + i] = off;
-    }
+    enumerate(t.lo, 0, j);
     int64_t nh = t.n / t.L;
     t.hi = (int64_t)tables.size();
     tables.resize(tables.size() + nh, 0);
-    for (int64_t i = 0; i < nh; ++i) {
-        int64_t r = i, off = 0;
-        for (size_t q = j; q < nm; ++q) { off += (r % extents[q]) * strides[q]; r /= extents[q]; }
-        tables[t.hi + i] = off;
-    }
+    enumerate(t.hi, j, nm);
     return t;
 }
 

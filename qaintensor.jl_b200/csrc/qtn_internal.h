@@ -148,6 +148,8 @@ int orth_cholqr2(void* dev_m, const void* dev_keep, void* dev_c, int64_t m, int6
 void* pool_alloc(size_t bytes);   // nullptr (and the error message set) when the device is out of memory
 void pool_free(void* p);          // back to the cache; never cudaFree
 void pool_trim();                 // release every cached block to the driver
+void* pinned_alloc(size_t bytes); // page-locked host staging buffer from the same kind of cache
+void pinned_free(void* p);
 void pool_stats(int64_t out[4]);  // cudaMalloc calls, cache hits, bytes owned, blocks handed out
 // RAII block of the pool.
 struct PoolBuf {

@@ -4,6 +4,8 @@
 
 #include <cstring>
 #include <memory>
+#include <vector>
+#include <cstdlib>
 
 #include "kernels.cuh"
 #include "qtn_internal.h"
@@ -32,6 +34,38 @@ using namespace qtn;
 struct qtn_plan {
     Plan* p;
 };
+
+// ---- plan cache of the one-shot entry point --------------------------------------------------------------------
+// `contract(net)` is called again and again on networks of the same structure (parameter sweeps, the reference's own
+// `@benchmark contract($T)` loop): the key is the complete structural description (dtype, ranks, dims, labels, order),
+// compared exactly, so a hit is the same plan by construction.  A hit skips the planner and the table build, and
+// from its second use the plan replays its captured CUDA graph.  Small plans only (<= 256 MB of device memory), at
+// most kPlanCacheMax of them, least-recently-used eviction; QTN_PLAN_CACHE=0 disables it; qtn_shutdown / a device
+// switch clears it.
+namespace {
+struct CachedPlan {
+    std::vector<int64_t> key;
+    std::unique_ptr<Plan> plan;
+    uint64_t stamp = 0;
+};
+std::vector<CachedPlan> g_plan_cache;
+uint64_t g_plan_stamp = 0;
+const size_t kPlanCacheMax = 4;
+const size_t kPlanCacheMaxBytes = (size_t)256 << 20;
+
+bool plan_cache_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("QTN_PLAN_CACHE"); v = e ? atoi(e) : 1; }
+    return v != 0;
+}
+}  // namespace
+
+namespace qtn {
+void plan_cache_clear() {
+    for (auto& c : g_plan_cache) plan_device_free(c.plan.get());
+    g_plan_cache.clear();
+}
+}  // namespace qtn
 
 extern "C" {
 
@@ -160,14 +194,49 @@ int qtn_contract(int32_t nt, const void* const* host_data, const int32_t* ranks,
     if (!host_data || !host_out) return fail(QTN_EINVAL, "qtn_contract: null argument");
     int rc = device_ready();
     if (rc) return rc;
+    auto report = [&](const Plan* p) {
+        if (out_rank) *out_rank = (int32_t)p->out_dims.size();
+        if (out_dims) for (size_t i = 0; i < p->out_dims.size() && i < 64; ++i) out_dims[i] = p->out_dims[i];
+    };
+    std::vector<int64_t> key;
+    const bool cacheable = plan_cache_enabled() && nt > 0 && ranks && dims && labels;
+    if (cacheable) {
+        key.push_back(dtype);
+        key.push_back(nt);
+        key.push_back(order ? norder : -1);
+        for (int i = 0; i < nt; ++i) {
+            key.push_back(ranks[i]);
+            if (ranks[i] < 0 || ranks[i] > 60 || (ranks[i] > 0 && (!dims[i] || !labels[i]))) { key.clear(); break; }  // the planner reports it
+            for (int j = 0; j < ranks[i]; ++j) { key.push_back(dims[i][j]); key.push_back(labels[i][j]); }
+        }
+        if (!key.empty() && order && norder > 0) for (int i = 0; i < norder; ++i) key.push_back(order[i]);
+        for (auto& c : g_plan_cache)
+            if (!key.empty() && c.key == key) {
+                c.stamp = ++g_plan_stamp;
+                rc = exec_host(c.plan.get(), host_data, 0, 1, host_out, false);
+                if (!rc) report(c.plan.get());
+                return rc;
+            }
+    }
     Plan* p = nullptr;
     rc = build_plan(nt, ranks, dims, labels, order, norder, nullptr, 0, dtype, &p);
     if (rc) return rc;
     std::unique_ptr<Plan> holder(p);
     rc = exec_host(p, host_data, 0, 1, host_out, false);
-    if (!rc) {
-        if (out_rank) *out_rank = (int32_t)p->out_dims.size();
-        if (out_dims) for (size_t i = 0; i < p->out_dims.size() && i < 64; ++i) out_dims[i] = p->out_dims[i];
+    if (!rc) report(p);
+    if (!rc && cacheable && !key.empty() && plan_device_bytes(p) <= kPlanCacheMaxBytes) {
+        if (g_plan_cache.size() >= kPlanCacheMax) {
+            size_t lru = 0;
+            for (size_t i = 1; i < g_plan_cache.size(); ++i) if (g_plan_cache[i].stamp < g_plan_cache[lru].stamp) lru = i;
+            plan_device_free(g_plan_cache[lru].plan.get());
+            g_plan_cache.erase(g_plan_cache.begin() + (long)lru);
+        }
+        CachedPlan c;
+        c.key = std::move(key);
+        c.plan = std::move(holder);
+        c.stamp = ++g_plan_stamp;
+        g_plan_cache.push_back(std::move(c));
+        return rc;
     }
     plan_device_free(p);
     return rc;

@@ -80,7 +80,7 @@ int device_init(int device) {
         return fail(QTN_ENODEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
     CUDA_TRY(cudaSetDevice(device));
     if (g_inited && g_device == device) return QTN_OK;
-    if (g_stream) { cudaStreamSynchronize(g_stream); pool_trim(); cudaStreamDestroy(g_stream); g_stream = nullptr; }  // cached workspace belongs to the old device
+    if (g_stream) { cudaStreamSynchronize(g_stream); plan_cache_clear(); pool_trim(); cudaStreamDestroy(g_stream); g_stream = nullptr; }  // cached plans / workspace belong to the old device
     CUDA_TRY(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
     g_device = device;
     g_inited = true;
@@ -88,7 +88,7 @@ int device_init(int device) {
 }
 
 int device_shutdown() {
-    if (g_stream) { cudaStreamSynchronize(g_stream); pool_trim(); cudaStreamDestroy(g_stream); g_stream = nullptr; }
+    if (g_stream) { cudaStreamSynchronize(g_stream); plan_cache_clear(); pool_trim(); cudaStreamDestroy(g_stream); g_stream = nullptr; }
     g_inited = false;
     g_device = -1;
     return QTN_OK;
@@ -333,6 +333,11 @@ static void dev_free(void* ptr, bool pooled) {
     else cudaFree(ptr);
 }
 
+size_t plan_device_bytes(const Plan* p) {
+    const size_t es = p->dtype == QTN_C64 ? 8 : 16;
+    return ((size_t)p->input_elems + (size_t)p->arena_elems) * es + p->tables.size() * 8;
+}
+
 int plan_device_init(Plan* p) {
     int rc = device_ready();
     if (rc) return rc;
@@ -372,7 +377,7 @@ int plan_device_init(Plan* p) {
     // the page-locked block holds the meta image first (copied once, below) and is then the input staging buffer
     if (!(d->h_stage = pinned_alloc(std::max(std::max<size_t>(d->h_stage_bytes, off), (size_t)256)))) return guard_fail(QTN_ENOMEM);
     char* img = (char*)d->h_stage;
-    memset(img, 0, off);   // sid, soff start at zero
+    memset(img + o_sid, 0, off - o_sid);   // sid, soff start at zero (the table section is overwritten in full)
     memcpy(img + o_tables, p->tables.data(), p->tables.size() * 8);
     memcpy(img + o_first, first.data(), first.size() * 4);
     if (!pos.empty()) {

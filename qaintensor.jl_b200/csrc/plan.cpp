@@ -76,6 +76,22 @@ int materialize_tables(Plan* p) {
     }
     if (total > 1.5e9) return fail(QTN_ENOMEM, "plan needs ~%.3g offset-table entries; slice the contraction", total);
     p->tables.clear();
+    {   // one allocation for all tables (growing the vector table by table cost more than filling it)
+        size_t entries = 1;
+        auto size_of = [&](const OffTable& t) {
+            if (t.spec < 0) return;
+            const TableSpec& sp = p->table_specs[t.spec];
+            const int64_t max_lo = std::max<int64_t>(kMaxLo, (int64_t)std::sqrt((double)t.n));
+            int64_t L = 1, n = 1;
+            size_t j = 0;
+            for (auto e : sp.extents) n *= e;
+            while (j < sp.extents.size() && L * sp.extents[j] <= max_lo) { L *= sp.extents[j]; ++j; }
+            if (j == 0 && !sp.extents.empty()) L = sp.extents[0];
+            entries += (size_t)L + (size_t)(L ? n / L : 0);
+        };
+        for (auto& s : p->steps) { size_of(s.a_row); size_of(s.a_k); size_of(s.b_k); size_of(s.b_col); size_of(s.c_row); size_of(s.c_col); }
+        p->tables.reserve(entries);
+    }
     p->tables.push_back(0);
     auto fill = [&](OffTable& t) {
         if (t.spec < 0) return;

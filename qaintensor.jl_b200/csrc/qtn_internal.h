@@ -174,5 +174,7 @@ int plan_upload(Plan* p, const void* const* host_data);
 int plan_execute(Plan* p, int64_t s0, int64_t s1, void* dev_out);
 int plan_time_steps(Plan* p, int64_t sid, float* ms);
 int plan_result_buffer(Plan* p, void** out);
+size_t plan_device_bytes(const Plan* p);   // device memory a plan will hold once uploaded (inputs + arena + tables)
+void plan_cache_clear();                  // api.cu: drops the plans qtn_contract keeps for repeated identical networks
 
 }  // namespace qtn

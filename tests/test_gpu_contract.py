@@ -365,7 +365,13 @@ def test_one_shot_plan_cache_new_data_and_eviction(gpu):
     net.contractions[1] = q.Summation([b.idx[0], a.idx[1]])
     assert rel_err(q.contract(net), oc.contract(to_oracle(net))) < TOL
     # more distinct structures than cache slots, each contracted twice (second pass hits or re-plans after eviction)
-    nets = [random_TN(q, 6 + k, 9 + k, np.random.default_rng(100 + k)) for k in range(7)]
+    nets = []
+    seed = 100
+    while len(nets) < 7:   # distinct sizes; skip draws that leave a tensor without legs (not a valid network)
+        n = random_TN(q, 7 + len(nets), 16 + 2 * len(nets), np.random.default_rng(seed))
+        seed += 1
+        if all(t.data.shape != (1,) for t in n.tensors):
+            nets.append(n)
     wants = [oc.contract(to_oracle(n)) for n in nets]
     for _ in range(2):
         for n, w in zip(nets, wants):

@@ -366,7 +366,7 @@ __global__ void __launch_bounds__(ET, ET == 128 ? 8 : 4)
 jacobi_eig_kernel(const SvdProblem* __restrict__ probs, int round, double tol, int* __restrict__ rotated,
                   const double* __restrict__ fro2, int inner_sweeps, int* __restrict__ stat, int stamp, int S, int maxpairs,
                   const double2* __restrict__ Gpart, double2* __restrict__ Wbuf, int* __restrict__ pflag, int cross,
-                  int* __restrict__ nactive) {
+                  int* __restrict__ nactive, int xrot) {
     pdl_wait();
     const int b = blockIdx.y, pair = blockIdx.x, tid = threadIdx.x;
     int* flag = pflag + (size_t)b * maxpairs + pair;
@@ -434,10 +434,16 @@ jacobi_eig_kernel(const SvdProblem* __restrict__ probs, int round, double tol, i
     for (int sweep = 0; sweep < inner_sweeps; ++sweep) {
         if (tid == 0) s_sweep_any = 0;
         __syncthreads();
-        for (int step = 0; step < JP - 1; ++step) {
+        // xrot (cached-diagonal visits of single-matrix launches): only the 16 x 16 pairs that join a column of block I
+        // with a column of block J -- 16 bipartite steps instead of the 31 of the full tournament.  Pairs inside a block
+        // are met in every one of the block's 63 visits of a sweep anyway; they keep being rotated in round 0 (full Gram)
+        // and in the polishing sweeps.  The eigensolve is the critical path of a single-matrix round (39 of 68 us).
+        const int nsteps = xrot ? JB : JP - 1;
+        for (int step = 0; step < nsteps; ++step) {
             if (tid < JB) {
                 int p, q;
-                if (tid == 0) { p = JP - 1; q = step; }
+                if (xrot) { p = tid; q = JB + ((tid + step) & (JB - 1)); }
+                else if (tid == 0) { p = JP - 1; q = step; }
                 else { p = (step + tid) % (JP - 1); q = (step - tid + (JP - 1)) % (JP - 1); }
                 if (p > q) { int tt = p; p = q; q = tt; }
                 const double alpha = G[p * JPITCH + p].x, beta = G[q * JPITCH + q].x;
@@ -674,7 +680,7 @@ template <bool FULL, int MINB>
 __global__ void __launch_bounds__(FLOW_THREADS, MINB)
 jacobi_flow_kernel(const SvdProblem* __restrict__ probs, const uint2* __restrict__ tasks, int ntasks, int* __restrict__ counter,
                    double tol, int* __restrict__ rotated, const double* __restrict__ fro2, int inner_sweeps, int* __restrict__ stat,
-                   int stamp_base, int* __restrict__ nactive, int* __restrict__ errflag) {
+                   int stamp_base, int* __restrict__ nactive, int* __restrict__ errflag, int xrot) {
     typedef FlowCfg<MINB> Cfg;
     extern __shared__ __align__(16) unsigned char flow_smem[];
     double2* const arena = reinterpret_cast<double2*>(flow_smem);
@@ -909,10 +915,12 @@ jacobi_flow_kernel(const SvdProblem* __restrict__ probs, const uint2* __restrict
         for (int sweep = 0; sweep < inner_sweeps; ++sweep) {
             if (tid == 0) s_sweep_any = 0;
             __syncthreads();
-            for (int step = 0; step < JP - 1; ++step) {
+            const int nsteps = (!FULL && xrot) ? JB : JP - 1;   // cached-diagonal visits: cross pairs only (see jacobi_eig_kernel)
+            for (int step = 0; step < nsteps; ++step) {
                 if (tid < JB) {
                     int p, q;
-                    if (tid == 0) { p = JP - 1; q = step; }
+                    if (!FULL && xrot) { p = tid; q = JB + ((tid + step) & (JB - 1)); }
+                    else if (tid == 0) { p = JP - 1; q = step; }
                     else { p = (step + tid) % (JP - 1); q = (step - tid + (JP - 1)) % (JP - 1); }
                     if (p > q) { int tt = p; p = q; q = tt; }
                     const double alpha = G[p * JPITCH + p].x, beta = G[q * JPITCH + q].x;
@@ -1435,6 +1443,8 @@ struct SvdGroup {
     int max_nb = 2, maxpairs = 1, maxm = 1, maxn = 1;
     bool any_v = false;
     int S = 1, SU = 1;
+    int S_tail = 1, SU_tail = 1;   // row splits of the tail sweeps of a dataflow batch (few live pairs: split as for one matrix)
+    int tail_sweeps = 0;
     size_t offG = 0, offW = 0, offF = 0;
     bool active = true;
     int sweeps = 0;
@@ -1569,8 +1579,10 @@ int svd_batched_device(int batch, const SvdJob* jobs_in, double er, int64_t maxd
         grp.SU = (int)std::max<long>(1, std::min<long>((target * (256 / JTHREADS) + units - 1) / units, ugroups / (2 * (JTHREADS / 32))));
         if (const char* e = getenv("QTN_JACOBI_S")) grp.S = std::max(1, atoi(e));
         if (const char* e = getenv("QTN_JACOBI_SU")) grp.SU = std::max(1, atoi(e));
+        grp.S_tail = (int)std::max<long>(grp.S, std::min<long>((target + grp.maxpairs - 1) / grp.maxpairs, ggroups / 8));
+        grp.SU_tail = (int)std::max<long>(grp.SU, std::min<long>((target * (256 / JTHREADS) + grp.maxpairs - 1) / grp.maxpairs, ugroups / (2 * (JTHREADS / 32))));
         const size_t nb_ = (size_t)(grp.b1 - grp.b0);
-        grp.offG = al(nb_ * grp.maxpairs * grp.S * GP_ELEMS * 16);   // partial Grams [problem][pair][S][640]
+        grp.offG = al(nb_ * grp.maxpairs * std::max(grp.S, flow ? grp.S_tail : 1) * GP_ELEMS * 16);   // partial Grams [problem][pair][S][640]
         grp.offW = al(nb_ * grp.maxpairs * JP * JP * 16);            // rotations W   [problem][pair][32*32]
         grp.offF = al(nb_ * grp.maxpairs * 4);                       // apply flags   [problem][pair]
     }
@@ -1665,6 +1677,15 @@ int svd_batched_device(int batch, const SvdJob* jobs_in, double er, int64_t maxd
     const bool eig_priority = [] { const char* e = getenv("QTN_JACOBI_EIGPRIO"); return !(e && atoi(e) == 0); }();  // A/B switch
     const bool use_pdl = [] { const char* e = getenv("QTN_JACOBI_PDL"); return !(e && atoi(e) == 0); }();  // A/B switch
     const bool use_cross = [] { const char* e = getenv("QTN_JACOBI_CROSS"); return !(e && atoi(e) == 0); }();  // A/B switch
+    // cross-only rotations in the cached-diagonal visits (QTN_JACOBI_XROT=0 / QTN_JACOBI_XROT_FLOW=0 disable them).
+    // Single-matrix launches: 1536 x 1024 66.3 -> 56.2 ms (15 -> 16 sweeps, 4.42 -> 3.51 ms per sweep), cfg 5 0.383 -> 0.433
+    // applies/s.  Dataflow kernel: cfg 4 at chi = 512 2.127 -> 2.208 layers/s (22 -> 21 sweeps of the late layers).
+    const bool xrot_single = [] { const char* e = getenv("QTN_JACOBI_XROT"); return !(e && atoi(e) == 0); }();
+    const bool xrot_flow = [] { const char* e = getenv("QTN_JACOBI_XROT_FLOW"); return !(e && atoi(e) == 0); }();
+    // QTN_JACOBI_TAIL=d (A/B switch, default off): sweeps of a dataflow batch that follow one with fewer than 1/d of
+    // the pairs rotating run on the three-kernel path with single-matrix row splits.  Measured +1 % on cfg 4 (d = 16:
+    // 2.222 -> 2.247 layers/s): the tail sweeps of the task-queue kernel are cheap already.
+    const long tail_div = [] { const char* e = getenv("QTN_JACOBI_TAIL"); return e ? atol(e) : 0L; }();
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     if (dstat) { cudaEventCreate(&ev0); cudaEventCreate(&ev1); cudaEventRecord(ev0, st); }
     // the sub-batch streams start after the set-up work on the library stream
@@ -1707,7 +1728,12 @@ int svd_batched_device(int batch, const SvdJob* jobs_in, double er, int64_t maxd
             max_rounds = std::max(max_rounds, grp.max_nb - 1);
         }
         int* st_ptr = dstat ? dstat + 2 * std::min(sweeps, 63) : (int*)nullptr;
-        if (flow) {
+        // Tail of a dataflow batch: once few pairs still rotate, a sweep of the task-queue kernel is bound by the serial
+        // chain of one straggler matrix (63 rounds x one CTA per pair: 7-11 ms whatever the number of live pairs), while
+        // three row-split kernels per round walk the same chain in ~4 ms (converged pairs and matrices exit at once).
+        const bool tail = flow && tail_div > 0 && groups[0].prev_active >= 0 && groups[0].prev_active * tail_div < groups[0].pairs_per_sweep;
+        if (tail) ++groups[0].tail_sweeps;
+        if (flow && !tail) {
             // one task-queue kernel per sweep (two when round 0 computes full Grams and the rest take cached diagonals)
             const SvdGroup& grp = groups[0];
             cudaStream_t fs = g_sub[0];
@@ -1721,7 +1747,7 @@ int svd_batched_device(int batch, const SvdJob* jobs_in, double er, int64_t maxd
                 const int ctas = std::min(t1 - t0, 148 * per_sm);
 #define QTN_FLOW_LAUNCH(F, B)                                                                                                   \
     jacobi_flow_kernel<F, B><<<ctas, FLOW_THREADS, FlowCfg<B>::SMEM, fs>>>(dp, dtasks + t0, t1 - t0, counter, tol, drot,          \
-                                                                           (const double*)dfro, inner, st_ptr, stamp + 1, dact, dflow_err)
+                                                                           (const double*)dfro, inner, st_ptr, stamp + 1, dact, dflow_err, (int)xrot_flow)
                 if (full) { if (per_sm == 3) QTN_FLOW_LAUNCH(true, 3); else QTN_FLOW_LAUNCH(true, 2); }
                 else if (per_sm == 4) QTN_FLOW_LAUNCH(false, 4);
                 else if (per_sm == 3) QTN_FLOW_LAUNCH(false, 3);
@@ -1745,12 +1771,13 @@ int svd_batched_device(int batch, const SvdJob* jobs_in, double er, int64_t maxd
                 // sub-batch chains its three kernels of a round by programmatic dependent launch instead)
                 const bool eprio = eig_priority && ngroups > 1;
                 const bool pdl = use_pdl && !eprio;
-                const dim3 gg((unsigned)(grp.maxpairs * grp.S), nb_);
+                const int S_cur = tail ? grp.S_tail : grp.S, SU_cur = tail ? grp.SU_tail : grp.SU;
+                const dim3 gg((unsigned)(grp.maxpairs * S_cur), nb_);
                 if (cross)
-                    CUDA_TRY(launch_k(jacobi_gram_cross_kernel, gg, dim3(GRAM_THREADS), g_sub[g], pdl, dp + grp.b0, round, drot + grp.b0, grp.S, grp.maxpairs,
+                    CUDA_TRY(launch_k(jacobi_gram_cross_kernel, gg, dim3(GRAM_THREADS), g_sub[g], pdl, dp + grp.b0, round, drot + grp.b0, S_cur, grp.maxpairs,
                                       (double2*)(base + grp.offG)));
                 else
-                    CUDA_TRY(launch_k(jacobi_gram_kernel, gg, dim3(GRAM_THREADS), g_sub[g], pdl, dp + grp.b0, round, drot + grp.b0, grp.S, grp.maxpairs,
+                    CUDA_TRY(launch_k(jacobi_gram_kernel, gg, dim3(GRAM_THREADS), g_sub[g], pdl, dp + grp.b0, round, drot + grp.b0, S_cur, grp.maxpairs,
                                       (double2*)(base + grp.offG)));
                 cudaStream_t se = eprio ? g_subE[g] : g_sub[g];
                 if (eprio) { CUDA_TRY(cudaEventRecord(g_evG[g], g_sub[g])); CUDA_TRY(cudaStreamWaitEvent(se, g_evG[g], 0)); }
@@ -1758,20 +1785,20 @@ int svd_batched_device(int batch, const SvdJob* jobs_in, double er, int64_t maxd
                 {
                     static int et_env = -1;
                     if (et_env < 0) { const char* e = getenv("QTN_JACOBI_ET"); et_env = e ? atoi(e) : 0; }
-                    const int et = et_env ? et_env : ((long)grp.maxpairs * nb_ <= 148 ? 256 : 128);
+                    const int et = et_env ? et_env : (((long)grp.maxpairs * nb_ <= 148 || tail) ? 256 : 128);
                     const dim3 eg((unsigned)grp.maxpairs, nb_);
                     if (et == 256)
                         CUDA_TRY(launch_k(jacobi_eig_kernel<256>, eg, dim3(256), se, pdl, dp + grp.b0, round, tol, drot + grp.b0, (const double*)dfro + grp.b0,
-                                          inner, st_ptr, stamp, grp.S, grp.maxpairs, (const double2*)(base + grp.offG), (double2*)(base + grp.offW),
-                                          (int*)(base + grp.offF), cross, dact + grp.b0));
+                                          inner, st_ptr, stamp, S_cur, grp.maxpairs, (const double2*)(base + grp.offG), (double2*)(base + grp.offW),
+                                          (int*)(base + grp.offF), cross, dact + grp.b0, (int)(cross && xrot_single && ngroups == 1 && nb_ == 1)));
                     else
                         CUDA_TRY(launch_k(jacobi_eig_kernel<128>, eg, dim3(128), se, pdl, dp + grp.b0, round, tol, drot + grp.b0, (const double*)dfro + grp.b0,
-                                          inner, st_ptr, stamp, grp.S, grp.maxpairs, (const double2*)(base + grp.offG), (double2*)(base + grp.offW),
-                                          (int*)(base + grp.offF), cross, dact + grp.b0));
+                                          inner, st_ptr, stamp, S_cur, grp.maxpairs, (const double2*)(base + grp.offG), (double2*)(base + grp.offW),
+                                          (int*)(base + grp.offF), cross, dact + grp.b0, (int)(cross && xrot_single && ngroups == 1 && nb_ == 1)));
                 }
                 if (eprio) { CUDA_TRY(cudaEventRecord(g_evE[g], se)); CUDA_TRY(cudaStreamWaitEvent(g_sub[g], g_evE[g], 0)); }
-                CUDA_TRY(launch_k(jacobi_update_kernel, dim3((unsigned)(grp.maxpairs * grp.SU), nb_), dim3(JTHREADS), g_sub[g], pdl, dp + grp.b0, round,
-                                  drot + grp.b0, grp.SU, grp.maxpairs, (const double2*)(base + grp.offW), (const int*)(base + grp.offF)));
+                CUDA_TRY(launch_k(jacobi_update_kernel, dim3((unsigned)(grp.maxpairs * SU_cur), nb_), dim3(JTHREADS), g_sub[g], pdl, dp + grp.b0, round,
+                                  drot + grp.b0, SU_cur, grp.maxpairs, (const double2*)(base + grp.offW), (const int*)(base + grp.offF)));
                 count_launch(3);
             }
         }
@@ -1826,8 +1853,8 @@ int svd_batched_device(int batch, const SvdJob* jobs_in, double er, int64_t maxd
         fprintf(stderr, "[jacobi] batch=%d maxm=%d maxn=%d sweeps=%d %.3f ms (%.3f ms/sweep); groups:", batch, maxm, maxn, sweeps, ms,
                 ms / std::max(sweeps, 1));
         for (const auto& grp : groups)
-            fprintf(stderr, " [%d..%d) n<=%d m<=%d v=%d S=%d SU=%d sweeps=%d (%d cached-Gram);", grp.b0, grp.b1, grp.maxn, grp.maxm, (int)grp.any_v, grp.S,
-                    grp.SU, grp.sweeps, grp.cross_sweeps);
+            fprintf(stderr, " [%d..%d) n<=%d m<=%d v=%d S=%d SU=%d sweeps=%d (%d cached-Gram, %d tail);", grp.b0, grp.b1, grp.maxn, grp.maxm, (int)grp.any_v, grp.S,
+                    grp.SU, grp.sweeps, grp.cross_sweeps, grp.tail_sweeps);
         fprintf(stderr, " (idle,active) pairs per sweep:");
         for (int i = 0; i < sweeps && i < 64; ++i) fprintf(stderr, " (%d,%d)", hs[2 * i], hs[2 * i + 1]);
         fprintf(stderr, "\n");

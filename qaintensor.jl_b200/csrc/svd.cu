@@ -1678,8 +1678,8 @@ int svd_batched_device(int batch, const SvdJob* jobs_in, double er, int64_t maxd
     const bool use_pdl = [] { const char* e = getenv("QTN_JACOBI_PDL"); return !(e && atoi(e) == 0); }();  // A/B switch
     const bool use_cross = [] { const char* e = getenv("QTN_JACOBI_CROSS"); return !(e && atoi(e) == 0); }();  // A/B switch
     // cross-only rotations in the cached-diagonal visits (QTN_JACOBI_XROT=0 / QTN_JACOBI_XROT_FLOW=0 disable them).
-    // Single-matrix launches: 1536 x 1024 66.3 -> 56.2 ms (15 -> 16 sweeps, 4.42 -> 3.51 ms per sweep), cfg 5 0.383 -> 0.433
-    // applies/s.  Dataflow kernel: cfg 4 at chi = 512 2.127 -> 2.208 layers/s (22 -> 21 sweeps of the late layers).
+    // Three-kernel path: 1536 x 1024 66.3 -> 56.2 ms (15 -> 16 sweeps, 4.42 -> 3.51 ms per sweep), cfg 5 0.383 -> 0.433
+    // applies/s; small batches 4 x 512^2 26.1 -> 21.6 ms, 8 x 700 x 520 44.2 -> 38.5 ms, 12 x 256^2 11.3 -> 9.4 ms.  Dataflow kernel: cfg 4 at chi = 512 2.127 -> 2.208 layers/s (22 -> 21 sweeps of the late layers).
     const bool xrot_single = [] { const char* e = getenv("QTN_JACOBI_XROT"); return !(e && atoi(e) == 0); }();
     const bool xrot_flow = [] { const char* e = getenv("QTN_JACOBI_XROT_FLOW"); return !(e && atoi(e) == 0); }();
     // QTN_JACOBI_TAIL=d (A/B switch, default off): sweeps of a dataflow batch that follow one with fewer than 1/d of
@@ -1790,11 +1790,11 @@ int svd_batched_device(int batch, const SvdJob* jobs_in, double er, int64_t maxd
                     if (et == 256)
                         CUDA_TRY(launch_k(jacobi_eig_kernel<256>, eg, dim3(256), se, pdl, dp + grp.b0, round, tol, drot + grp.b0, (const double*)dfro + grp.b0,
                                           inner, st_ptr, stamp, S_cur, grp.maxpairs, (const double2*)(base + grp.offG), (double2*)(base + grp.offW),
-                                          (int*)(base + grp.offF), cross, dact + grp.b0, (int)(cross && xrot_single && ngroups == 1 && nb_ == 1)));
+                                          (int*)(base + grp.offF), cross, dact + grp.b0, (int)(cross && xrot_single)));
                     else
                         CUDA_TRY(launch_k(jacobi_eig_kernel<128>, eg, dim3(128), se, pdl, dp + grp.b0, round, tol, drot + grp.b0, (const double*)dfro + grp.b0,
                                           inner, st_ptr, stamp, S_cur, grp.maxpairs, (const double2*)(base + grp.offG), (double2*)(base + grp.offW),
-                                          (int*)(base + grp.offF), cross, dact + grp.b0, (int)(cross && xrot_single && ngroups == 1 && nb_ == 1)));
+                                          (int*)(base + grp.offF), cross, dact + grp.b0, (int)(cross && xrot_single)));
                 }
                 if (eprio) { CUDA_TRY(cudaEventRecord(g_evE[g], se)); CUDA_TRY(cudaStreamWaitEvent(g_sub[g], g_evE[g], 0)); }
                 CUDA_TRY(launch_k(jacobi_update_kernel, dim3((unsigned)(grp.maxpairs * SU_cur), nb_), dim3(JTHREADS), g_sub[g], pdl, dp + grp.b0, round,

@@ -185,7 +185,12 @@ int qtn_plan_execute_host(qtn_plan* plan, const void* const* host_data, int64_t 
 /* Per-step device timing of one slice (CUDA events, ms[nsteps]); diagnostics.   */
 int qtn_plan_time_steps(qtn_plan* plan, int64_t slice_id, float* ms);
 
-/* One-shot `ncon`: plan + upload + execute + download (src/contract.jl:257, 263). */
+/* One-shot `ncon`: plan + upload + execute + download (src/contract.jl:257, 263).
+ * The library keeps the plans of the last four network structures it was called with
+ * (exact match of dtype, ranks, dims, labels and order; <= 256 MB of device memory each):
+ * calling it again on the same structure with new tensor data skips the planner and, from
+ * the second repeat on, replays the plan's CUDA graph.  QTN_PLAN_CACHE=0 in the environment
+ * disables the cache; qtn_shutdown releases it.                                            */
 int qtn_contract(int32_t nt, const void* const* host_data, const int32_t* ranks,
                  const int64_t* const* dims, const int32_t* const* labels,
                  const int32_t* order, int32_t norder, int32_t dtype, void* host_out,

@@ -194,6 +194,11 @@ int launch_gemm(GemmArgs& g, int variant, int split_k, cudaStream_t st) {
         if (stream_on < 0) { const char* e = getenv("QTN_STREAM"); stream_on = e ? atoi(e) : 1; }
         if (stream_on && variant != 2 && split_k == 1 && g.M >= 16384 && g.K <= 32 && g.N <= 128) {
             // HBM-bound shapes: small tiles, 16 warps; tensor-bound shapes (N > 16): 8 warps with wide column blocks
+            // K <= 4, N <= 8 (a gate applied to a large tensor: 94 % of the steps of the reference's default order on its
+            // QFT-20 benchmark network): a 4-deep stage halves the copies and the DMMAs per tile (QTN_STREAM_K4=0: A/B)
+            static int k4_on = -1;
+            if (k4_on < 0) { const char* e = getenv("QTN_STREAM_K4"); k4_on = e ? atoi(e) : 1; }
+            if (g.N <= 8 && g.K <= 4 && k4_on) return launch_stream_t<4, 1, 4, 16>(g, st);
             if (g.N <= 8) return g.K <= 8 ? launch_stream_t<4, 1, 8, 16>(g, st) : launch_stream_k<2, 1, 16>(g, st);
             if (g.N <= 16) return launch_stream_k<2, 2, 16>(g, st);
             return launch_stream_k<2, 4, 8>(g, st);   // column blocks of 32

@@ -355,7 +355,7 @@ zgemm_stream_kernel(const __grid_constant__ GemmArgs g, int S) {
     constexpr int KPI = 32 / TR;   // k rows per load instruction (rows fastest)
     const int lrow = lane % TR, lksub = lane / TR;
     const unsigned ldst = (unsigned)((lksub * PA + lrow) * 16);
-    constexpr int KSH = KP >= 32 ? 5 : (KP >= 16 ? 4 : 3);
+    constexpr int KSH = KP >= 32 ? 5 : (KP >= 16 ? 4 : (KP >= 8 ? 3 : 2));
     const int kk = lane & (KP - 1), rsub = lane >> KSH;   // (k fastest; KP = 32 -> one row per instruction)
     constexpr int RPER = 32 >> KSH;
     auto issue = [&](i64 tile, int stage) {
@@ -437,12 +437,16 @@ zgemm_stream_kernel(const __grid_constant__ GemmArgs g, int S) {
                     for (int j = 0; j < NI; ++j) dmma884(ci[i][j][0], ci[i][j][1], af[i].y, bf[j].x);
             };
             load_frags(af0, bf0, 0);
-#pragma unroll
-            for (int k4 = 0; k4 < NK4; k4 += 2) {   // the LDS.128 of the next k4 fly under the DMMAs of the current one
-                load_frags(af1, bf1, k4 + 1);
+            if constexpr (NK4 == 1) {   // K <= 4 (a two-qubit gate on a big tensor): one k4 step, nothing to prefetch
                 mma(af0, bf0);
-                if (k4 + 2 < NK4) load_frags(af0, bf0, k4 + 2);
-                mma(af1, bf1);
+            } else {
+#pragma unroll
+                for (int k4 = 0; k4 < NK4; k4 += 2) {   // the LDS.128 of the next k4 fly under the DMMAs of the current one
+                    load_frags(af1, bf1, k4 + 1);
+                    mma(af0, bf0);
+                    if (k4 + 2 < NK4) load_frags(af0, bf0, k4 + 2);
+                    mma(af1, bf1);
+                }
             }
             if (g.conj_a) {
 #pragma unroll

@@ -385,6 +385,9 @@ zgemm_stream_kernel(const __grid_constant__ GemmArgs g, int S) {
         cp_async_commit();
     }
     const bool fast_cols = g.c_dense && g.mode == 0 && N == ncb * CB;
+    // N = 4 in a single 8-column block (a two-qubit gate: most steps of a default-order walk): lanes t < 2 hold the four
+    // real columns and store them through the same predicate-free path
+    const bool half_cols = NI == 1 && g.c_dense && g.mode == 0 && N == 4;
     int stage = 0;
     for (i64 tile = w0; tile < ntiles; tile += wstride) {
         // S - 2 groups may stay pending: the oldest (this tile's) has landed for this thread; __syncwarp makes the
@@ -399,7 +402,7 @@ zgemm_stream_kernel(const __grid_constant__ GemmArgs g, int S) {
         }
         const double2* a_s = sA + ((size_t)warp * S + stage) * (KP * PA) + gq;
         const i64 rbase = tile * TR + gq;
-        const bool fast = fast_cols && (tile + 1) * TR <= M;
+        const bool fast = (fast_cols || half_cols) && (tile + 1) * TR <= M;
         for (int cb = 0; cb < ncb; ++cb) {
             const double2* b_s = sB + cb * CB + gq;
             double cr[MI][NI][2], ci[MI][NI][2];
@@ -456,6 +459,7 @@ zgemm_stream_kernel(const __grid_constant__ GemmArgs g, int S) {
             }
             // epilogue: straight from the accumulators (8 consecutive rows per column = one full 128-byte line per store)
             if (fast) {
+                if (half_cols && t >= 2) continue;   // ncb == 1: nothing else to do for this tile
                 double2* cp = Cbase + rbase + (i64)(cb * CB + 2 * t) * M;
 #pragma unroll
                 for (int j = 0; j < NI; ++j) {

@@ -31,6 +31,14 @@ def run():
                 if M <= 20007:
                     ak = np.asfortranarray(a.T)   # (K, M) column-major: k is the contiguous direction
                     chk(q.ncon([ak, b], [[1, -1], [1, -2]]), a @ b, ("kmajor", M, N, K))
+    # dense intermediates (c_dense, plain store): the predicate-free epilogues, incl. the N = 4 half-block of a two-qubit gate
+    for M in (16384, 32768 + 5):
+        for N in (2, 3, 4, 8, 16):
+            for K in (2, 4, 8):
+                a = np.asfortranarray(rng.standard_normal((M, K)) + 1j * rng.standard_normal((M, K)))
+                b = rng.standard_normal((K, N)) + 1j * rng.standard_normal((K, N))
+                c = rng.standard_normal((N, 3)) + 1j * rng.standard_normal((N, 3))
+                chk(q.ncon([a, b, c], [[-1, 1], [1, 2], [2, -2]]), a @ b @ c, ("intermediate", M, N, K))
     # gathered operand: the contracted legs sit in the middle of a rank-5 tensor (runs of 4 contiguous rows)
     for (k1, k2, N) in ((2, 2, 4), (4, 4, 16), (2, 8, 8), (4, 8, 32)):
         t = np.asfortranarray(rng.standard_normal((4, k1, 64, k2, 128)) + 1j * rng.standard_normal((4, k1, 64, k2, 128)))

@@ -15,22 +15,27 @@ from ._lib import NetworkArgs, arr_i32, arr_i64, as_c128, check, data_ptrs, lib
 def contract_rep(net, optimize=False):
     """Label assignment of src/contract.jl:8-32 / :39-60: +k for contraction k,
     -(i + ncontractions) for open leg i."""
-    indexlist = [[0] * t.ndims() for t in net.tensors]
+    shapes = [t.data.shape for t in net.tensors]     # one attribute walk per tensor (this runs on every contract(net))
+    indexlist = [[0] * len(sh) for sh in shapes]
     leg_costs = {}
     for k, s in enumerate(net.contractions, 1):
         for (t, l) in s.idx:
-            if not 1 <= l <= net.tensors[t - 1].ndims():
+            sh = shapes[t - 1]
+            if not 1 <= l <= len(sh):
                 raise AssertionError("leg %d out of range for tensor %d" % (l, t))
             indexlist[t - 1][l - 1] = k
-            leg_costs[k] = net.tensors[t - 1].size()[l - 1]
+            if optimize:
+                leg_costs[k] = sh[l - 1]
     nc = len(net.contractions)
     for i, (t, l) in enumerate(net.openidx, 1):
         if indexlist[t - 1][l - 1] != 0:
             raise AssertionError("open leg participates in a contraction")
         indexlist[t - 1][l - 1] = -i - nc
-        leg_costs[i + nc] = net.tensors[t - 1].size()[l - 1]
-    if any(x == 0 for idx in indexlist for x in idx):
-        raise AssertionError("tensor leg without contraction or open index")
+        if optimize:
+            leg_costs[i + nc] = shapes[t - 1][l - 1]
+    for idx in indexlist:
+        if 0 in idx:
+            raise AssertionError("tensor leg without contraction or open index")
     return (leg_costs, indexlist) if optimize else indexlist
 
 
@@ -212,7 +217,11 @@ def ncon(arrays, indexlist, order=None, precision="c128"):
     if nopen > 64:
         raise ValueError("more than 64 open legs")
     ord_arr = arr_i32(order) if order is not None else None
-    check(lib.qtn_contract(args.nt, data_ptrs(arrs), args.ranks, args.dims, args.labels, ord_arr,
+    if len(arrs) > 32 and sum(a.size for a in arrs) <= (1 << 20):
+        keep, ptrs = _lib.packed_ptrs(arrs)   # many small tensors (a circuit's gates)
+    else:
+        ptrs = data_ptrs(arrs)
+    check(lib.qtn_contract(args.nt, ptrs, args.ranks, args.dims, args.labels, ord_arr,
                            len(order) if order is not None else 0, code, out.ctypes.data_as(C.c_void_p),
                            C.byref(rank), dims))
     shape = tuple(int(dims[i]) for i in range(rank.value))

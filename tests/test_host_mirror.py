@@ -137,3 +137,19 @@ def test_mpo_argument_errors(q):  # test/test_mpo.jl:124-140 (no SVD is reached)
     nets_equal(out, oout)
     with pytest.raises(ValueError, match="Wires not sorted"):
         q.extend_MPO(one, (1, 3))
+
+
+def test_packed_pointer_table_round_trip(q):
+    """_lib.packed_ptrs (the marshalling of `contract(net)` for many small tensors): every table entry must point at
+    the column-major image of its tensor."""
+    import ctypes as C
+    from qaintensor_b200 import _lib
+    rng = np.random.default_rng(3)
+    shapes = [(2,), (2, 2), (2, 2, 2), (2, 2, 2, 2), (3, 1, 2), (1,), (4, 4)] * 6
+    for dtype in (np.complex128, np.complex64):
+        arrs = [np.asfortranarray((rng.standard_normal(s) + 1j * rng.standard_normal(s)).astype(dtype)) for s in shapes]
+        keep, ptrs = _lib.packed_ptrs(arrs)
+        for i, a in enumerate(arrs):
+            raw = (C.c_char * a.nbytes).from_address(ptrs[i])
+            back = np.frombuffer(raw, dtype=dtype).reshape(a.shape, order="F")
+            assert np.array_equal(back, a)
